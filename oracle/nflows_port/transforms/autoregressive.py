@@ -1,0 +1,169 @@
+"""Autoregressive transforms (restating nflows.transforms.autoregressive; A.6)."""
+import numpy as np
+import torch
+from torch.nn import functional as F
+
+from ..utils import torchutils
+from . import made as made_module
+from .base import Transform
+from .splines import rational_quadratic
+from .splines.rational_quadratic import (
+    rational_quadratic_spline, unconstrained_rational_quadratic_spline,
+)
+
+# nflows 0.14 (PyPI, Nov 2020) bounds the MAF scale with a shifted sigmoid; later
+# upstream commits switched to softplus.  sbi pins nflows==0.14, so "sigmoid" is the
+# restated default; the alternative is kept selectable so both can be checked
+# (SURVEY.md Appendix A.6 -- recollection, flagged "verify").
+MAF_SCALE_FN = "sigmoid"
+
+
+class AutoregressiveTransform(Transform):
+    """Forward is one pass; inverse needs D sequential passes."""
+
+    def __init__(self, autoregressive_net):
+        super().__init__()
+        self.autoregressive_net = autoregressive_net
+
+    def forward(self, inputs, context=None):
+        autoregressive_params = self.autoregressive_net(inputs, context)
+        return self._elementwise_forward(inputs, autoregressive_params)
+
+    def inverse(self, inputs, context=None):
+        num_inputs = int(np.prod(inputs.shape[1:]))
+        outputs = torch.zeros_like(inputs)
+        logabsdet = None
+        for _ in range(num_inputs):
+            autoregressive_params = self.autoregressive_net(outputs, context)
+            outputs, logabsdet = self._elementwise_inverse(inputs, autoregressive_params)
+        return outputs, logabsdet
+
+    def _output_dim_multiplier(self):
+        raise NotImplementedError()
+
+    def _elementwise_forward(self, inputs, autoregressive_params):
+        raise NotImplementedError()
+
+    def _elementwise_inverse(self, inputs, autoregressive_params):
+        raise NotImplementedError()
+
+
+class MaskedAffineAutoregressiveTransform(AutoregressiveTransform):
+    def __init__(self, features, hidden_features, context_features=None, num_blocks=2,
+                 use_residual_blocks=True, random_mask=False, activation=F.relu,
+                 dropout_probability=0.0, use_batch_norm=False, scale_fn=None):
+        self.features = features
+        made = made_module.MADE(
+            features=features, hidden_features=hidden_features,
+            context_features=context_features, num_blocks=num_blocks,
+            output_multiplier=self._output_dim_multiplier(),
+            use_residual_blocks=use_residual_blocks, random_mask=random_mask,
+            activation=activation, dropout_probability=dropout_probability,
+            use_batch_norm=use_batch_norm,
+        )
+        self._epsilon = 1e-3
+        self._scale_fn = scale_fn or MAF_SCALE_FN
+        super().__init__(made)
+
+    def _output_dim_multiplier(self):
+        return 2
+
+    def _scale(self, unconstrained_scale):
+        if self._scale_fn == "sigmoid":
+            return torch.sigmoid(unconstrained_scale + 2.0) + self._epsilon
+        return F.softplus(unconstrained_scale) + self._epsilon
+
+    def _elementwise_forward(self, inputs, autoregressive_params):
+        unconstrained_scale, shift = self._unconstrained_scale_and_shift(autoregressive_params)
+        scale = self._scale(unconstrained_scale)
+        log_scale = torch.log(scale)
+        outputs = scale * inputs + shift
+        logabsdet = torchutils.sum_except_batch(log_scale, num_batch_dims=1)
+        return outputs, logabsdet
+
+    def _elementwise_inverse(self, inputs, autoregressive_params):
+        unconstrained_scale, shift = self._unconstrained_scale_and_shift(autoregressive_params)
+        scale = self._scale(unconstrained_scale)
+        log_scale = torch.log(scale)
+        outputs = (inputs - shift) / scale
+        logabsdet = -torchutils.sum_except_batch(log_scale, num_batch_dims=1)
+        return outputs, logabsdet
+
+    def _unconstrained_scale_and_shift(self, autoregressive_params):
+        autoregressive_params = autoregressive_params.view(
+            -1, self.features, self._output_dim_multiplier()
+        )
+        return autoregressive_params[..., 0], autoregressive_params[..., 1]
+
+
+class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTransform):
+    def __init__(self, features, hidden_features, context_features=None, num_bins=10,
+                 tails=None, tail_bound=1.0, num_blocks=2, use_residual_blocks=True,
+                 random_mask=False, activation=F.relu, dropout_probability=0.0,
+                 use_batch_norm=False,
+                 min_bin_width=rational_quadratic.DEFAULT_MIN_BIN_WIDTH,
+                 min_bin_height=rational_quadratic.DEFAULT_MIN_BIN_HEIGHT,
+                 min_derivative=rational_quadratic.DEFAULT_MIN_DERIVATIVE):
+        self.num_bins = num_bins
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+        self.min_derivative = min_derivative
+        self.tails = tails
+        self.tail_bound = tail_bound
+        autoregressive_net = made_module.MADE(
+            features=features, hidden_features=hidden_features,
+            context_features=context_features, num_blocks=num_blocks,
+            output_multiplier=self._output_dim_multiplier(),
+            use_residual_blocks=use_residual_blocks, random_mask=random_mask,
+            activation=activation, dropout_probability=dropout_probability,
+            use_batch_norm=use_batch_norm,
+        )
+        super().__init__(autoregressive_net)
+
+    def _output_dim_multiplier(self):
+        if self.tails == "linear":
+            return self.num_bins * 3 - 1
+        elif self.tails is None:
+            return self.num_bins * 3 + 1
+        raise ValueError
+
+    def _elementwise(self, inputs, autoregressive_params, inverse=False):
+        batch_size, features = inputs.shape[0], inputs.shape[1]
+        transform_params = autoregressive_params.view(
+            batch_size, features, self._output_dim_multiplier()
+        )
+        unnormalized_widths = transform_params[..., : self.num_bins]
+        unnormalized_heights = transform_params[..., self.num_bins : 2 * self.num_bins]
+        unnormalized_derivatives = transform_params[..., 2 * self.num_bins :]
+
+        if hasattr(self.autoregressive_net, "hidden_features"):
+            unnormalized_widths = unnormalized_widths / np.sqrt(self.autoregressive_net.hidden_features)
+            unnormalized_heights = unnormalized_heights / np.sqrt(self.autoregressive_net.hidden_features)
+
+        if self.tails is None:
+            spline_fn = rational_quadratic_spline
+            spline_kwargs = {}
+        elif self.tails == "linear":
+            spline_fn = unconstrained_rational_quadratic_spline
+            spline_kwargs = {"tails": self.tails, "tail_bound": self.tail_bound}
+        else:
+            raise ValueError
+
+        outputs, logabsdet = spline_fn(
+            inputs=inputs,
+            unnormalized_widths=unnormalized_widths,
+            unnormalized_heights=unnormalized_heights,
+            unnormalized_derivatives=unnormalized_derivatives,
+            inverse=inverse,
+            min_bin_width=self.min_bin_width,
+            min_bin_height=self.min_bin_height,
+            min_derivative=self.min_derivative,
+            **spline_kwargs,
+        )
+        return outputs, torchutils.sum_except_batch(logabsdet)
+
+    def _elementwise_forward(self, inputs, autoregressive_params):
+        return self._elementwise(inputs, autoregressive_params)
+
+    def _elementwise_inverse(self, inputs, autoregressive_params):
+        return self._elementwise(inputs, autoregressive_params, inverse=True)
