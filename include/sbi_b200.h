@@ -1,0 +1,153 @@
+/* sbi_b200 -- C ABI of the B200-native hot path of sbi (density-estimator training and
+ * posterior evaluation).  Plain pointers and sizes only; no torch types.
+ *
+ * Every pointer named d_* is a DEVICE pointer (sm_100a), every h_* a HOST pointer.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * All functions return 0 on success, a negative SBI_E* code on argument errors, or a
+ * positive cudaError_t value if a CUDA call failed.  Nothing here synchronises unless the
+ * name ends in _host (those take host buffers and block until the result is on the host).
+ *
+ * Reference interface replaced (file:line under /root/reference):
+ *   sbi/neural_nets/estimators/nflows_flow.py:77-97   NFlowsFlow.log_prob   -> sbi_b200_nsf_logprob
+ *   sbi/neural_nets/estimators/nflows_flow.py:99-109  NFlowsFlow.loss + autograd backward
+ *                                                      (trainers/base.py:1171-1187)  -> sbi_b200_nsf_vjp
+ *   sbi/neural_nets/estimators/nflows_flow.py:111-128 NFlowsFlow.sample     -> sbi_b200_nsf_inverse
+ *   sbi/neural_nets/estimators/nflows_flow.py:42-75   inverse_transform     -> sbi_b200_nsf_logprob (z_out)
+ *   sbi/inference/trainers/base.py:1181-1187          clip_grad_norm_ + Adam.step -> sbi_b200_reduce_partials,
+ *                                                                                  sbi_b200_adam_clip_step
+ */
+#ifndef SBI_B200_H
+#define SBI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBI_B200_ABI_VERSION 1
+
+#define SBI_EINVAL (-1)   /* bad argument */
+#define SBI_ESMEM (-2)    /* model does not fit the shared-memory budget of one CTA */
+#define SBI_ENOGPU (-3)   /* no sm_100 device */
+
+/* per-layer descriptor table: SBI_NSF_LAYER_STRIDE ints per coupling layer */
+#define SBI_NSF_LAYER_STRIDE 64
+#define SBI_NSF_MAX_BLOCKS 8
+enum {
+  SBI_L_NID = 0,      /* number of identity (conditioner-input) features */
+  SBI_L_NTR = 1,      /* number of transformed features */
+  SBI_L_W0 = 2,       /* float offset: initial layer  [Hp][Cp+IDp], columns = [ctx | id] */
+  SBI_L_B0 = 3,
+  SBI_L_WF = 4,       /* final layer [n_tr*PR][Hp]; feature f owns rows f*PR .. f*PR+3K-2 */
+  SBI_L_BF = 5,
+  SBI_L_LU_LOWER = 6, /* nflows LULinear params, native shapes */
+  SBI_L_LU_UPPER = 7,
+  SBI_L_LU_DIAG = 8,
+  SBI_L_LU_BIAS = 9,
+  SBI_L_FEAT = 10,    /* offset into feat_tab: n_id identity features then n_tr transformed */
+  SBI_L_HAS_LU = 11,
+  SBI_L_BLK0 = 16     /* per residual block b, 6 ints at SBI_L_BLK0+6*b: W1,B1,W2,B2,WC,BC */
+};
+
+/* Neural spline flow (sbi `posterior_nn("nsf")` / `likelihood_nn("nsf")`,
+ * reference builder sbi/neural_nets/net_builders/flow.py:333-460). */
+typedef struct {
+  int32_t D, C, H, NB, KB, T;      /* input dim, context dim, hidden, res-blocks, bins, layers */
+  int32_t Dp, Cp, IDp, Hp, PR;     /* padded: round4(D), round4(C), round4(max n_id), round4(H), round4(3KB-1) */
+  int32_t TRmax;                   /* max transformed features over layers */
+  int32_t nf_chunk;                /* features per final-layer weight chunk */
+  int32_t rpc0, rpc1, rpc2;        /* rows per weight chunk: initial, hidden, hidden+context (GLU) */
+  int32_t wcap, nbuf;              /* weight ring: floats per slot, slots */
+  int32_t n_params;                /* floats in d_params */
+  float tail_bound, inv_sqrt_h, min_bw, min_bh, min_d, edge_raw;
+  float ld_zscore;                 /* sum_d log|scale_d| of the input z-score transform */
+  const float* d_params;           /* packed parameters (see sbi_b200/pack.py) */
+  const int32_t* d_layer_tab;      /* T * SBI_NSF_LAYER_STRIDE */
+  const int32_t* d_feat_tab;
+  const float* d_stats;            /* [shift(Dp) | scale(Dp) | ctx_mean(Cp) | ctx_std(Cp)] */
+} sbi_nsf_model;
+
+/* Optional outputs / inputs of the row kernels; any pointer may be NULL. */
+typedef struct {
+  const float* d_input;            /* (R, D) row-major, or the gather source when d_index != NULL */
+  const float* d_cond;             /* (R, C) row-major, (1, C) when cond_shared, or gather source */
+  const int64_t* d_index;          /* (R,) row indices into d_input/d_cond (device-resident data set) */
+  int64_t R;
+  int32_t cond_shared;             /* 1: one condition row for all R rows (posterior at x_o) */
+} sbi_rows;
+
+int sbi_b200_abi_version(void);
+int sbi_b200_device_ok(void);      /* 1 if device 0 is sm_100, else 0 */
+
+/* log q(input | cond) for R rows.  d_logp (R,) ; d_noise (R, D) optional (the base-space
+ * point z, i.e. NFlowsFlow.inverse_transform). */
+int sbi_b200_nsf_logprob(const sbi_nsf_model* m, const sbi_rows* rows, float* d_logp,
+                         float* d_noise, void* stream);
+
+/* Vector-Jacobian product of sum_r g_r * log q_r: forward + backward in one kernel.
+ *   d_gout (R,) upstream gradient per row, or NULL with g_const used for every row.
+ *   d_logp (R,) optional forward output.
+ *   d_gpart  (n_part, n_params) per-CTA partial parameter gradients (written, not
+ *            accumulated); n_part = sbi_b200_nsf_vjp_parts(R).
+ *   d_ginput (R, D), d_gcond (R, C) optional input / condition gradients.
+ *   d_loss_acc optional: [0] += sum_r -logp_r , [1] += #non-finite rows.              */
+int sbi_b200_nsf_vjp_parts(int64_t R);
+int sbi_b200_nsf_vjp(const sbi_nsf_model* m, const sbi_rows* rows, const float* d_gout,
+                     float g_const, float* d_logp, float* d_gpart, float* d_ginput,
+                     float* d_gcond, float* d_loss_acc, void* stream);
+
+/* x = flow^{-1}(noise | cond): sampling path.  d_noise (R, D) -> d_out (R, D);
+ * d_logabsdet (R,) optional = log|det d x / d noise|. */
+int sbi_b200_nsf_inverse(const sbi_nsf_model* m, const sbi_rows* rows, float* d_out,
+                         float* d_logabsdet, void* stream);
+
+/* grad[p] = sum_i gpart[i][p]  (i < n_part) */
+int sbi_b200_reduce_partials(const float* d_gpart, int n_part, int64_t n_params, float* d_grad,
+                             void* stream);
+
+/* clip_grad_norm_(max_norm) + Adam (torch defaults, no weight decay), in place.
+ *   d_state: [m (n) | v (n)] ; d_step: int32 device counter (incremented here);
+ *   grad_scale multiplies the gradient first (e.g. 1/world_size after an all-reduce);
+ *   d_mask optional (n,) uint8: 0 = frozen entry (padding / structural zero).
+ *   max_norm <= 0 disables clipping. */
+int sbi_b200_adam_clip_step(float* d_params, const float* d_grad, float* d_state,
+                            int32_t* d_step, const uint8_t* d_mask, int64_t n, float lr,
+                            float beta1, float beta2, float eps, float max_norm,
+                            float grad_scale, void* stream);
+
+/* ---- host-buffer entry points (the end-to-end path a CPU caller binds) ------------------
+ * Device staging / optimizer buffers are owned by the caller and passed in a workspace;
+ * h_* buffers should be pinned for full PCIe bandwidth.  These calls copy host->device,
+ * run the kernels, copy the result device->host and block until it has landed. */
+typedef struct {
+  float* d_input;        /* (cap_rows, D) staging */
+  float* d_cond;         /* (cap_rows, C) staging */
+  float* d_logp;         /* (cap_rows) */
+  float* d_gpart;        /* (sbi_b200_nsf_vjp_parts(cap_rows), n_params), zero-initialised once */
+  float* d_grad;         /* (n_params) */
+  float* d_state;        /* (2*n_params) Adam m | v */
+  int32_t* d_step;       /* (2) */
+  const uint8_t* d_mask; /* (n_params) or NULL */
+  float* d_loss_acc;     /* (2) */
+  int64_t cap_rows;
+} sbi_train_ws;
+
+/* One optimisation step on a host batch (replaces one iteration of
+ * sbi/inference/trainers/base.py:1171-1187 incl. the batch `.to(device)` of
+ * npe_base.py:722-726): loss = mean_r -log q(theta_r | x_r); h_loss_out[0] = sum_r -log q,
+ * h_loss_out[1] = number of non-finite rows. */
+int sbi_b200_nsf_train_step_host(const sbi_nsf_model* m, const sbi_train_ws* ws,
+                                 const float* h_input, const float* h_cond, int64_t B, float lr,
+                                 float beta1, float beta2, float eps, float max_norm,
+                                 float* h_loss_out, void* stream);
+
+/* log q(input_r | cond) for R host rows (cond: (R,C), or (1,C) when cond_shared). */
+int sbi_b200_nsf_logprob_host(const sbi_nsf_model* m, const sbi_train_ws* ws,
+                              const float* h_input, const float* h_cond, int64_t R,
+                              int cond_shared, float* h_logp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBI_B200_H */

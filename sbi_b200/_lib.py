@@ -1,0 +1,135 @@
+"""ctypes binding of the C-ABI library (include/sbi_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing or no sm_100 device
+is present, calls raise.  PyTorch is used only for device memory and streams; kernels are
+launched through the C ABI with raw device pointers on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsbi_b200.so")
+
+SBI_NSF_LAYER_STRIDE = 64
+SBI_NSF_MAX_BLOCKS = 8
+# layer-table field indices (mirror include/sbi_b200.h)
+L_NID, L_NTR, L_W0, L_B0, L_WF, L_BF = 0, 1, 2, 3, 4, 5
+L_LU_LOWER, L_LU_UPPER, L_LU_DIAG, L_LU_BIAS, L_FEAT, L_HAS_LU, L_BLK0 = 6, 7, 8, 9, 10, 11, 16
+
+
+class NsfModel(C.Structure):
+    _fields_ = [
+        ("D", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("NB", C.c_int32),
+        ("KB", C.c_int32), ("T", C.c_int32),
+        ("Dp", C.c_int32), ("Cp", C.c_int32), ("IDp", C.c_int32), ("Hp", C.c_int32),
+        ("PR", C.c_int32), ("TRmax", C.c_int32), ("nf_chunk", C.c_int32),
+        ("rpc0", C.c_int32), ("rpc1", C.c_int32), ("rpc2", C.c_int32),
+        ("wcap", C.c_int32), ("nbuf", C.c_int32), ("n_params", C.c_int32),
+        ("tail_bound", C.c_float), ("inv_sqrt_h", C.c_float), ("min_bw", C.c_float),
+        ("min_bh", C.c_float), ("min_d", C.c_float), ("edge_raw", C.c_float),
+        ("ld_zscore", C.c_float),
+        ("d_params", C.c_void_p), ("d_layer_tab", C.c_void_p), ("d_feat_tab", C.c_void_p),
+        ("d_stats", C.c_void_p),
+    ]
+
+
+class Rows(C.Structure):
+    _fields_ = [
+        ("d_input", C.c_void_p), ("d_cond", C.c_void_p), ("d_index", C.c_void_p),
+        ("R", C.c_int64), ("cond_shared", C.c_int32),
+    ]
+
+
+class TrainWs(C.Structure):
+    _fields_ = [
+        ("d_input", C.c_void_p), ("d_cond", C.c_void_p), ("d_logp", C.c_void_p),
+        ("d_gpart", C.c_void_p), ("d_grad", C.c_void_p), ("d_state", C.c_void_p),
+        ("d_step", C.c_void_p), ("d_mask", C.c_void_p), ("d_loss_acc", C.c_void_p),
+        ("cap_rows", C.c_int64),
+    ]
+
+
+_EXPORTS = {
+    "sbi_b200_abi_version": (C.c_int, []),
+    "sbi_b200_device_ok": (C.c_int, []),
+    "sbi_b200_nsf_logprob": (C.c_int, [C.POINTER(NsfModel), C.POINTER(Rows), C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "sbi_b200_nsf_vjp_parts": (C.c_int, [C.c_int64]),
+    "sbi_b200_nsf_vjp": (C.c_int, [C.POINTER(NsfModel), C.POINTER(Rows), C.c_void_p, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+    "sbi_b200_nsf_inverse": (C.c_int, [C.POINTER(NsfModel), C.POINTER(Rows), C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "sbi_b200_reduce_partials": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                           C.c_void_p]),
+    "sbi_b200_adam_clip_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                          C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "sbi_b200_nsf_train_step_host": (C.c_int, [C.POINTER(NsfModel), C.POINTER(TrainWs), C.c_void_p,
+                                               C.c_void_p, C.c_int64, C.c_float, C.c_float,
+                                               C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                               C.c_void_p]),
+    "sbi_b200_nsf_logprob_host": (C.c_int, [C.POINTER(NsfModel), C.POINTER(TrainWs), C.c_void_p,
+                                            C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                            C.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names every entry point declared in include/sbi_b200.h."""
+    return list(_EXPORTS)
+
+
+def load():
+    """dlopen the library and bind prototypes (no GPU needed for this)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m sbi_b200.build` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.sbi_b200_abi_version() != 1:
+            raise RuntimeError("libsbi_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+class SbiB200Error(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc == -1:
+        raise ValueError(f"{what}: invalid argument (SBI_EINVAL)")
+    if rc == -2:
+        raise SbiB200Error(f"{what}: model does not fit the shared-memory budget (SBI_ESMEM)")
+    raise SbiB200Error(f"{what}: CUDA error {rc}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"sbi_b200: `{name}` lives on {t.device}; the kernels only run on a CUDA (sm_100a) "
+            "device and there is no CPU fallback")
+    return t
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,62 @@
+// Host-buffer entry points: H2D staging -> kernels -> D2H result, one blocking call.
+#include <cuda_runtime.h>
+
+#include "../../include/sbi_b200.h"
+
+#define CK(x)                            \
+  do {                                   \
+    cudaError_t e_ = (x);                \
+    if (e_ != cudaSuccess) return (int)e_; \
+  } while (0)
+
+extern "C" int sbi_b200_nsf_train_step_host(const sbi_nsf_model* m, const sbi_train_ws* ws,
+                                            const float* h_input, const float* h_cond, int64_t B,
+                                            float lr, float beta1, float beta2, float eps,
+                                            float max_norm, float* h_loss_out, void* stream) {
+  if (!m || !ws || !h_input || !h_cond || !h_loss_out || B < 1 || B > ws->cap_rows)
+    return SBI_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(ws->d_input, h_input, sizeof(float) * B * m->D, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ws->d_cond, h_cond, sizeof(float) * B * m->C, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ws->d_loss_acc, 0, 2 * sizeof(float), s));
+  sbi_rows rows;
+  rows.d_input = ws->d_input;
+  rows.d_cond = ws->d_cond;
+  rows.d_index = nullptr;
+  rows.R = B;
+  rows.cond_shared = 0;
+  int rc = sbi_b200_nsf_vjp(m, &rows, nullptr, -1.0f / (float)B, nullptr, ws->d_gpart, nullptr,
+                            nullptr, ws->d_loss_acc, stream);
+  if (rc) return rc;
+  rc = sbi_b200_reduce_partials(ws->d_gpart, sbi_b200_nsf_vjp_parts(B), m->n_params, ws->d_grad,
+                                stream);
+  if (rc) return rc;
+  rc = sbi_b200_adam_clip_step(const_cast<float*>(m->d_params), ws->d_grad, ws->d_state,
+                               ws->d_step, ws->d_mask, m->n_params, lr, beta1, beta2, eps,
+                               max_norm, 1.0f, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_loss_out, ws->d_loss_acc, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int sbi_b200_nsf_logprob_host(const sbi_nsf_model* m, const sbi_train_ws* ws,
+                                         const float* h_input, const float* h_cond, int64_t R,
+                                         int cond_shared, float* h_logp, void* stream) {
+  if (!m || !ws || !h_input || !h_cond || !h_logp || R < 1 || R > ws->cap_rows) return SBI_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(ws->d_input, h_input, sizeof(float) * R * m->D, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ws->d_cond, h_cond, sizeof(float) * (cond_shared ? 1 : R) * m->C,
+                     cudaMemcpyHostToDevice, s));
+  sbi_rows rows;
+  rows.d_input = ws->d_input;
+  rows.d_cond = ws->d_cond;
+  rows.d_index = nullptr;
+  rows.R = R;
+  rows.cond_shared = cond_shared ? 1 : 0;
+  int rc = sbi_b200_nsf_logprob(m, &rows, ws->d_logp, nullptr, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_logp, ws->d_logp, sizeof(float) * R, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}

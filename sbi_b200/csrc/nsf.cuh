@@ -1,0 +1,463 @@
+// Neural-spline-flow kernels: fused log_prob, fused forward+backward (VJP) and inverse
+// (sampling) for the flow that sbi's `build_nsf` assembles
+// (/root/reference/sbi/neural_nets/net_builders/flow.py:333-460):
+//
+//   z-score -> T x [ RQ-spline coupling (ResidualNet conditioner, GLU context) -> LULinear ]
+//   -> standard normal base.
+//
+// One CTA = 8 consumer warps + 1 TMA producer warp, owning a tile of TM rows.  All
+// activations of the tile stay in shared memory (feature-major), weights are streamed from
+// L2 with cp.async.bulk into an mbarrier ring, inputs are read once and one float per row
+// is written back.  Both roles run the same stage sequence (template parameter Role), so the
+// producer always knows the next chunk without a table.
+#pragma once
+#include "../../include/sbi_b200.h"
+#include "rqs.cuh"
+#include "tile_gemm.cuh"
+
+namespace sbi {
+
+enum Role { kProducer = 0, kConsumer = 1 };
+
+// ---- shared memory plan (row counts are in rows of LD floats) --------------------------
+struct NsfSmem {
+  int LD;
+  // forward
+  int U, Z, H, A0, A1, PRM, LDF, Y, Y2, LDACC;
+  // training extras
+  int ZS, VS, HS, A1S, T2S, SS, dZ, dU, dH, dT, dG, dPRM, GR, dCTX;
+  int ring;        // float offset of the weight ring
+  int bar_bytes;   // byte offset of the mbarriers
+  int total_bytes;
+};
+
+__host__ __device__ inline NsfSmem nsf_smem_layout(const sbi_nsf_model& m, int TM, bool train) {
+  NsfSmem L;
+  L.LD = TM + 4;
+  int rows = 0;
+  auto take = [&](int n) { int o = rows * L.LD; rows += n; return o; };
+  const int K0p = m.Cp + m.IDp;
+  const int prm = m.nf_chunk * m.PR;
+  L.U = take(K0p);
+  L.Z = take(m.Dp);
+  L.H = take(m.Hp);
+  L.A0 = take(m.Hp);
+  L.A1 = take(m.Hp);
+  L.PRM = take(prm);
+  L.LDF = take(round4(m.TRmax));
+  L.Y = take(m.Dp);
+  L.Y2 = take(m.Dp);
+  L.LDACC = take(1);
+  L.ZS = L.VS = L.HS = L.A1S = L.T2S = L.SS = 0;
+  L.dZ = L.dU = L.dH = L.dT = L.dG = L.dPRM = L.GR = L.dCTX = 0;
+  if (train) {
+    L.ZS = take(m.T * m.Dp);
+    L.VS = take(m.T * m.Dp);
+    L.HS = take((m.NB + 1) * m.Hp);
+    L.A1S = take(m.NB * m.Hp);
+    L.T2S = take(m.NB * m.Hp);
+    L.SS = take(m.NB * m.Hp);
+    L.dZ = take(m.Dp);
+    L.dU = take(K0p);
+    L.dH = take(m.Hp);
+    L.dT = take(m.Hp);
+    L.dG = take(m.Hp);
+    L.dPRM = take(prm);
+    L.GR = take(1);
+    L.dCTX = take(m.Cp);
+  }
+  int fl = rows * L.LD;
+  fl = (fl + 31) & ~31;   // 128-byte align the ring
+  L.ring = fl;
+  fl += m.nbuf * m.wcap;
+  L.bar_bytes = fl * 4;
+  L.total_bytes = L.bar_bytes + 2 * m.nbuf * 8 + 16;
+  return L;
+}
+
+// ---- stage helpers (both roles) -----------------------------------------------------------
+// forward GEMM stage: Y = W X, streamed in chunks of `rpc` rows.
+// epi(n0, g, ng, r0, acc): chunk first row n0, thread rows n0 + g + i*ng, tile rows r0..r0+3
+template <Role R, int TM, int RN, class Epi>
+__device__ __forceinline__ void fwd_stage(WPipe& pipe, const float* __restrict__ Wg, int N,
+                                          int Kp, int rpc, const float* X, Epi&& epi) {
+  for (int n0 = 0; n0 < N; n0 += rpc) {
+    const int cnt = min(rpc, N - n0);
+    if (R == kProducer) {
+      pipe.produce(Wg + (size_t)n0 * Kp, cnt * Kp);
+    } else {
+      const float* w = pipe.acquire();
+      gemm_fwd_chunk<TM, RN>(X, Kp >> 2, w, Kp, cnt,
+                             [&](int g, int ng, int r0, float(&acc)[RN][4]) {
+                               epi(n0, g, ng, r0, acc);
+                             });
+      pipe.release();
+    }
+  }
+  if (R == kConsumer) consumer_sync();
+}
+
+// GLU stage: t = W2 X1, gt = Wc X2 for the same output rows; one chunk = [W2 rows | Wc rows]
+template <Role R, int TM, int RN, class Epi>
+__device__ __forceinline__ void glu_stage(WPipe& pipe, const float* __restrict__ W2g, int Kp2,
+                                          const float* __restrict__ Wcg, int Kpc, int N, int rpc,
+                                          const float* X1, const float* X2, Epi&& epi) {
+  constexpr int NRG = Tile<TM>::NRG, NOG = Tile<TM>::NOG;
+  for (int n0 = 0; n0 < N; n0 += rpc) {
+    const int cnt = min(rpc, N - n0);
+    if (R == kProducer) {
+      pipe.produce(W2g + (size_t)n0 * Kp2, cnt * Kp2, Wcg + (size_t)n0 * Kpc, cnt * Kpc);
+    } else {
+      const float* w2 = pipe.acquire();
+      const float* wc = w2 + cnt * Kp2;
+      const int rg = threadIdx.x % NRG, og = threadIdx.x / NRG;
+      const int ng = cnt / RN;
+      for (int g = og; g < ng; g += NOG) {
+        float at[RN][4], ag[RN][4];
+#pragma unroll
+        for (int i = 0; i < RN; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) at[i][c] = ag[i][c] = 0.f;
+        gemm_fwd_acc<TM, RN>(at, X1, Kp2 >> 2, w2, Kp2, g, ng, rg);
+        gemm_fwd_acc<TM, RN>(ag, X2, Kpc >> 2, wc, Kpc, g, ng, rg);
+        epi(n0, g, ng, 4 * rg, at, ag);
+      }
+      pipe.release();
+    }
+  }
+  if (R == kConsumer) consumer_sync();
+}
+
+// backward-x stage over a weight matrix of N rows: dX = W^T dY (accumulated over chunks).
+// epi(k0, r0, acc, first) ; `first` = first chunk (overwrite vs. add is up to the epilogue).
+template <Role R, int TM, int RK, class Epi>
+__device__ __forceinline__ void dx_stage(WPipe& pipe, const float* __restrict__ Wg, int N, int Kp,
+                                         int rpc, const float* dY, int Kout, Epi&& epi) {
+  for (int n0 = 0; n0 < N; n0 += rpc) {
+    const int cnt = min(rpc, N - n0);
+    if (R == kProducer) {
+      pipe.produce(Wg + (size_t)n0 * Kp, cnt * Kp);
+    } else {
+      const float* w = pipe.acquire();
+      gemm_dx_chunk<TM, RK>(dY, n0, cnt, w, Kp, Kout,
+                            [&](int k0, int r0, float(&acc)[RK][4]) { epi(k0, r0, acc, n0 == 0); });
+      pipe.release();
+    }
+  }
+  if (R == kConsumer) consumer_sync();
+}
+
+// ---- per-layer pieces -----------------------------------------------------------------------
+struct NsfLayerView {
+  const int* LT;    // layer table row
+  const int* idf;   // identity feature indices
+  const int* trf;   // transformed feature indices
+  int n_id, n_tr;
+};
+__device__ __forceinline__ NsfLayerView layer_view(const sbi_nsf_model& m, int l) {
+  NsfLayerView v;
+  v.LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
+  v.n_id = __ldg(v.LT + SBI_L_NID);
+  v.n_tr = __ldg(v.LT + SBI_L_NTR);
+  v.idf = m.d_feat_tab + __ldg(v.LT + SBI_L_FEAT);
+  v.trf = v.idf + v.n_id;
+  return v;
+}
+
+__device__ __forceinline__ RqsConst rqs_const(const sbi_nsf_model& m) {
+  RqsConst c;
+  c.K = m.KB; c.B = m.tail_bound; c.isq = m.inv_sqrt_h;
+  c.min_w = m.min_bw; c.min_h = m.min_bh; c.min_d = m.min_d; c.edge_raw = m.edge_raw;
+  return c;
+}
+
+__device__ __forceinline__ float4 relu4(float4 v) {
+  return make_float4(relu_f(v.x), relu_f(v.y), relu_f(v.z), relu_f(v.w));
+}
+
+// U[Cp + i] = Zsrc[idf[i]] (identity features feeding the conditioner), pad rows zero
+template <int TM>
+__device__ __forceinline__ void gather_identity(const sbi_nsf_model& m, const NsfLayerView& v,
+                                                const float* Zsrc, float* U) {
+  constexpr int LD = Tile<TM>::LD;
+  for (int e = threadIdx.x; e < m.IDp * TM; e += kConsumerThreads) {
+    const int i = e / TM, r = e % TM;
+    U[(m.Cp + i) * LD + r] = (i < v.n_id) ? Zsrc[__ldg(v.idf + i) * LD + r] : 0.f;
+  }
+  consumer_sync();
+}
+
+// ResidualNet conditioner up to the last hidden state (restating nflows ResidualNet,
+// oracle/nflows_port/nn/nets/resnet.py).  SAVE keeps every intermediate for the backward.
+// Returns the buffer holding the final hidden state.
+template <Role R, int TM, int RN, bool SAVE>
+__device__ __forceinline__ float* cond_forward(const sbi_nsf_model& m, const NsfLayerView& v,
+                                               WPipe& pipe, float* sm, const NsfSmem& L) {
+  constexpr int LD = Tile<TM>::LD;
+  const float* __restrict__ P = m.d_params;
+  const int Hp = m.Hp, Cp = m.Cp, K0p = m.Cp + m.IDp;
+  float* U = sm + L.U;
+  float* A0 = sm + L.A0;
+  float* Hout = SAVE ? sm + L.HS : sm + L.H;
+  {
+    const float* b0 = P + __ldg(v.LT + SBI_L_B0);
+    fwd_stage<R, TM, RN>(pipe, P + __ldg(v.LT + SBI_L_W0), Hp, K0p, m.rpc0, U,
+                         [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
+#pragma unroll
+                           for (int i = 0; i < RN; ++i) {
+                             const int n = n0 + g + i * ng;
+                             const float b = __ldg(b0 + n);
+                             const float4 h = make_float4(acc[i][0] + b, acc[i][1] + b,
+                                                          acc[i][2] + b, acc[i][3] + b);
+                             st4(Hout + n * LD + r0, h);
+                             st4(A0 + n * LD + r0, relu4(h));
+                           }
+                         });
+  }
+  for (int b = 0; b < m.NB; ++b) {
+    const int* BT = v.LT + SBI_L_BLK0 + 6 * b;
+    float* Hin = Hout;
+    if (SAVE) Hout = Hin + Hp * LD;
+    float* A1o = SAVE ? sm + L.A1S + b * Hp * LD : sm + L.A1;
+    float* T2o = sm + L.T2S + b * Hp * LD;
+    float* So = sm + L.SS + b * Hp * LD;
+    const float* b1 = P + __ldg(BT + 1);
+    fwd_stage<R, TM, RN>(pipe, P + __ldg(BT + 0), Hp, Hp, m.rpc1, A0,
+                         [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
+#pragma unroll
+                           for (int i = 0; i < RN; ++i) {
+                             const int n = n0 + g + i * ng;
+                             const float bb = __ldg(b1 + n);
+                             st4(A1o + n * LD + r0,
+                                 make_float4(relu_f(acc[i][0] + bb), relu_f(acc[i][1] + bb),
+                                             relu_f(acc[i][2] + bb), relu_f(acc[i][3] + bb)));
+                           }
+                         });
+    const float* b2 = P + __ldg(BT + 3);
+    const float* bc = P + __ldg(BT + 5);
+    glu_stage<R, TM, RN>(
+        pipe, P + __ldg(BT + 2), Hp, P + __ldg(BT + 4), Cp, Hp, m.rpc2, A1o, U,
+        [&](int n0, int g, int ng, int r0, float(&at)[RN][4], float(&ag)[RN][4]) {
+#pragma unroll
+          for (int i = 0; i < RN; ++i) {
+            const int n = n0 + g + i * ng;
+            const float bt = __ldg(b2 + n), bg = __ldg(bc + n);
+            const float4 hin = ld4(Hin + n * LD + r0);
+            float t[4], s[4], h[4];
+            const float hi[4] = {hin.x, hin.y, hin.z, hin.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              t[c] = at[i][c] + bt;
+              s[c] = sigmoid_f(ag[i][c] + bg);
+              h[c] = hi[c] + t[c] * s[c];
+            }
+            const float4 hv = make_float4(h[0], h[1], h[2], h[3]);
+            st4(Hout + n * LD + r0, hv);
+            st4(A0 + n * LD + r0, relu4(hv));
+            if (SAVE) {
+              st4(T2o + n * LD + r0, make_float4(t[0], t[1], t[2], t[3]));
+              st4(So + n * LD + r0, make_float4(s[0], s[1], s[2], s[3]));
+            }
+          }
+        });
+  }
+  return Hout;
+}
+
+// final layer + spline, chunked over transformed features (forward or inverse direction)
+template <Role R, int TM, int RN, bool INVERSE>
+__device__ __forceinline__ void spline_forward(const sbi_nsf_model& m, const NsfLayerView& v,
+                                               WPipe& pipe, float* sm, const NsfSmem& L,
+                                               const float* Hfin) {
+  constexpr int LD = Tile<TM>::LD;
+  const float* __restrict__ P = m.d_params;
+  const RqsConst rc = rqs_const(m);
+  float* PRM = sm + L.PRM;
+  float* Z = sm + L.Z;
+  float* LDF = sm + L.LDF;
+  const float* WF = P + __ldg(v.LT + SBI_L_WF);
+  const float* BF = P + __ldg(v.LT + SBI_L_BF);
+  for (int f0 = 0; f0 < v.n_tr; f0 += m.nf_chunk) {
+    const int nfc = min(m.nf_chunk, v.n_tr - f0);
+    const int N = nfc * m.PR;
+    const float* bf = BF + f0 * m.PR;
+    fwd_stage<R, TM, RN>(pipe, WF + (size_t)f0 * m.PR * m.Hp, N, m.Hp, N, Hfin,
+                         [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
+#pragma unroll
+                           for (int i = 0; i < RN; ++i) {
+                             const int n = n0 + g + i * ng;
+                             const float b = __ldg(bf + n);
+                             st4(PRM + n * LD + r0, make_float4(acc[i][0] + b, acc[i][1] + b,
+                                                                acc[i][2] + b, acc[i][3] + b));
+                           }
+                         });
+    if (R == kConsumer) {
+      for (int t = threadIdx.x; t < nfc * TM; t += kConsumerThreads) {
+        const int f = t / TM, r = t % TM;
+        const int j = __ldg(v.trf + f0 + f);
+        const float x = Z[j * LD + r];
+        float y, ld;
+        if (INVERSE) rqs_inverse(PRM + f * m.PR * LD + r, LD, rc, x, y, ld);
+        else rqs_forward(PRM + f * m.PR * LD + r, LD, rc, x, y, ld);
+        Z[j * LD + r] = y;
+        LDF[(f0 + f) * LD + r] = ld;
+      }
+      consumer_sync();
+    }
+  }
+}
+
+// LULinear helpers (restating nflows LULinear, oracle/nflows_port/transforms/lu.py)
+__device__ __forceinline__ float lu_lower(const float* lo, int i, int j) {   // j < i
+  return __ldg(lo + i * (i - 1) / 2 + j);
+}
+__device__ __forceinline__ float lu_upper(const float* up, int D, int i, int j) {   // j > i
+  return __ldg(up + i * D - i * (i + 1) / 2 + (j - i - 1));
+}
+__device__ __forceinline__ float lu_diag(const float* dg, int i) {
+  return softplus_f(__ldg(dg + i)) + 1e-3f;
+}
+
+// LDACC[r] += sum_f LDF[f][r]  (this layer's spline log-dets, fixed order over features).
+// No barrier: callers have one before LDF is rewritten / LDACC is read.
+template <int TM>
+__device__ __forceinline__ void fold_ldf(const NsfLayerView& v, float* sm, const NsfSmem& L) {
+  constexpr int LD = Tile<TM>::LD;
+  for (int r = threadIdx.x; r < TM; r += kConsumerThreads) {
+    float a = sm[L.LDACC + r];
+    for (int f = 0; f < v.n_tr; ++f) a += sm[L.LDF + f * LD + r];
+    sm[L.LDACC + r] = a;
+  }
+}
+
+// z <- L (U z) + b
+template <int TM>
+__device__ __forceinline__ void lu_forward(const sbi_nsf_model& m, const NsfLayerView& v,
+                                           float* sm, const NsfSmem& L) {
+  constexpr int LD = Tile<TM>::LD;
+  const float* __restrict__ P = m.d_params;
+  const int D = m.D;
+  float* Z = sm + L.Z;
+  float* Y = sm + L.Y;
+  if (!__ldg(v.LT + SBI_L_HAS_LU)) return;
+  const float* lo = P + __ldg(v.LT + SBI_L_LU_LOWER);
+  const float* up = P + __ldg(v.LT + SBI_L_LU_UPPER);
+  const float* dg = P + __ldg(v.LT + SBI_L_LU_DIAG);
+  const float* bi = P + __ldg(v.LT + SBI_L_LU_BIAS);
+  for (int t = threadIdx.x; t < D * TM; t += kConsumerThreads) {
+    const int i = t / TM, r = t % TM;
+    float a = lu_diag(dg, i) * Z[i * LD + r];
+    for (int j = i + 1; j < D; ++j) a = fmaf(lu_upper(up, D, i, j), Z[j * LD + r], a);
+    Y[i * LD + r] = a;
+  }
+  consumer_sync();
+  for (int t = threadIdx.x; t < D * TM; t += kConsumerThreads) {
+    const int i = t / TM, r = t % TM;
+    float a = Y[i * LD + r];
+    for (int j = 0; j < i; ++j) a = fmaf(lu_lower(lo, i, j), Y[j * LD + r], a);
+    Z[i * LD + r] = a + __ldg(bi + i);
+  }
+  consumer_sync();
+}
+
+// z <- U^{-1} L^{-1} (z - b)   (sampling direction)
+template <int TM>
+__device__ __forceinline__ void lu_inverse(const sbi_nsf_model& m, const NsfLayerView& v,
+                                           float* sm, const NsfSmem& L) {
+  constexpr int LD = Tile<TM>::LD;
+  const float* __restrict__ P = m.d_params;
+  const int D = m.D;
+  if (!__ldg(v.LT + SBI_L_HAS_LU)) return;
+  float* Z = sm + L.Z;
+  const float* lo = P + __ldg(v.LT + SBI_L_LU_LOWER);
+  const float* up = P + __ldg(v.LT + SBI_L_LU_UPPER);
+  const float* dg = P + __ldg(v.LT + SBI_L_LU_DIAG);
+  const float* bi = P + __ldg(v.LT + SBI_L_LU_BIAS);
+  // one thread per row: forward substitution with unit-lower L, back substitution with U
+  for (int r = threadIdx.x; r < TM; r += kConsumerThreads) {
+    for (int i = 0; i < D; ++i) {
+      float a = Z[i * LD + r] - __ldg(bi + i);
+      for (int j = 0; j < i; ++j) a -= lu_lower(lo, i, j) * Z[j * LD + r];
+      Z[i * LD + r] = a;
+    }
+    for (int i = D - 1; i >= 0; --i) {
+      float a = Z[i * LD + r];
+      for (int j = i + 1; j < D; ++j) a -= lu_upper(up, D, i, j) * Z[j * LD + r];
+      Z[i * LD + r] = a / lu_diag(dg, i);
+    }
+  }
+  consumer_sync();
+}
+
+// sum over layers of log|det LU| = sum_i log(softplus(raw_i)+eps): identical for every row
+__device__ __forceinline__ float lu_logdet_total(const sbi_nsf_model& m) {
+  float tot = 0.f;
+  for (int l = 0; l < m.T; ++l) {
+    const int* LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
+    if (!__ldg(LT + SBI_L_HAS_LU)) continue;
+    const float* dg = m.d_params + __ldg(LT + SBI_L_LU_DIAG);
+    float s = 0.f;
+    for (int i = 0; i < m.D; ++i) s += logf(lu_diag(dg, i));
+    tot += s;
+  }
+  return tot;
+}
+
+// ---- tile load / store ---------------------------------------------------------------------------
+// Z = zscore(input rows), U[0:C] = standardize(cond rows); zero pads; LDACC = 0
+template <int TM>
+__device__ __forceinline__ void load_tile(const sbi_nsf_model& m, const sbi_rows& rows,
+                                          int64_t row0, float* sm, const NsfSmem& L,
+                                          bool raw_input) {
+  constexpr int LD = Tile<TM>::LD;
+  const float* __restrict__ st = m.d_stats;
+  float* Z = sm + L.Z;
+  float* U = sm + L.U;
+  const int D = m.D, C = m.C;
+  for (int e = threadIdx.x; e < TM * m.Dp; e += kConsumerThreads) {
+    const int r = e / m.Dp, d = e % m.Dp;
+    const int64_t gr = row0 + r;
+    float val = 0.f;
+    if (d < D && gr < rows.R) {
+      const int64_t src = rows.d_index ? __ldg(rows.d_index + gr) : gr;
+      const float x = __ldg(rows.d_input + src * D + d);
+      val = raw_input ? x : rqs_mul_add(x, __ldg(st + m.Dp + d), __ldg(st + d));
+    }
+    Z[d * LD + r] = val;
+  }
+  for (int e = threadIdx.x; e < TM * m.Cp; e += kConsumerThreads) {
+    const int r = e / m.Cp, c = e % m.Cp;
+    const int64_t gr = row0 + r;
+    float val = 0.f;
+    if (c < C && gr < rows.R) {
+      const int64_t src = rows.cond_shared ? 0 : (rows.d_index ? __ldg(rows.d_index + gr) : gr);
+      val = (__ldg(rows.d_cond + src * C + c) - __ldg(st + 2 * m.Dp + c)) /
+            __ldg(st + 2 * m.Dp + m.Cp + c);
+    }
+    U[c * LD + r] = val;
+  }
+  for (int r = threadIdx.x; r < TM; r += kConsumerThreads) sm[L.LDACC + r] = 0.f;
+  consumer_sync();
+}
+
+// ---- shared-memory setup common to the three kernels ---------------------------------------------
+__device__ __forceinline__ WPipe make_pipe(const sbi_nsf_model& m, float* sm, const NsfSmem& L) {
+  WPipe p;
+  p.buf = sm + L.ring;
+  p.full = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(sm) + L.bar_bytes);
+  p.empty = p.full + m.nbuf;
+  p.cap = m.wcap;
+  p.nbuf = m.nbuf;
+  p.it = 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < m.nbuf; ++s) {
+      mbar_init(&p.full[s], 1);
+      mbar_init(&p.empty[s], kConsumerThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  return p;
+}
+
+}  // namespace sbi

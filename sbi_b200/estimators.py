@@ -1,0 +1,381 @@
+"""Estimator modules at sbi's estimator boundary, backed by the sm_100a kernels.
+
+`NSFEstimator` mirrors `sbi.neural_nets.estimators.NFlowsFlow`
+(/root/reference/sbi/neural_nets/estimators/nflows_flow.py:14-151) on the shape rules of
+`ConditionalDensityEstimator` (/root/reference/sbi/neural_nets/estimators/base.py:35-306):
+same method names, argument meaning, output shapes and error behaviour, and a
+`state_dict()` with the reference's own keys, so reference checkpoints load verbatim.
+All parameters live in ONE flat `nn.Parameter` (the packed layout of `pack.NsfLayout`);
+`log_prob` is a `torch.autograd.Function` whose forward is the fused log-prob kernel and
+whose backward is the fused forward+backward (VJP) kernel.  No CPU path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib as L
+from .pack import NsfLayout
+
+
+class Standardize(nn.Module):
+    """(t - mean) / std -- mirrors sbi.utils.sbiutils.Standardize (sbiutils.py:418-428)."""
+
+    def __init__(self, mean, std):
+        super().__init__()
+        mean, std = map(torch.as_tensor, (mean, std))
+        self.register_buffer("_mean", mean.clone().float())
+        self.register_buffer("_std", std.clone().float())
+
+    def forward(self, tensor):
+        return (tensor - self._mean) / self._std
+
+
+class _NsfNet(nn.Module):
+    """Plays the role of the nflows `Flow` object that sits at `estimator.net`."""
+
+    def __init__(self, layout: NsfLayout, shift: Tensor, scale: Tensor,
+                 embedding_net: nn.Module):
+        super().__init__()
+        self.layout = layout
+        self.flat = nn.Parameter(torch.zeros(layout.n_params, dtype=torch.float32))
+        self.register_buffer("_shift", shift.clone().float(), persistent=False)
+        self.register_buffer("_scale", scale.clone().float(), persistent=False)
+        self.register_buffer("_layer_tab", torch.from_numpy(layout.layer_tab.reshape(-1).copy()),
+                             persistent=False)
+        self.register_buffer("_feat_tab", torch.from_numpy(layout.feat_tab.copy()),
+                             persistent=False)
+        self.register_buffer("_mask", layout.trainable_mask(), persistent=False)
+        self._embedding_net = embedding_net
+
+    # -- reference-compatible (de)serialisation ---------------------------------------------
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        lay = self.layout
+        if lay.zscore_input:
+            destination[prefix + "_transform._transforms.0._shift"] = self._shift.detach().clone()
+            destination[prefix + "_transform._transforms.0._scale"] = self._scale.detach().clone()
+        for k, t in lay.unpack(self.flat).items():
+            destination[prefix + k[len("net."):]] = t
+        for k, t in lay.buffers.items():
+            destination[prefix + k[len("net."):]] = t.to(self.flat.device)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
+                              unexpected_keys, error_msgs):
+        lay = self.layout
+        if prefix + "flat" in state_dict:   # native format
+            with torch.no_grad():
+                self.flat.copy_(state_dict.pop(prefix + "flat"))
+        else:
+            src = {}
+            for k in lay.index:
+                kk = prefix + k[len("net."):]
+                if kk in state_dict:
+                    src[k] = state_dict.pop(kk)
+                elif strict:
+                    missing_keys.append(kk)
+            if len(src) == len(lay.index):
+                with torch.no_grad():
+                    lay.pack(src, out=self.flat.data)
+        for name, buf in (("_shift", self._shift), ("_scale", self._scale)):
+            kk = prefix + "_transform._transforms.0." + name
+            if kk in state_dict:
+                with torch.no_grad():
+                    buf.copy_(state_dict.pop(kk))
+        for k in lay.buffers:
+            state_dict.pop(prefix + k[len("net."):], None)
+
+
+def _is_identity(m: nn.Module) -> bool:
+    return isinstance(m, nn.Identity)
+
+
+class NSFEstimator(nn.Module):
+    r"""Neural spline flow q(input | condition) evaluated by hand-written sm_100a kernels."""
+
+    def __init__(self, layout: NsfLayout, input_shape, condition_shape, shift: Tensor,
+                 scale: Tensor, cond_mean: Optional[Tensor], cond_std: Optional[Tensor],
+                 embedding_net: Optional[nn.Module] = None):
+        super().__init__()
+        self._input_shape = torch.Size(input_shape)
+        self._condition_shape = torch.Size(condition_shape)
+        user_net = embedding_net if embedding_net is not None else nn.Identity()
+        self._embed_identity = _is_identity(user_net)
+        if cond_mean is not None:
+            emb = nn.Sequential(Standardize(cond_mean, cond_std), user_net)
+        else:
+            emb = user_net
+        self.net = _NsfNet(layout, shift, scale, emb)
+        self._cache = {}
+
+    # ---- properties of the reference interface ---------------------------------------------
+    @property
+    def layout(self) -> NsfLayout:
+        return self.net.layout
+
+    @property
+    def input_shape(self) -> torch.Size:
+        return self._input_shape
+
+    @property
+    def condition_shape(self) -> torch.Size:
+        return self._condition_shape
+
+    @property
+    def embedding_net(self) -> nn.Module:
+        return self.net._embedding_net
+
+    @property
+    def flat(self) -> nn.Parameter:
+        return self.net.flat
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == "_cache":
+                new.__dict__[k] = {}
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_cache"] = {}
+        return d
+
+    # ---- kernel-side views --------------------------------------------------------------------
+    def _kernel_stats(self) -> Tuple[Tensor, float]:
+        """[shift(Dp) | scale(Dp) | ctx_mean(Cp) | ctx_std(Cp)] on the parameter device."""
+        lay = self.layout
+        net = self.net
+        emb = net._embedding_net
+        std_mod = emb[0] if isinstance(emb, nn.Sequential) and isinstance(emb[0], Standardize) else None
+        srcs = [net._shift, net._scale] + ([std_mod._mean, std_mod._std] if std_mod is not None else [])
+        key = tuple((t.data_ptr(), t._version) for t in srcs) + (str(net.flat.device),)
+        hit = self._cache.get("stats")
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        dev = net.flat.device
+        st = torch.zeros(2 * lay.Dp + 2 * lay.Cp, dtype=torch.float32, device=dev)
+        st[lay.Dp:2 * lay.Dp] = 1.0
+        st[2 * lay.Dp + lay.Cp:] = 1.0
+        st[:lay.D] = net._shift.expand(lay.D)
+        st[lay.Dp:lay.Dp + lay.D] = net._scale.expand(lay.D)
+        if std_mod is not None and self._embed_identity:
+            st[2 * lay.Dp:2 * lay.Dp + lay.C] = std_mod._mean.reshape(-1).expand(lay.C)
+            st[2 * lay.Dp + lay.Cp:2 * lay.Dp + lay.Cp + lay.C] = std_mod._std.reshape(-1).expand(lay.C)
+        ld = float(torch.log(torch.abs(net._scale.double())).expand(lay.D).sum())
+        self._cache["stats"] = (key, st, ld)
+        return st, ld
+
+    def _model(self, nbuf: int) -> L.NsfModel:
+        net = self.net
+        L.require_cuda(net.flat, "estimator parameters")
+        st, ld = self._kernel_stats()
+        s = L.NsfModel()
+        self.layout.fill_struct(s, nbuf)
+        s.ld_zscore = ld
+        s.d_params = net.flat.data_ptr()
+        s.d_layer_tab = net._layer_tab.data_ptr()
+        s.d_feat_tab = net._feat_tab.data_ptr()
+        s.d_stats = st.data_ptr()
+        s._keep = (st,)
+        return s
+
+    def _embed(self, condition: Tensor) -> Tensor:
+        """Context fed to the kernels.  Identity embedding: raw condition (standardised
+        in-kernel); otherwise the torch embedding net runs first."""
+        if self._embed_identity:
+            return condition.reshape(condition.shape[0], -1)
+        return self.net._embedding_net(condition).reshape(condition.shape[0], -1)
+
+    def _gpart(self, n_part: int) -> Tensor:
+        buf = self._cache.get("gpart")
+        n = self.layout.n_params
+        if buf is None or buf.shape[0] < n_part or buf.device != self.net.flat.device:
+            buf = torch.zeros(max(n_part, 1), n, dtype=torch.float32, device=self.net.flat.device)
+            self._cache["gpart"] = buf
+        return buf
+
+    # ---- shape handling: base.py:84-198 --------------------------------------------------------
+    def _check_condition_shape(self, condition: Tensor):
+        exp = self.condition_shape
+        if len(condition.shape) < len(exp):
+            raise ValueError(
+                "Dimensionality of condition is too small and does not match the "
+                f"expected dimensionality {len(exp)}. It should "
+                f"be compatible with condition_shape {exp}.")
+        if condition.shape[-len(exp):] != exp:
+            raise ValueError(
+                f"Shape of condition {condition.shape[-len(exp):]} does not match the "
+                f"expected input dimensionality {exp}, as "
+                "provided by condition_shape. Please reshape it accordingly.")
+
+    def _check_input_shape(self, input: Tensor):
+        exp = self.input_shape
+        if len(input.shape) < len(exp):
+            raise ValueError(
+                "Dimensionality of input is too small and does not match the "
+                f"expected dimensionality {len(exp)}. It should "
+                f"be compatible with the provided input_shape {exp}.")
+        if input.shape[-len(exp):] != exp:
+            raise ValueError(
+                f"Shape of input {input.shape[-len(exp):]} does not match the "
+                f"expected input dimensionality {exp}, as "
+                "provided by input_shape. Please reshape it accordingly.")
+
+    def _align(self, input: Tensor, condition: Tensor):
+        """_broadcast_and_align (base.py:142-198) without materialising a broadcast
+        condition: returns input (S*B, D), condition rows and a `shared` flag."""
+        in_ev, c_ev = len(self.input_shape), len(self.condition_shape)
+        if input.dim() <= in_ev + 1:
+            input = input.unsqueeze(0)
+        S, Bi = input.shape[0], input.shape[1]
+        cond_has_sample = condition.dim() > c_ev + 1
+        Bc = condition.shape[1] if cond_has_sample else condition.shape[0]
+        try:
+            B = torch.broadcast_shapes((Bi,), (Bc,))[0]
+        except RuntimeError as err:
+            raise RuntimeError(
+                "Expected `input` and `condition` to have broadcastable batch "
+                "dimensions: their batch sizes must match, or one of them must be 1. "
+                f"Got input={Bi} and condition={Bc}.") from err
+        input = input.expand(S, B, *self.input_shape).reshape(S * B, -1)
+        if not cond_has_sample and Bc == 1:
+            return input, condition.reshape(1, *self.condition_shape), True, S, B
+        if cond_has_sample:
+            condition = condition.expand(S, B, *self.condition_shape)
+        else:
+            condition = condition.expand(B, *self.condition_shape).unsqueeze(0).expand(
+                S, B, *self.condition_shape)
+        return input, condition.reshape(S * B, *self.condition_shape), False, S, B
+
+    # ---- the reference API ------------------------------------------------------------------------
+    def log_prob(self, input: Tensor, condition: Tensor) -> Tensor:
+        """(sample_dim, batch_dim) log-probabilities; nflows_flow.py:77-97."""
+        self._check_input_shape(input)
+        self._check_condition_shape(condition)
+        inp, cond, shared, S, B = self._align(input, condition)
+        ctx = self._embed(cond)
+        lp = _NsfLogProb.apply(self.net.flat, inp.contiguous().float(), ctx.contiguous().float(),
+                               self, shared)
+        return lp.reshape(S, B)
+
+    def loss(self, input: Tensor, condition: Tensor) -> Tensor:
+        """(batch_dim,) negative log-probabilities; nflows_flow.py:99-109."""
+        return -self.log_prob(input.unsqueeze(0), condition)[0]
+
+    def inverse_transform(self, input: Tensor, condition: Tensor) -> Tensor:
+        """Base-space noise of the inputs; nflows_flow.py:42-75."""
+        self._check_condition_shape(condition)
+        cdims = len(self.condition_shape)
+        bshape = torch.broadcast_shapes(input.shape[:-1], condition.shape[:-cdims])
+        inp = input.expand(bshape + (input.shape[-1],)).reshape(-1, input.shape[-1])
+        cond = condition.expand(bshape + self.condition_shape).reshape(-1, *self.condition_shape)
+        ctx = self._embed(cond)
+        _, noise = self._logprob_raw(inp.contiguous().float(), ctx.contiguous().float(), False,
+                                     want_noise=True)
+        return noise.reshape(bshape + (noise.shape[-1],))
+
+    @torch.no_grad()
+    def sample(self, sample_shape, condition: Tensor) -> Tensor:
+        """(*sample_shape, batch_dim, *input_shape); nflows_flow.py:111-128.  Noise is drawn
+        with torch.randn on the parameter device in the order nflows draws it
+        (B*n rows, condition-major), then pushed through the inverse-flow kernel."""
+        self._check_condition_shape(condition)
+        Bc = condition.shape[0]
+        n = torch.Size(sample_shape).numel()
+        D = self.layout.D
+        noise = torch.randn(Bc * n, D, device=self.net.flat.device)
+        x, _ = self.inverse_flow(noise, condition, n)
+        x = x.reshape(Bc, n, D).transpose(0, 1)
+        return x.reshape((*sample_shape, Bc, *self.input_shape))
+
+    @torch.no_grad()
+    def sample_and_log_prob(self, sample_shape, condition: Tensor, **kwargs):
+        """nflows_flow.py:130-151 (via nflows Flow.sample_and_log_prob)."""
+        Bc = condition.shape[0]
+        n = torch.Size(sample_shape).numel()
+        D = self.layout.D
+        noise = torch.randn(Bc * n, D, device=self.net.flat.device)
+        base_lp = -0.5 * (noise ** 2).sum(1) - 0.5 * D * 1.8378770664093453
+        x, lad = self.inverse_flow(noise, condition, n)
+        samples = x.reshape(Bc, n, D).reshape((*sample_shape, Bc, -1))
+        log_probs = (base_lp - lad).reshape(Bc, n).reshape((*sample_shape, -1))
+        return samples, log_probs
+
+    @torch.no_grad()
+    def inverse_flow(self, noise: Tensor, condition: Tensor, reps: int = 1):
+        """x = T^{-1}(noise | condition); `noise` (B*reps, D) condition-major,
+        `condition` (B, *condition_shape).  Returns (x, log|det dx/dnoise|)."""
+        lib = L.load()
+        L.require_cuda(noise, "noise")
+        Bc = condition.shape[0]
+        ctx = self._embed(condition.to(noise.device)).contiguous().float()
+        shared = Bc == 1
+        if not shared:
+            ctx = ctx.repeat_interleave(reps, dim=0).contiguous()
+        noise = noise.contiguous().float()
+        R = noise.shape[0]
+        out = torch.empty_like(noise)
+        lad = torch.empty(R, dtype=torch.float32, device=noise.device)
+        m = self._model(nbuf=2)
+        rows = L.Rows(noise.data_ptr(), ctx.data_ptr(), None, R, 1 if shared else 0)
+        L.check(lib.sbi_b200_nsf_inverse(C.byref(m), C.byref(rows), L.ptr(out), L.ptr(lad),
+                                         L.stream_ptr()), "nsf_inverse")
+        return out, lad
+
+    # ---- raw kernel entry (no autograd) --------------------------------------------------------------
+    def _logprob_raw(self, inp: Tensor, ctx: Tensor, shared: bool, want_noise=False,
+                     index: Optional[Tensor] = None, n_rows: Optional[int] = None):
+        lib = L.load()
+        L.require_cuda(inp, "input")
+        L.require_cuda(ctx, "condition")
+        R = inp.shape[0] if n_rows is None else n_rows
+        lp = torch.empty(R, dtype=torch.float32, device=inp.device)
+        noise = torch.empty(R, self.layout.D, dtype=torch.float32, device=inp.device) if want_noise else None
+        m = self._model(nbuf=2)
+        rows = L.Rows(inp.data_ptr(), ctx.data_ptr(),
+                      None if index is None else index.data_ptr(), R, 1 if shared else 0)
+        L.check(lib.sbi_b200_nsf_logprob(C.byref(m), C.byref(rows), L.ptr(lp), L.ptr(noise),
+                                         L.stream_ptr()), "nsf_logprob")
+        return lp, noise
+
+
+class _NsfLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flat, inp, cond, est: NSFEstimator, shared: bool):
+        lp, _ = est._logprob_raw(inp, cond, shared)
+        ctx.save_for_backward(inp, cond)
+        ctx.est, ctx.shared = est, shared
+        return lp
+
+    @staticmethod
+    def backward(ctx, g):
+        inp, cond = ctx.saved_tensors
+        est, shared = ctx.est, ctx.shared
+        lib = L.load()
+        need_flat, need_inp, need_cond = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        R = inp.shape[0]
+        n_part = lib.sbi_b200_nsf_vjp_parts(R)
+        gpart = est._gpart(n_part)
+        ginp = torch.empty_like(inp) if need_inp else None
+        gcond = torch.empty(R, cond.shape[1], dtype=torch.float32, device=inp.device) if need_cond else None
+        m = est._model(nbuf=3)
+        rows = L.Rows(inp.data_ptr(), cond.data_ptr(), None, R, 1 if shared else 0)
+        g = g.contiguous().float()
+        L.check(lib.sbi_b200_nsf_vjp(C.byref(m), C.byref(rows), L.ptr(g), 0.0, None, L.ptr(gpart),
+                                     L.ptr(ginp), L.ptr(gcond), None, L.stream_ptr()), "nsf_vjp")
+        gflat = None
+        if need_flat:
+            gflat = torch.empty(est.layout.n_params, dtype=torch.float32, device=inp.device)
+            L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, est.layout.n_params,
+                                                 L.ptr(gflat), L.stream_ptr()), "reduce_partials")
+        if need_cond and shared:
+            gcond = gcond.sum(0, keepdim=True)
+        return gflat, ginp, gcond, None, None

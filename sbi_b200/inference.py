@@ -1,0 +1,306 @@
+"""Device-resident trainers and posteriors mirroring the reference's public API for the path.
+
+`NPE` / `NLE` mirror `sbi.inference.NPE` (NPE-C, first round) and `sbi.inference.NLE`
+(/root/reference/sbi/inference/trainers/npe/npe_base.py:81-418,
+ /root/reference/sbi/inference/trainers/nle/nle_base.py:190-272) and the shared loop of
+/root/reference/sbi/inference/trainers/base.py:499-563 (get_dataloaders), :1060-1148
+(_run_training_loop), :1150-1225 (_train_epoch/_validate_epoch), :1254-1284 (_converged):
+
+* same `append_simulations(theta, x).train(...)` / `build_posterior()` call sequence,
+  argument names, defaults and stopping rule (validation loss, `stop_after_epochs`);
+* same loss, optimiser (Adam, lr 5e-4), gradient clipping (5.0), 90/10 split, per-epoch
+  reshuffle with `drop_last`, epoch-granular early stopping restoring the best weights.
+
+What is different is where the work happens: the (theta, x) set lives in HBM, an epoch is ONE
+CUDA-graph launch (steps_per_epoch x [fused fwd+bwd kernel -> partial-gradient reduce ->
+clip+Adam kernel] + the validation pass), and the host reads three scalars per epoch instead
+of syncing twice per step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+import warnings
+from copy import deepcopy
+from typing import Any, Callable, Dict, Optional, Union
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib as L
+from .estimators import NSFEstimator
+from .neural_nets import likelihood_nn, posterior_nn
+
+
+def _process_device(device: str) -> str:
+    """torchutils.py:54-103 (subset): only CUDA devices are valid here."""
+    if device in ("gpu", "cuda"):
+        device = "cuda:0"
+    if not str(device).startswith("cuda"):
+        raise RuntimeError(
+            f"sbi_b200 trains on a CUDA (sm_100a) device only; got device={device!r}. "
+            "There is no CPU fallback.")
+    if not torch.cuda.is_available():
+        raise RuntimeError("sbi_b200: no CUDA device available (no CPU fallback)")
+    return str(device)
+
+
+class _FlowTrainer:
+    """Shared first-round trainer for density estimators (NPE: q(theta|x); NLE: q(x|theta))."""
+
+    _swap = False   # NLE: estimator input = x, condition = theta
+
+    def __init__(self, prior=None, density_estimator: Union[str, Callable] = "nsf",
+                 device: str = "cuda", logging_level: Union[int, str] = "WARNING",
+                 summary_writer=None, tracker=None, show_progress_bars: bool = False):
+        self._prior = prior
+        self._device = _process_device(device)
+        if isinstance(density_estimator, str):
+            factory = likelihood_nn if self._swap else posterior_nn
+            self._build_neural_net = factory(model=density_estimator)
+        else:
+            self._build_neural_net = density_estimator
+        self._neural_net: Optional[NSFEstimator] = None
+        self._theta: Optional[Tensor] = None
+        self._x: Optional[Tensor] = None
+        self._show_progress_bars = show_progress_bars
+        self._round = 0
+        self.epoch = 0
+        self._val_loss = float("Inf")
+        self._summary: Dict[str, list] = dict(
+            epochs_trained=[], best_validation_loss=[], validation_loss=[], training_loss=[],
+            epoch_durations_sec=[])
+        self._graphs = {}
+        self._dist = None   # (rank, world) when data-parallel
+
+    # ------------------------------------------------------------------ data
+    def append_simulations(self, theta: Tensor, x: Tensor, proposal=None,
+                           exclude_invalid_x: Optional[bool] = None, data_device: Optional[str] = None):
+        """Store simulations (npe_base.py:188-299): float32 only, rows with NaN/Inf in x are
+        dropped (user_input_checks.py:708-765, sbiutils.py:491-525)."""
+        if proposal is not None:
+            raise NotImplementedError("multi-round (proposal != prior) training is out of scope")
+        if theta.dtype != torch.float32 or x.dtype != torch.float32:
+            raise AssertionError("theta and x must be float32")
+        if theta.shape[0] != x.shape[0]:
+            raise AssertionError("Number of parameter sets must equal number of simulation outputs")
+        xf = x.reshape(x.shape[0], -1)
+        ok = ~torch.isnan(xf).any(1) & ~torch.isinf(xf).any(1)
+        if exclude_invalid_x is None or exclude_invalid_x:
+            if not bool(ok.all()):
+                warnings.warn(f"Found {int((~ok).sum())} invalid simulations; they are excluded.",
+                              stacklevel=2)
+                theta, x = theta[ok], x[ok]
+        theta = theta.reshape(theta.shape[0], -1)
+        th = theta.to(self._device).contiguous()
+        xx = x.to(self._device).contiguous()
+        if self._theta is None:
+            self._theta, self._x = th, xx
+        else:
+            self._theta = torch.cat([self._theta, th])
+            self._x = torch.cat([self._x, xx])
+        return self
+
+    def get_simulations(self):
+        return self._theta, self._x
+
+    # ------------------------------------------------------------------ training
+    def _inp_cond(self):
+        """(estimator input set, condition set) as (N, .) device tensors."""
+        th, xx = self._theta, self._x.reshape(self._x.shape[0], -1)
+        return (xx, th) if self._swap else (th, xx)
+
+    def train(self, training_batch_size: int = 200, learning_rate: float = 5e-4,
+              validation_fraction: float = 0.1, stop_after_epochs: int = 20,
+              max_num_epochs: int = 2 ** 31 - 1, clip_max_norm: Optional[float] = 5.0,
+              calibration_kernel: Optional[Callable] = None, resume_training: bool = False,
+              force_first_round_loss: bool = False, discard_prior_samples: bool = False,
+              retrain_from_scratch: bool = False, show_train_summary: bool = False,
+              dataloader_kwargs: Optional[dict] = None) -> NSFEstimator:
+        if calibration_kernel is not None:
+            raise NotImplementedError("calibration_kernel is not supported on the fused path")
+        if self._theta is None:
+            raise RuntimeError("call append_simulations() first")
+        lib = L.load()
+        dev = self._device
+        N = self._theta.shape[0]
+        # --- split (base.py:525-539): CPU global generator, like the reference
+        n_train = int((1 - validation_fraction) * N)
+        n_val = N - n_train
+        if not resume_training or not hasattr(self, "train_indices"):
+            perm = torch.randperm(N)
+            self.train_indices, self.val_indices = perm[:n_train], perm[n_train:]
+        # --- network (npe_base.py:674-708): built from the CPU training split
+        if self._neural_net is None or retrain_from_scratch:
+            th_cpu = self._theta[self.train_indices.to(dev)].cpu()
+            x_cpu = self._x[self.train_indices.to(dev)].cpu()
+            self._neural_net = self._build_neural_net(th_cpu, x_cpu)
+            del th_cpu, x_cpu
+        net = self._neural_net.to(dev)
+        self._neural_net = net
+        if not isinstance(net, NSFEstimator):
+            raise TypeError(f"{type(self).__name__} needs an sbi_b200 flow estimator, "
+                            f"got {type(net).__name__}")
+        lay = net.layout
+        if not net._embed_identity:
+            raise NotImplementedError(
+                "the fused trainer supports nn.Identity() embedding nets; train estimators with "
+                "torch embedding nets through estimator.loss(...).backward()")
+        P = lay.n_params
+        B = min(training_batch_size, n_train)
+        Bv = min(training_batch_size, n_val)
+        steps = n_train // B
+        vsteps = n_val // Bv if Bv > 0 else 0
+        rank, world = self._dist if self._dist is not None else (0, 1)
+
+        if not resume_training or not hasattr(self, "_opt_state"):
+            self._opt_state = torch.zeros(2 * P, dtype=torch.float32, device=dev)
+            self._opt_step = torch.zeros(2, dtype=torch.int32, device=dev)
+            self.epoch, self._val_loss = 0, float("Inf")
+            self._best_val_loss = float("Inf")
+            self._best_flat = None
+            self._epochs_since_last_improvement = 0
+
+        inp_all, cond_all = self._inp_cond()
+        train_idx = self.train_indices.to(dev)
+        val_idx = self.val_indices.to(dev)
+        # static buffers the epoch graph reads
+        perm_buf = torch.empty(steps * B, dtype=torch.int64, device=dev)
+        vperm_buf = torch.empty(max(vsteps * Bv, 1), dtype=torch.int64, device=dev)
+        grad = torch.zeros(P, dtype=torch.float32, device=dev)
+        n_part = lib.sbi_b200_nsf_vjp_parts(B)
+        gpart = net._gpart(n_part)
+        loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
+        val_lp = torch.empty(max(vsteps * Bv, 1), dtype=torch.float32, device=dev)
+        stats = torch.zeros(4, dtype=torch.float32, device=dev)   # train nll sum, bad, val nll sum, val bad
+        mask = net.net._mask
+        max_norm = float(clip_max_norm) if clip_max_norm is not None else 0.0
+
+        def run_epoch():
+            """All kernels of one epoch on the current stream (graph-capturable)."""
+            m_tr = net._model(nbuf=3)
+            loss_acc.zero_()
+            for s in range(steps):
+                idx = perm_buf[s * B:(s + 1) * B]
+                rows = L.Rows(inp_all.data_ptr(), cond_all.data_ptr(), idx.data_ptr(), B, 0)
+                L.check(lib.sbi_b200_nsf_vjp(C.byref(m_tr), C.byref(rows), None, -1.0 / (B * world),
+                                             None, L.ptr(gpart), None, None, L.ptr(loss_acc),
+                                             L.stream_ptr()), "nsf_vjp")
+                L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad),
+                                                     L.stream_ptr()), "reduce_partials")
+                if world > 1:
+                    torch.distributed.all_reduce(grad)
+                L.check(lib.sbi_b200_adam_clip_step(
+                    L.ptr(net.flat.data), L.ptr(grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
+                    L.ptr(mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0,
+                    L.stream_ptr()), "adam_clip_step")
+            stats[0:2].copy_(loss_acc)
+            if vsteps > 0:
+                m_ev = net._model(nbuf=2)
+                rows = L.Rows(inp_all.data_ptr(), cond_all.data_ptr(), vperm_buf.data_ptr(),
+                              vsteps * Bv, 0)
+                L.check(lib.sbi_b200_nsf_logprob(C.byref(m_ev), C.byref(rows), L.ptr(val_lp), None,
+                                                 L.stream_ptr()), "nsf_logprob")
+                finite = torch.isfinite(val_lp)
+                stats[2] = -(torch.where(finite, val_lp, torch.zeros_like(val_lp))).sum()
+                stats[3] = (~finite).sum().float()
+
+        def fill_perms():
+            perm_buf.copy_(train_idx[torch.randperm(n_train, device=dev)[:steps * B]])
+            if vsteps > 0:
+                vperm_buf.copy_(val_idx[torch.randperm(n_val, device=dev)[:vsteps * Bv]])
+
+        # warm-up (also sets kernel attributes) on a throw-away copy of the state, then capture
+        graph = None
+        if world == 1:
+            snap = (net.flat.data.clone(), self._opt_state.clone(), self._opt_step.clone())
+            fill_perms()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run_epoch()
+            torch.cuda.current_stream().wait_stream(side)
+            net.flat.data.copy_(snap[0]); self._opt_state.copy_(snap[1]); self._opt_step.copy_(snap[2])
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run_epoch()
+            net.flat.data.copy_(snap[0]); self._opt_state.copy_(snap[1]); self._opt_step.copy_(snap[2])
+
+        def converged() -> bool:
+            """base.py:1254-1284."""
+            if self.epoch == 0 or self._val_loss < self._best_val_loss:
+                self._best_val_loss = self._val_loss
+                self._epochs_since_last_improvement = 0
+                self._best_flat = net.flat.data.clone()
+            else:
+                self._epochs_since_last_improvement += 1
+            if self._epochs_since_last_improvement > stop_after_epochs - 1:
+                net.flat.data.copy_(self._best_flat)
+                return True
+            return False
+
+        while self.epoch <= max_num_epochs and not converged():
+            t0 = time.time()
+            fill_perms()
+            if graph is not None:
+                graph.replay()
+            else:
+                run_epoch()
+            s = stats.tolist()   # the one host sync of the epoch
+            if world > 1:
+                t = torch.tensor(s, device=dev)
+                torch.distributed.all_reduce(t)
+                s = (t / world).tolist()
+            if s[1] > 0 or s[3] > 0:
+                raise AssertionError("NaN/Inf present in NPE loss.")
+            train_loss = s[0] / (steps * B)
+            self._val_loss = s[2] / (vsteps * Bv) if vsteps > 0 else float("nan")
+            self._summary["training_loss"].append(train_loss)
+            self._summary["validation_loss"].append(self._val_loss)
+            self._summary["epoch_durations_sec"].append(time.time() - t0)
+            self.epoch += 1
+
+        if self.epoch > max_num_epochs:   # base.py:1122-1129
+            if self._val_loss < self._best_val_loss:
+                self._best_val_loss = self._val_loss
+                self._best_flat = net.flat.data.clone()
+            elif self._best_flat is not None:
+                net.flat.data.copy_(self._best_flat)
+            warnings.warn(f"Maximum number of epochs `max_num_epochs={max_num_epochs}` reached, "
+                          "but network has not yet fully converged.", stacklevel=2)
+        self._summary["epochs_trained"].append(self.epoch)
+        self._summary["best_validation_loss"].append(self._best_val_loss)
+        net.zero_grad(set_to_none=True)
+        return deepcopy(net)
+
+    @property
+    def summary(self):
+        return self._summary
+
+
+class NPE(_FlowTrainer):
+    """Neural posterior estimation, first round (reference: NPE_C, npe_c.py:91 / npe_base.py)."""
+    _swap = False
+
+    def build_posterior(self, density_estimator: Optional[nn.Module] = None, prior=None,
+                        sample_with: str = "direct", **kwargs):
+        from .posteriors import DirectPosterior
+        if sample_with != "direct":
+            raise NotImplementedError("NPE.build_posterior supports sample_with='direct'")
+        est = density_estimator if density_estimator is not None else self._neural_net
+        prior = prior if prior is not None else self._prior
+        return DirectPosterior(deepcopy(est), prior, device=self._device)
+
+
+NPE_C = NPE
+SNPE = NPE
+
+
+class NLE(_FlowTrainer):
+    """Neural likelihood estimation (reference: NLE_A, nle_base.py:190-272, _loss :380-392)."""
+    _swap = True
+
+
+NLE_A = NLE
+SNLE = NLE

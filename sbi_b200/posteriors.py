@@ -1,0 +1,228 @@
+"""Posteriors and the accept/reject loop on the device, mirroring the reference.
+
+`DirectPosterior` mirrors /root/reference/sbi/inference/posteriors/direct_posterior.py
+(sample :142-216, log_prob :308-386, leakage_correction :467-523); `accept_reject_sample`
+mirrors /root/reference/sbi/samplers/rejection/rejection.py:230-457 (same adaptive batch-size
+rule :406-409, same truncation to the first `num_samples` accepted draws, same acceptance
+rate bookkeeping) and `within_support` /root/reference/sbi/utils/sbiutils.py:729-766.
+Proposals come out of the inverse-flow kernel; support checks and compaction are torch
+device ops (no per-iteration host list appends; one host sync per loop iteration for the
+remaining-count, as the loop's data-dependent trip count requires).
+"""
+from __future__ import annotations
+
+import logging
+import time
+import warnings
+from math import log
+from typing import Any, Callable, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .estimators import NSFEstimator
+
+
+def within_support(distribution: Any, samples: Tensor) -> Tensor:
+    """sbiutils.py:729-766."""
+    try:
+        check = distribution.support.check(samples)
+        if check.shape == samples.shape:
+            check = torch.all(check, dim=-1)
+        return check
+    except (NotImplementedError, AttributeError):
+        return torch.isfinite(distribution.log_prob(samples))
+
+
+def prior_to_device(prior, device):
+    """Move a torch.distributions prior to `device` (the reference requires the user to do
+    this, inference_on_device_test.py; we do it for the common families)."""
+    if prior is None:
+        return None
+    try:
+        import torch.distributions as td
+        if isinstance(prior, td.MultivariateNormal):
+            return td.MultivariateNormal(prior.loc.to(device), covariance_matrix=prior.covariance_matrix.to(device))
+        if isinstance(prior, td.Independent):
+            return td.Independent(prior_to_device(prior.base_dist, device), prior.reinterpreted_batch_ndims)
+        if isinstance(prior, td.Uniform):
+            return td.Uniform(prior.low.to(device), prior.high.to(device), validate_args=False)
+        if isinstance(prior, td.Normal):
+            return td.Normal(prior.loc.to(device), prior.scale.to(device))
+    except Exception:   # pragma: no cover
+        pass
+    if hasattr(prior, "to"):
+        try:
+            prior.to(device)
+        except Exception:
+            pass
+    return prior
+
+
+@torch.no_grad()
+def accept_reject_sample(
+    proposal: Callable, accept_reject_fn: Callable, num_samples: int, num_xos: int = 1,
+    show_progress_bars: bool = False, warn_acceptance: float = 0.01,
+    sample_for_correction_factor: bool = False, max_sampling_batch_size: int = 10_000,
+    proposal_sampling_kwargs: Optional[dict] = None, alternative_method: Optional[str] = None,
+    max_sampling_time: Optional[float] = None, return_partial_on_timeout: bool = False,
+    **kwargs,
+) -> Tuple[Tensor, Tensor]:
+    """rejection.py:230-457: draw from `proposal`, keep what `accept_reject_fn` accepts, until
+    `num_samples` per observation are collected.  Returns (samples (num_samples, num_xos, D),
+    acceptance rate per observation)."""
+    if kwargs:
+        logging.warning(f"Unused arguments passed to accept_reject_sample: {list(kwargs)}")
+    proposal_sampling_kwargs = proposal_sampling_kwargs or {}
+    num_remaining = num_samples
+    accepted = [[] for _ in range(num_xos)]
+    sampling_batch_size = min(num_samples, max_sampling_batch_size)
+    num_sampled_total = None
+    num_samples_possible = 0
+    leakage_warning_raised = False
+    acceptance_rate = torch.full((num_xos,), float("nan"))
+    start = time.time()
+    candidates = None
+    while num_remaining > 0:
+        if max_sampling_time is not None and (time.time() - start) > max_sampling_time:
+            num_collected = min(sum(s.shape[0] for s in accepted[i]) for i in range(num_xos))
+            if return_partial_on_timeout and num_collected > 0:
+                warnings.warn(f"Timeout exceeded after collecting {num_collected}/{num_samples}"
+                              " samples. Returning partial results.", stacklevel=2)
+                samples = [torch.cat(accepted[i], dim=0)[:num_collected] for i in range(num_xos)]
+                return torch.stack(samples, dim=1), acceptance_rate
+            raise RuntimeError(
+                "Sampling aborted early because rejection sampling exceeded max_sampling_time. "
+                "This is likely due to extremely low acceptance.")
+        candidates = proposal(torch.Size((sampling_batch_size,)), **proposal_sampling_kwargs)
+        are_accepted = accept_reject_fn(candidates).reshape(sampling_batch_size, num_xos)
+        cands = candidates.reshape(sampling_batch_size, num_xos, *candidates.shape[candidates.ndim - 1:])
+        for i in range(num_xos):
+            accepted[i].append(cands[are_accepted[:, i], i])
+        num_accepted = are_accepted.sum(dim=0)
+        num_sampled_total = num_accepted.clone() if num_sampled_total is None else num_sampled_total + num_accepted
+        num_samples_possible += sampling_batch_size
+        min_num_accepted = int(num_accepted.min().item())   # the loop's one host sync
+        num_remaining -= min_num_accepted
+        acceptance_rate = num_sampled_total.float() / num_samples_possible
+        min_acceptance_rate = float(acceptance_rate.min().item())
+        sampling_batch_size = min(
+            max_sampling_batch_size,
+            max(int(1.5 * num_remaining / max(min_acceptance_rate, 1e-12)), 100))
+        if (num_samples_possible > (sampling_batch_size - 1) and min_acceptance_rate < warn_acceptance
+                and not leakage_warning_raised):
+            if sample_for_correction_factor:
+                logging.warning(
+                    f"Drawing samples from posterior to estimate the normalizing constant for "
+                    f"`log_prob()`. However, only {min_acceptance_rate:.3%} posterior samples are "
+                    f"within the prior support. It may take a long time to collect the remaining "
+                    f"{num_remaining} samples.")
+            else:
+                msg = (f"Only {min_acceptance_rate:.3%} proposal samples are accepted. It may take "
+                       f"a long time to collect the remaining {num_remaining} samples.")
+                if alternative_method is not None:
+                    msg += f" Alternatively, consider switching to `{alternative_method}`."
+                logging.warning(msg)
+            leakage_warning_raised = True
+    samples = [torch.cat(accepted[i], dim=0)[:num_samples] for i in range(num_xos)]
+    samples = torch.stack(samples, dim=1)
+    samples = samples.reshape(num_samples, *candidates.shape[1:])
+    assert samples.shape[0] == num_samples
+    return samples, acceptance_rate.to(samples.device)
+
+
+class DirectPosterior:
+    """p(theta | x) represented by the trained estimator itself (NPE)."""
+
+    def __init__(self, posterior_estimator: NSFEstimator, prior, max_sampling_batch_size: int = 10_000,
+                 device: Optional[str] = None, x_shape=None, enable_transform: bool = True):
+        self.posterior_estimator = posterior_estimator
+        self._device = device or str(posterior_estimator.flat.device)
+        self.posterior_estimator.to(self._device)
+        self.prior = prior_to_device(prior, self._device)
+        self.max_sampling_batch_size = max_sampling_batch_size
+        self._leakage_density_correction_factor = None
+        self.default_x = None
+
+    def set_default_x(self, x: Tensor):
+        self.default_x = x.to(self._device)
+        self._leakage_density_correction_factor = None
+        return self
+
+    def _x_else_default_x(self, x):
+        if x is not None:
+            return torch.as_tensor(x, dtype=torch.float32).to(self._device)
+        if self.default_x is None:
+            raise ValueError("Context `x` needed when a default has not been set. "
+                             "If you'd like to have a default, use the `.set_default_x()` method.")
+        return self.default_x
+
+    def _batch_x(self, x: Tensor) -> Tensor:
+        cs = self.posterior_estimator.condition_shape
+        if x.shape == cs:
+            x = x.unsqueeze(0)
+        return x.reshape(-1, *cs)
+
+    def sample(self, sample_shape=torch.Size(), x: Optional[Tensor] = None,
+               max_sampling_batch_size: int = 10_000, show_progress_bars: bool = False,
+               reject_outside_prior: bool = True, max_sampling_time: Optional[float] = None,
+               return_partial_on_timeout: bool = False) -> Tensor:
+        num_samples = torch.Size(sample_shape).numel()
+        x = self._batch_x(self._x_else_default_x(x))
+        if x.shape[0] > 1:
+            raise ValueError(".sample() supports only `batchsize == 1`. If you intend "
+                             "to sample multiple observations, use `.sample_batched()`.")
+        if max_sampling_batch_size is None:
+            max_sampling_batch_size = self.max_sampling_batch_size
+        if reject_outside_prior and self.prior is not None:
+            samples = accept_reject_sample(
+                proposal=self.posterior_estimator.sample,
+                accept_reject_fn=lambda theta: within_support(self.prior, theta),
+                num_samples=num_samples, show_progress_bars=show_progress_bars,
+                max_sampling_batch_size=max_sampling_batch_size,
+                proposal_sampling_kwargs={"condition": x},
+                alternative_method="build_posterior(..., sample_with='mcmc')",
+                max_sampling_time=max_sampling_time,
+                return_partial_on_timeout=return_partial_on_timeout)[0]
+        else:
+            samples = self.posterior_estimator.sample(torch.Size([num_samples]), condition=x)
+        return samples[:, 0].reshape(*torch.Size(sample_shape), -1)
+
+    def log_prob(self, theta: Tensor, x: Optional[Tensor] = None, norm_posterior: bool = True,
+                 track_gradients: bool = False, leakage_correction_params: Optional[dict] = None) -> Tensor:
+        x = self._batch_x(self._x_else_default_x(x))
+        if x.shape[0] > 1:
+            raise ValueError(".log_prob() supports only `batchsize == 1`. If you intend "
+                             "to evaluate given multiple observations, use `.log_prob_batched()`.")
+        theta = torch.as_tensor(theta, dtype=torch.float32).to(self._device)
+        if theta.dim() == 1:
+            theta = theta.unsqueeze(0)
+        self.posterior_estimator.eval()
+        with torch.set_grad_enabled(track_gradients):
+            unnorm = self.posterior_estimator.log_prob(theta.unsqueeze(1), condition=x).squeeze(dim=1)
+            if self.prior is not None:
+                inside = within_support(self.prior, theta)
+                unnorm = torch.where(inside, unnorm,
+                                     torch.tensor(float("-inf"), dtype=torch.float32, device=theta.device))
+            log_factor = (log(self.leakage_correction(x=x, **(leakage_correction_params or {})))
+                          if norm_posterior and self.prior is not None else 0)
+            return unnorm - log_factor
+
+    @torch.no_grad()
+    def leakage_correction(self, x: Tensor, num_rejection_samples: int = 10_000,
+                           force_update: bool = False, show_progress_bars: bool = False,
+                           rejection_sampling_batch_size: int = 10_000) -> Tensor:
+        def acceptance_at(xx):
+            return accept_reject_sample(
+                proposal=self.posterior_estimator.sample,
+                accept_reject_fn=lambda theta: within_support(self.prior, theta),
+                num_samples=num_rejection_samples, sample_for_correction_factor=True,
+                max_sampling_batch_size=rejection_sampling_batch_size,
+                proposal_sampling_kwargs={"condition": self._batch_x(xx)})[1]
+
+        is_new_x = self.default_x is None or (x is not self.default_x and (x != self.default_x).any())
+        if is_new_x:
+            return acceptance_at(x)
+        if self._leakage_density_correction_factor is None or force_update:
+            self._leakage_density_correction_factor = acceptance_at(self.default_x)
+        return self._leakage_density_correction_factor

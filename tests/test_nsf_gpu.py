@@ -1,0 +1,118 @@
+"""Parity of the sm_100a NSF kernels against the CPU oracle (through the C ABI).
+
+Tolerances (fp32 kernels vs. the fp64 oracle; the fp32 oracle's own error against fp64 is
+printed next to it):  |dlogp| <= 2e-3 absolute on log-probs of magnitude O(10..50),
+samples |dx| <= 2e-3, parameter gradients <= 2e-3 relative to the gradient's max-norm.
+"""
+import pytest
+import torch
+
+from tests.helpers import b200_from_oracle, oracle_nsf
+
+pytestmark = pytest.mark.gpu
+
+LOGP_TOL = 2e-3
+GRAD_TOL = 2e-3
+
+
+def _flat_grad_from_oracle(est, flow):
+    sd = {k: p.grad for k, p in flow.named_parameters()}
+    return est.layout.pack(sd)
+
+
+@pytest.mark.parametrize("D,C,R", [(10, 10, 257), (2, 2, 64), (3, 2, 1000), (10, 10, 20000), (5, 7, 33)])
+def test_logprob_matches_oracle(cuda_lib, D, C, R):
+    flow, theta, x = oracle_nsf(D, C, n=max(R, 500))
+    est = b200_from_oracle(flow, theta, x)
+    inp, cond = theta[:R] * 1.5, x[:R]        # some rows leave [-3,3] -> linear tails
+    with torch.no_grad():
+        ref64 = flow.double().log_prob(inp.double(), cond.double())[0]
+        ref32 = flow.float().log_prob(inp, cond)[0]
+        got = est.log_prob(inp.cuda(), cond.cuda())[0].cpu()
+    err = (got.double() - ref64).abs().max().item()
+    err32 = (ref32.double() - ref64).abs().max().item()
+    print(f"D={D} C={C} R={R}: kernel err {err:.3e}  torch-fp32 err {err32:.3e}")
+    assert torch.isfinite(got).all()
+    assert err <= LOGP_TOL
+
+
+def test_logprob_shared_condition_and_noise(cuda_lib):
+    flow, theta, x = oracle_nsf(10, 10)
+    est = b200_from_oracle(flow, theta, x)
+    xo = x[:1]
+    with torch.no_grad():
+        ref = flow.double().log_prob(theta[:300].double().unsqueeze(1), xo.double())[:, 0]
+        got = est.log_prob(theta[:300].cuda().unsqueeze(1), xo.cuda())[:, 0].cpu()
+        z_ref = flow.inverse_transform(theta[:300].double(), xo.double())
+        z = est.inverse_transform(theta[:300].cuda(), xo.cuda()).cpu()
+    assert (got.double() - ref).abs().max() <= LOGP_TOL
+    assert (z.double() - z_ref).abs().max() <= 1e-3
+
+
+def _oracle_grads(flow, est, inp, cond, g, dtype):
+    flow = flow.to(dtype)
+    flow.zero_grad()
+    i = inp.to(dtype).detach().requires_grad_(True)
+    c = cond.to(dtype).detach().requires_grad_(True)
+    lp = flow.log_prob(i, c)[0]
+    (lp * g.to(dtype)).sum().backward()
+    return _flat_grad_from_oracle(est, flow).double(), i.grad.double(), c.grad.double()
+
+
+@pytest.mark.parametrize("D,C,R", [(10, 10, 256), (3, 2, 77), (2, 2, 31), (10, 10, 4096)])
+def test_vjp_matches_oracle_autograd(cuda_lib, D, C, R):
+    """Gradients wrt parameters, inputs and conditions vs the fp64 oracle autograd.  The bar is
+    GRAD_TOL of the gradient's max-norm, or 4x the error torch's own fp32 autograd makes against
+    fp64 on the same problem, whichever is larger (a few rows sit on steep spline segments
+    where fp32 itself loses digits)."""
+    flow, theta, x = oracle_nsf(D, C, n=max(R, 500))
+    est = b200_from_oracle(flow, theta, x)
+    inp, cond = theta[:R] * 1.3, x[:R]
+    g = torch.randn(R, dtype=torch.float64)
+    ref32 = _oracle_grads(flow, est, inp, cond, g, torch.float32)
+    ref64 = _oracle_grads(flow, est, inp, cond, g, torch.float64)
+
+    inp_c = inp.float().cuda().requires_grad_(True)
+    cond_c = cond.float().cuda().requires_grad_(True)
+    est.zero_grad()
+    lpc = est.log_prob(inp_c, cond_c)[0]
+    (lpc * g.float().cuda()).sum().backward()
+    got = (est.flat.grad.cpu().double(), inp_c.grad.cpu().double(), cond_c.grad.cpu().double())
+    mask = est.net._mask.cpu().bool()
+    assert (got[0][~mask] == 0).all(), "padding entries must receive zero gradient"
+    for name, a, r32, r64 in zip(("param", "input", "cond"), got, ref32, ref64):
+        scale = r64.abs().max().item()
+        err = (a - r64).abs().max().item() / scale
+        err32 = (r32 - r64).abs().max().item() / scale
+        print(f"D={D} R={R} {name}-grad: kernel rel err {err:.3e}  torch-fp32 rel err {err32:.3e}")
+        assert err <= max(GRAD_TOL, 4 * err32), name
+
+
+@pytest.mark.parametrize("D,C,R,B", [(10, 10, 1000, 1), (3, 2, 50, 4), (2, 2, 20000, 1)])
+def test_inverse_matches_oracle(cuda_lib, D, C, R, B):
+    flow, theta, x = oracle_nsf(D, C)
+    est = b200_from_oracle(flow, theta, x)
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(B * R, D, generator=g)
+    cond = x[:B]
+    with torch.no_grad():
+        emb = flow.net._embedding_net(cond.double())
+        ctx = emb.repeat_interleave(R, dim=0)
+        ref, ld_ref = flow.double().net._transform.inverse(noise.double(), context=ctx)
+        got, ld = est.inverse_flow(noise.cuda(), cond.cuda(), R)
+    err = (got.cpu().double() - ref).abs().max().item()
+    eld = (ld.cpu().double() - ld_ref).abs().max().item()
+    print(f"inverse D={D}: x err {err:.3e}  logabsdet err {eld:.3e}")
+    assert err <= 2e-3 and eld <= 5e-3
+
+
+def test_sample_shapes_and_roundtrip(cuda_lib):
+    flow, theta, x = oracle_nsf(10, 10)
+    est = b200_from_oracle(flow, theta, x)
+    cond = x[:3].cuda()
+    s = est.sample((7, 2), cond)
+    assert s.shape == (7, 2, 3, 10)
+    s2, lp2 = est.sample_and_log_prob(torch.Size((50,)), cond)
+    assert s2.shape == (50, 3, 10) and lp2.shape == (50, 3)
+    lp = est.log_prob(s2, cond)
+    assert (lp - lp2).abs().max() <= 5e-3
