@@ -103,15 +103,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ reference arm
-def cpu_reference_train(steps, warmup, max_seconds=None):
+def cpu_reference_train(steps, warmup, max_seconds=None, threads=None):
     """The reference's CPU training step (oracle port of sbi's loop on the nflows port):
     DataLoader(SubsetRandomSampler, drop_last) batch of 4096 -> loss -> backward ->
-    clip_grad_norm_(5) -> Adam.  Returns (samples/s, seconds per step, cores, steps done)."""
+    clip_grad_norm_(5) -> Adam.  The intra-op thread count is the best of a quick probe over
+    {16, 32, 64, all cores} (the tiny ATen ops of this path get slower with too many threads).
+    Returns (samples/s, seconds per step, threads used, steps done)."""
     import torch
     from torch.nn.utils.clip_grad import clip_grad_norm_
     from oracle import sbi_port
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     theta, x = make_data(NUM_SIMS, DIM)
     torch.manual_seed(0)
     tr = sbi_port.ReferenceTrainer(sbi_port.build_nsf)
@@ -119,15 +120,15 @@ def cpu_reference_train(steps, warmup, max_seconds=None):
     net = sbi_port.build_nsf(theta[tr.train_indices], x[tr.train_indices])
     tr.net = net
     opt = torch.optim.Adam(list(net.parameters()), lr=5e-4)
-    done, t_timed, it = 0, 0.0, iter(train_loader)
-    t_begin = time.perf_counter()
-    for i in range(warmup + steps):
+    it = [iter(train_loader)]
+
+    def one_step():
         t0 = time.perf_counter()
         try:
-            batch = next(it)
+            batch = next(it[0])
         except StopIteration:
-            it = iter(train_loader)
-            batch = next(it)
+            it[0] = iter(train_loader)
+            batch = next(it[0])
         opt.zero_grad()
         losses = tr._losses(batch)
         loss = torch.mean(losses)
@@ -135,21 +136,37 @@ def cpu_reference_train(steps, warmup, max_seconds=None):
         loss.backward()
         clip_grad_norm_(net.parameters(), max_norm=5.0)
         opt.step()
-        dt = time.perf_counter() - t0
+        return time.perf_counter() - t0
+
+    if threads is None:
+        cands = sorted({min(c, cores) for c in (16, 32, 64, cores)})
+        best = None
+        for c in cands:
+            torch.set_num_threads(c)
+            one_step()
+            dt = one_step()
+            if best is None or dt < best[0]:
+                best = (dt, c)
+        threads = best[1]
+    torch.set_num_threads(threads)
+    done, t_timed = 0, 0.0
+    t_begin = time.perf_counter()
+    for i in range(warmup + steps):
+        dt = one_step()
         if i >= warmup:
             done += 1
             t_timed += dt
         if max_seconds is not None and time.perf_counter() - t_begin > max_seconds and done >= 2:
             break
     sps = done * BATCH / t_timed
-    return sps, t_timed / done, cores, done
+    return sps, t_timed / done, threads, done
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sps, sec, cores, done = cpu_reference_train(args.steps, args.warmup)
+    sps, sec, cores, done = cpu_reference_train(args.steps, max(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": sec * 1e3,

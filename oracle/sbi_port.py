@@ -189,7 +189,9 @@ class NFlowsFlow(nn.Module):
         condition = condition.expand(batch_shape + self.condition_shape)
         input = input.reshape(-1, input.shape[-1])
         condition = condition.reshape(-1, *self.condition_shape)
-        noise, _ = self.net._transform(input, context=self.net._embedding_net(condition))
+        # NB: exactly like the reference (nflows_flow.py:73) the RAW condition is passed -- the
+        # embedding net / condition z-scoring is NOT applied on this code path.
+        noise, _ = self.net._transform(input, context=condition)
         return noise.reshape(batch_shape + (noise.shape[-1],))
 
     def log_prob(self, input: Tensor, condition: Tensor) -> Tensor:

@@ -50,6 +50,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
+// producer-side wait: back off between probes so the spinning lane does not eat issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(20);
+  }
+}
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (complete_tx).
 // bytes must be a multiple of 16; both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
@@ -84,7 +100,7 @@ struct WPipe {
   __device__ __forceinline__ void produce(const float* src0, int n0, const float* src1 = nullptr,
                                           int n1 = 0) {
     int s = slot();
-    mbar_wait(&empty[s], phase() ^ 1u);
+    mbar_wait_backoff(&empty[s], phase() ^ 1u);
     float* dst = buf + (size_t)s * cap;
     mbar_arrive_expect_tx(&full[s], (uint32_t)(n0 + n1) * 4u);
     bulk_g2s(dst, src0, (uint32_t)n0 * 4u, &full[s]);

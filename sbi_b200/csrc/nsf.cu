@@ -33,12 +33,14 @@ nsf_logprob_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constan
     return;
   }
 
-  const float ld_const = lu_logdet_total(m) + m.ld_zscore - 0.5f * (float)m.D * 1.8378770664093453f;
+  const float ld_const = lu_logdet_total(m, sm + L.PRM) + m.ld_zscore -
+                         0.5f * (float)m.D * 1.8378770664093453f;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * TM;
     load_tile<TM>(m, rows, row0, sm, L, false);
     for (int l = 0; l < m.T; ++l) {
       const NsfLayerView v = layer_view(m, l);
+      lu_prepare(m, v, sm, L);
       gather_identity<TM>(m, v, sm + L.Z, sm + L.U);
       float* hf = cond_forward<kConsumer, TM, RN, false>(m, v, pipe, sm, L);
       spline_forward<kConsumer, TM, RN, false>(m, v, pipe, sm, L, hf);
@@ -90,13 +92,15 @@ nsf_inverse_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constan
     return;
   }
 
-  const float ld_const = -lu_logdet_total(m) - m.ld_zscore;
+  const float ld_const = -lu_logdet_total(m, sm + L.PRM) - m.ld_zscore;
   const float* __restrict__ st = m.d_stats;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * TM;
     load_tile<TM>(m, rows, row0, sm, L, true);
     for (int l = m.T - 1; l >= 0; --l) {
       const NsfLayerView v = layer_view(m, l);
+      lu_prepare(m, v, sm, L);
+      consumer_sync();
       lu_inverse<TM>(m, v, sm, L);
       gather_identity<TM>(m, v, sm + L.Z, sm + L.U);
       float* hf = cond_forward<kConsumer, TM, RN, false>(m, v, pipe, sm, L);
@@ -129,24 +133,21 @@ __device__ __forceinline__ void lu_backward(const sbi_nsf_model& m, const NsfLay
                                             float* __restrict__ gp, bool accumulate) {
   constexpr int LD = Tile<TM>::LD;
   if (!__ldg(v.LT + SBI_L_HAS_LU)) return;
-  const float* __restrict__ P = m.d_params;
   const int D = m.D;
+  const LuView w = lu_view(m, sm, L);
   float* dZ = sm + L.dZ;
   float* Y = sm + L.Y;     // y = U v
   float* DY = sm + L.Y2;   // dy = L^T dz
   const float* GR = sm + L.GR;
   const int o_lo = __ldg(v.LT + SBI_L_LU_LOWER), o_up = __ldg(v.LT + SBI_L_LU_UPPER);
   const int o_dg = __ldg(v.LT + SBI_L_LU_DIAG), o_bi = __ldg(v.LT + SBI_L_LU_BIAS);
-  const float* lo = P + o_lo;
-  const float* up = P + o_up;
-  const float* dg = P + o_dg;
   for (int t = threadIdx.x; t < D * TM; t += kConsumerThreads) {
     const int i = t / TM, r = t % TM;
-    float a = lu_diag(dg, i) * V[i * LD + r];
-    for (int j = i + 1; j < D; ++j) a = fmaf(lu_upper(up, D, i, j), V[j * LD + r], a);
+    float a = 0.f;
+    for (int j = i; j < D; ++j) a = fmaf(w.U[i * D + j], V[j * LD + r], a);
     Y[i * LD + r] = a;
     float b = dZ[i * LD + r];
-    for (int k = i + 1; k < D; ++k) b = fmaf(lu_lower(lo, k, i), dZ[k * LD + r], b);
+    for (int k = i + 1; k < D; ++k) b = fmaf(w.Lw[k * D + i], dZ[k * LD + r], b);
     DY[i * LD + r] = b;
   }
   consumer_sync();
@@ -168,8 +169,7 @@ __device__ __forceinline__ void lu_backward(const sbi_nsf_model& m, const NsfLay
           a = fmaf(DY[i * LD + r], V[i * LD + r], a);
           gs += GR[r];
         }
-        const float raw = __ldg(dg + i);
-        a = (a + gs / lu_diag(dg, i)) * sigmoid_f(raw);
+        a = (a + gs / w.diag[i]) * sigmoid_f(__ldg(m.d_params + o_dg + i));
         dst = gp + o_dg + i;
       }
     } else {
@@ -182,8 +182,8 @@ __device__ __forceinline__ void lu_backward(const sbi_nsf_model& m, const NsfLay
   consumer_sync();
   for (int t = threadIdx.x; t < D * TM; t += kConsumerThreads) {
     const int j = t / TM, r = t % TM;
-    float a = lu_diag(dg, j) * DY[j * LD + r];
-    for (int i = 0; i < j; ++i) a = fmaf(lu_upper(up, D, i, j), DY[i * LD + r], a);
+    float a = 0.f;
+    for (int i = 0; i <= j; ++i) a = fmaf(w.U[i * D + j], DY[i * LD + r], a);
     dZ[j * LD + r] = a;
   }
   consumer_sync();
@@ -215,13 +215,11 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
         }
         for (int l = m.T - 1; l >= 0; --l) {
           const NsfLayerView v = layer_view(m, l);
-          cond_forward<kProducer, TM, RN, true>(m, v, pipe, sm, L);
-          const float* WF = P + __ldg(v.LT + SBI_L_WF);
-          for (int f0 = 0; f0 < v.n_tr; f0 += m.nf_chunk) {
-            const int nfc = min(m.nf_chunk, v.n_tr - f0);
-            pipe.produce(WF + (size_t)f0 * m.PR * Hp, nfc * m.PR * Hp);
-          }
+          float* hf = cond_forward<kProducer, TM, RN, true>(m, v, pipe, sm, L);
+          final_layer<kProducer, TM, RN>(m, v, pipe, sm, L, hf);
           auto noop2 = [](int, int, float(&)[RK][4], bool) {};
+          dx_stage<kProducer, TM, RK>(pipe, P + __ldg(v.LT + SBI_L_WF), v.n_tr * m.PR, Hp,
+                                      m.nf_chunk * m.PR, nullptr, Hp, noop2);
           for (int b = m.NB - 1; b >= 0; --b) {
             const int* BT = v.LT + SBI_L_BLK0 + 6 * b;
             dx_stage<kProducer, TM, RK>(pipe, P + __ldg(BT + 2), Hp, Hp, m.rpc1, nullptr, Hp, noop2);
@@ -239,7 +237,8 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
 
   // ------------------------------------------------------------------ consumers
   const RqsConst rc = rqs_const(m);
-  const float ld_const = lu_logdet_total(m) + m.ld_zscore - 0.5f * (float)m.D * 1.8378770664093453f;
+  const float ld_const = lu_logdet_total(m, sm + L.PRM) + m.ld_zscore -
+                         0.5f * (float)m.D * 1.8378770664093453f;
   float* gp = gpart + (size_t)blockIdx.x * m.n_params;
   float* Z = sm + L.Z;
   float* U = sm + L.U;
@@ -256,7 +255,7 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
   float* dCTX = sm + L.dCTX;
   const float* __restrict__ st = m.d_stats;
 
-  for (int e = threadIdx.x; e < m.nf_chunk * m.PR * LD; e += kConsumerThreads) dPRM[e] = 0.f;
+  for (int e = threadIdx.x; e < m.TRmax * m.PR * LD; e += kConsumerThreads) dPRM[e] = 0.f;
 
   int iter = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
@@ -268,6 +267,7 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
       const NsfLayerView v = layer_view(m, l);
       for (int e = threadIdx.x; e < m.Dp * LD; e += kConsumerThreads)
         sm[L.ZS + l * m.Dp * LD + e] = Z[e];
+      lu_prepare(m, v, sm, L);
       gather_identity<TM>(m, v, Z, U);
       float* hf = cond_forward<kConsumer, TM, RN, false>(m, v, pipe, sm, L);
       spline_forward<kConsumer, TM, RN, false>(m, v, pipe, sm, L, hf);
@@ -316,56 +316,40 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
       const NsfLayerView v = layer_view(m, l);
       const float* ZSl = sm + L.ZS + l * m.Dp * LD;
       const float* VSl = sm + L.VS + l * m.Dp * LD;
+      lu_prepare(m, v, sm, L);
+      consumer_sync();
       lu_backward<TM>(m, v, sm, L, VSl, gp, accum);
       // recompute the conditioner from the saved layer input
       gather_identity<TM>(m, v, ZSl, U);
       float* hf = cond_forward<kConsumer, TM, RN, true>(m, v, pipe, sm, L);
-      // final layer + spline backward, chunked over transformed features
+      // final layer (all features) -> spline backward -> dW, dH
       {
         const int oWF = __ldg(v.LT + SBI_L_WF), oBF = __ldg(v.LT + SBI_L_BF);
-        for (int f0 = 0; f0 < v.n_tr; f0 += m.nf_chunk) {
-          const int nfc = min(m.nf_chunk, v.n_tr - f0);
-          const int N = nfc * m.PR;
-          const float* bf = P + oBF + f0 * m.PR;
-          const float* w = pipe.acquire();
-          gemm_fwd_chunk<TM, RN>(hf, Hp >> 2, w, Hp, N,
-                                 [&](int g, int ng, int r0, float(&acc)[RN][4]) {
-#pragma unroll
-                                   for (int i = 0; i < RN; ++i) {
-                                     const int n = g + i * ng;
-                                     const float b = __ldg(bf + n);
-                                     st4(PRM + n * LD + r0,
-                                         make_float4(acc[i][0] + b, acc[i][1] + b, acc[i][2] + b,
-                                                     acc[i][3] + b));
-                                   }
-                                 });
-          consumer_sync();
-          for (int t = threadIdx.x; t < nfc * TM; t += kConsumerThreads) {
-            const int f = t / TM, r = t % TM;
-            const int j = __ldg(v.trf + f0 + f);
-            const float gx = rqs_backward(PRM + f * m.PR * LD + r, LD, rc, ZSl[j * LD + r],
-                                          dZ[j * LD + r], GR[r], dPRM + f * m.PR * LD + r, LD);
-            dZ[j * LD + r] = gx;
-          }
-          consumer_sync();
-          gemm_dw<TM>(dPRM, N, hf, m.H, Hp, gp + oWF + (size_t)f0 * m.PR * Hp, gp + oBF + f0 * m.PR,
-                      accum);
-          const bool first = (f0 == 0);
-          gemm_dx_chunk<TM, RK>(dPRM, 0, N, w, Hp, Hp, [&](int k0, int r0, float(&acc)[RK][4]) {
-#pragma unroll
-            for (int j = 0; j < RK; ++j) {
-              float* p = dH + (k0 + j) * LD + r0;
-              float4 o = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-              if (!first) {
-                const float4 c = ld4(p);
-                o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
-              }
-              st4(p, o);
-            }
-          });
-          pipe.release();
-          consumer_sync();
+        const int N = v.n_tr * m.PR;
+        final_layer<kConsumer, TM, RN>(m, v, pipe, sm, L, hf);
+        for (int t = threadIdx.x; t < v.n_tr * TM; t += kConsumerThreads) {
+          const int f = t / TM, r = t % TM;
+          const int j = __ldg(v.trf + f);
+          const float gx = rqs_backward(PRM + f * m.PR * LD + r, LD, rc, ZSl[j * LD + r],
+                                        dZ[j * LD + r], GR[r], dPRM + f * m.PR * LD + r, LD);
+          dZ[j * LD + r] = gx;
         }
+        consumer_sync();
+        gemm_dw<TM>(dPRM, N, hf, m.H, Hp, gp + oWF, gp + oBF, accum);
+        dx_stage<kConsumer, TM, RK>(
+            pipe, nullptr, N, Hp, m.nf_chunk * m.PR, dPRM, Hp,
+            [&](int k0, int r0, float(&acc)[RK][4], bool first) {
+#pragma unroll
+              for (int j = 0; j < RK; ++j) {
+                float* p = dH + (k0 + j) * LD + r0;
+                float4 o = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                if (!first) {
+                  const float4 c = ld4(p);
+                  o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+                }
+                st4(p, o);
+              }
+            });
       }
       // residual blocks, last to first.  dH = grad wrt HS[b+1]
       for (int b = m.NB - 1; b >= 0; --b) {
@@ -494,6 +478,7 @@ static int num_sms() {
 static int check_model(const sbi_nsf_model* m) {
   if (!m || !m->d_params || !m->d_layer_tab || !m->d_feat_tab || !m->d_stats) return SBI_EINVAL;
   if (m->D < 1 || m->C < 1 || m->H < 1 || m->T < 1 || m->KB < 2 || m->NB < 0) return SBI_EINVAL;
+  if (m->KB > kRqsMaxBins) return SBI_EINVAL;
   if (m->NB > SBI_NSF_MAX_BLOCKS) return SBI_EINVAL;
   if (m->Dp != round4(m->D) || m->Cp != round4(m->C) || m->Hp != round4(m->H)) return SBI_EINVAL;
   if (m->PR != round4(3 * m->KB - 1) || (m->IDp & 3) || m->nf_chunk < 1) return SBI_EINVAL;

@@ -23,7 +23,7 @@ enum Role { kProducer = 0, kConsumer = 1 };
 struct NsfSmem {
   int LD;
   // forward
-  int U, Z, H, A0, A1, PRM, LDF, Y, Y2, LDACC;
+  int U, Z, H, A0, A1, PRM, LDF, Y, Y2, LDACC, LUM;
   // training extras
   int ZS, VS, HS, A1S, T2S, SS, dZ, dU, dH, dT, dG, dPRM, GR, dCTX;
   int ring;        // float offset of the weight ring
@@ -37,17 +37,21 @@ __host__ __device__ inline NsfSmem nsf_smem_layout(const sbi_nsf_model& m, int T
   int rows = 0;
   auto take = [&](int n) { int o = rows * L.LD; rows += n; return o; };
   const int K0p = m.Cp + m.IDp;
-  const int prm = m.nf_chunk * m.PR;
+  const int prm = m.TRmax * m.PR;   // spline parameters of ALL transformed features
   L.U = take(K0p);
   L.Z = take(m.Dp);
   L.H = take(m.Hp);
+  // PRM aliases [A0 | A1 | extra]: the relu/hidden scratch is dead while the final layer runs
   L.A0 = take(m.Hp);
   L.A1 = take(m.Hp);
-  L.PRM = take(prm);
+  L.PRM = L.A0;
+  if (prm > 2 * m.Hp) take(prm - 2 * m.Hp);
   L.LDF = take(round4(m.TRmax));
   L.Y = take(m.Dp);
   L.Y2 = take(m.Dp);
   L.LDACC = take(1);
+  // dense LU factors of the current layer: [U D*D | L D*D | bias D | diag D] (+1 scalar)
+  L.LUM = take((2 * m.D * m.D + 2 * m.D + 4 + L.LD - 1) / L.LD);
   L.ZS = L.VS = L.HS = L.A1S = L.T2S = L.SS = 0;
   L.dZ = L.dU = L.dH = L.dT = L.dG = L.dPRM = L.GR = L.dCTX = 0;
   if (train) {
@@ -264,58 +268,96 @@ __device__ __forceinline__ float* cond_forward(const sbi_nsf_model& m, const Nsf
   return Hout;
 }
 
-// final layer + spline, chunked over transformed features (forward or inverse direction)
+// final layer: PRM[f*PR + i] = Wf H + bf for ALL transformed features, weights streamed in
+// chunks of nf_chunk features
+template <Role R, int TM, int RN>
+__device__ __forceinline__ void final_layer(const sbi_nsf_model& m, const NsfLayerView& v,
+                                            WPipe& pipe, float* sm, const NsfSmem& L,
+                                            const float* Hfin) {
+  constexpr int LD = Tile<TM>::LD;
+  const float* __restrict__ P = m.d_params;
+  float* PRM = sm + L.PRM;
+  const float* bf = P + __ldg(v.LT + SBI_L_BF);
+  fwd_stage<R, TM, RN>(pipe, P + __ldg(v.LT + SBI_L_WF), v.n_tr * m.PR, m.Hp, m.nf_chunk * m.PR, Hfin,
+                       [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
+#pragma unroll
+                         for (int i = 0; i < RN; ++i) {
+                           const int n = n0 + g + i * ng;
+                           const float b = __ldg(bf + n);
+                           st4(PRM + n * LD + r0, make_float4(acc[i][0] + b, acc[i][1] + b,
+                                                              acc[i][2] + b, acc[i][3] + b));
+                         }
+                       });
+}
+
+// final layer + spline on every transformed feature (forward or inverse direction)
 template <Role R, int TM, int RN, bool INVERSE>
 __device__ __forceinline__ void spline_forward(const sbi_nsf_model& m, const NsfLayerView& v,
                                                WPipe& pipe, float* sm, const NsfSmem& L,
                                                const float* Hfin) {
   constexpr int LD = Tile<TM>::LD;
-  const float* __restrict__ P = m.d_params;
-  const RqsConst rc = rqs_const(m);
-  float* PRM = sm + L.PRM;
-  float* Z = sm + L.Z;
-  float* LDF = sm + L.LDF;
-  const float* WF = P + __ldg(v.LT + SBI_L_WF);
-  const float* BF = P + __ldg(v.LT + SBI_L_BF);
-  for (int f0 = 0; f0 < v.n_tr; f0 += m.nf_chunk) {
-    const int nfc = min(m.nf_chunk, v.n_tr - f0);
-    const int N = nfc * m.PR;
-    const float* bf = BF + f0 * m.PR;
-    fwd_stage<R, TM, RN>(pipe, WF + (size_t)f0 * m.PR * m.Hp, N, m.Hp, N, Hfin,
-                         [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
-#pragma unroll
-                           for (int i = 0; i < RN; ++i) {
-                             const int n = n0 + g + i * ng;
-                             const float b = __ldg(bf + n);
-                             st4(PRM + n * LD + r0, make_float4(acc[i][0] + b, acc[i][1] + b,
-                                                                acc[i][2] + b, acc[i][3] + b));
-                           }
-                         });
-    if (R == kConsumer) {
-      for (int t = threadIdx.x; t < nfc * TM; t += kConsumerThreads) {
-        const int f = t / TM, r = t % TM;
-        const int j = __ldg(v.trf + f0 + f);
-        const float x = Z[j * LD + r];
-        float y, ld;
-        if (INVERSE) rqs_inverse(PRM + f * m.PR * LD + r, LD, rc, x, y, ld);
-        else rqs_forward(PRM + f * m.PR * LD + r, LD, rc, x, y, ld);
-        Z[j * LD + r] = y;
-        LDF[(f0 + f) * LD + r] = ld;
-      }
-      consumer_sync();
+  final_layer<R, TM, RN>(m, v, pipe, sm, L, Hfin);
+  if (R == kConsumer) {
+    const RqsConst rc = rqs_const(m);
+    const float* PRM = sm + L.PRM;
+    float* Z = sm + L.Z;
+    float* LDF = sm + L.LDF;
+    for (int t = threadIdx.x; t < v.n_tr * TM; t += kConsumerThreads) {
+      const int f = t / TM, r = t % TM;
+      const int j = __ldg(v.trf + f);
+      const float x = Z[j * LD + r];
+      float y, ld;
+      if (INVERSE) rqs_inverse(PRM + f * m.PR * LD + r, LD, rc, x, y, ld);
+      else rqs_forward(PRM + f * m.PR * LD + r, LD, rc, x, y, ld);
+      Z[j * LD + r] = y;
+      LDF[f * LD + r] = ld;
     }
+    consumer_sync();
   }
 }
 
-// LULinear helpers (restating nflows LULinear, oracle/nflows_port/transforms/lu.py)
-__device__ __forceinline__ float lu_lower(const float* lo, int i, int j) {   // j < i
-  return __ldg(lo + i * (i - 1) / 2 + j);
+// LULinear (restating nflows LULinear, oracle/nflows_port/transforms/lu.py).  The dense factors
+// of the current layer are built once per layer-tile in shared memory:
+//   LUM = [U (D*D, upper incl. diag = softplus(raw)+eps) | L (D*D, strictly lower) | bias D | diag D]
+struct LuView {
+  const float* U;
+  const float* Lw;
+  const float* bias;
+  const float* diag;
+};
+__device__ __forceinline__ LuView lu_view(const sbi_nsf_model& m, const float* sm, const NsfSmem& L) {
+  LuView w;
+  w.U = sm + L.LUM;
+  w.Lw = w.U + m.D * m.D;
+  w.bias = w.Lw + m.D * m.D;
+  w.diag = w.bias + m.D;
+  return w;
 }
-__device__ __forceinline__ float lu_upper(const float* up, int D, int i, int j) {   // j > i
-  return __ldg(up + i * D - i * (i + 1) / 2 + (j - i - 1));
-}
-__device__ __forceinline__ float lu_diag(const float* dg, int i) {
-  return softplus_f(__ldg(dg + i)) + 1e-3f;
+// no barrier inside: callers sync before the factors are read
+__device__ __forceinline__ void lu_prepare(const sbi_nsf_model& m, const NsfLayerView& v, float* sm,
+                                           const NsfSmem& L) {
+  if (!__ldg(v.LT + SBI_L_HAS_LU)) return;
+  const float* __restrict__ P = m.d_params;
+  const int D = m.D;
+  const float* lo = P + __ldg(v.LT + SBI_L_LU_LOWER);
+  const float* up = P + __ldg(v.LT + SBI_L_LU_UPPER);
+  const float* dg = P + __ldg(v.LT + SBI_L_LU_DIAG);
+  const float* bi = P + __ldg(v.LT + SBI_L_LU_BIAS);
+  float* U = sm + L.LUM;
+  float* Lw = U + D * D;
+  for (int t = threadIdx.x; t < D * D; t += kConsumerThreads) {
+    const int i = t / D, j = t % D;
+    float u = 0.f, l = 0.f;
+    if (j > i) u = __ldg(up + i * D - i * (i + 1) / 2 + (j - i - 1));
+    else if (j < i) l = __ldg(lo + i * (i - 1) / 2 + j);
+    else u = softplus_f(__ldg(dg + i)) + 1e-3f;
+    U[t] = u;
+    Lw[t] = l;
+    if (j == i) {
+      Lw[D * D + i] = __ldg(bi + i);        // bias
+      Lw[D * D + D + i] = u;                // diag
+    }
+  }
 }
 
 // LDACC[r] += sum_f LDF[f][r]  (this layer's spline log-dets, fixed order over features).
@@ -330,32 +372,28 @@ __device__ __forceinline__ void fold_ldf(const NsfLayerView& v, float* sm, const
   }
 }
 
-// z <- L (U z) + b
+// z <- L (U z) + b   (factors from lu_prepare)
 template <int TM>
 __device__ __forceinline__ void lu_forward(const sbi_nsf_model& m, const NsfLayerView& v,
                                            float* sm, const NsfSmem& L) {
   constexpr int LD = Tile<TM>::LD;
-  const float* __restrict__ P = m.d_params;
+  if (!__ldg(v.LT + SBI_L_HAS_LU)) return;
   const int D = m.D;
+  const LuView w = lu_view(m, sm, L);
   float* Z = sm + L.Z;
   float* Y = sm + L.Y;
-  if (!__ldg(v.LT + SBI_L_HAS_LU)) return;
-  const float* lo = P + __ldg(v.LT + SBI_L_LU_LOWER);
-  const float* up = P + __ldg(v.LT + SBI_L_LU_UPPER);
-  const float* dg = P + __ldg(v.LT + SBI_L_LU_DIAG);
-  const float* bi = P + __ldg(v.LT + SBI_L_LU_BIAS);
   for (int t = threadIdx.x; t < D * TM; t += kConsumerThreads) {
     const int i = t / TM, r = t % TM;
-    float a = lu_diag(dg, i) * Z[i * LD + r];
-    for (int j = i + 1; j < D; ++j) a = fmaf(lu_upper(up, D, i, j), Z[j * LD + r], a);
+    float a = 0.f;
+    for (int j = i; j < D; ++j) a = fmaf(w.U[i * D + j], Z[j * LD + r], a);
     Y[i * LD + r] = a;
   }
   consumer_sync();
   for (int t = threadIdx.x; t < D * TM; t += kConsumerThreads) {
     const int i = t / TM, r = t % TM;
     float a = Y[i * LD + r];
-    for (int j = 0; j < i; ++j) a = fmaf(lu_lower(lo, i, j), Y[j * LD + r], a);
-    Z[i * LD + r] = a + __ldg(bi + i);
+    for (int j = 0; j < i; ++j) a = fmaf(w.Lw[i * D + j], Y[j * LD + r], a);
+    Z[i * LD + r] = a + w.bias[i];
   }
   consumer_sync();
 }
@@ -365,41 +403,46 @@ template <int TM>
 __device__ __forceinline__ void lu_inverse(const sbi_nsf_model& m, const NsfLayerView& v,
                                            float* sm, const NsfSmem& L) {
   constexpr int LD = Tile<TM>::LD;
-  const float* __restrict__ P = m.d_params;
-  const int D = m.D;
   if (!__ldg(v.LT + SBI_L_HAS_LU)) return;
+  const int D = m.D;
+  const LuView w = lu_view(m, sm, L);
   float* Z = sm + L.Z;
-  const float* lo = P + __ldg(v.LT + SBI_L_LU_LOWER);
-  const float* up = P + __ldg(v.LT + SBI_L_LU_UPPER);
-  const float* dg = P + __ldg(v.LT + SBI_L_LU_DIAG);
-  const float* bi = P + __ldg(v.LT + SBI_L_LU_BIAS);
   // one thread per row: forward substitution with unit-lower L, back substitution with U
   for (int r = threadIdx.x; r < TM; r += kConsumerThreads) {
     for (int i = 0; i < D; ++i) {
-      float a = Z[i * LD + r] - __ldg(bi + i);
-      for (int j = 0; j < i; ++j) a -= lu_lower(lo, i, j) * Z[j * LD + r];
+      float a = Z[i * LD + r] - w.bias[i];
+      for (int j = 0; j < i; ++j) a -= w.Lw[i * D + j] * Z[j * LD + r];
       Z[i * LD + r] = a;
     }
     for (int i = D - 1; i >= 0; --i) {
       float a = Z[i * LD + r];
-      for (int j = i + 1; j < D; ++j) a -= lu_upper(up, D, i, j) * Z[j * LD + r];
-      Z[i * LD + r] = a / lu_diag(dg, i);
+      for (int j = i + 1; j < D; ++j) a -= w.U[i * D + j] * Z[j * LD + r];
+      Z[i * LD + r] = a / w.diag[i];
     }
   }
   consumer_sync();
 }
 
-// sum over layers of log|det LU| = sum_i log(softplus(raw_i)+eps): identical for every row
-__device__ __forceinline__ float lu_logdet_total(const sbi_nsf_model& m) {
+// sum over layers of log|det LU| = sum_i log(softplus(raw_i)+eps): identical for every row.
+// Cooperative: one (layer, i) term per thread into scratch, then a fixed-order sum.
+__device__ __forceinline__ float lu_logdet_total(const sbi_nsf_model& m, float* scratch) {
+  const int n = m.T * m.D;
+  for (int t = threadIdx.x; t < n; t += kConsumerThreads) {
+    const int l = t / m.D, i = t % m.D;
+    const int* LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
+    float val = 0.f;
+    if (__ldg(LT + SBI_L_HAS_LU))
+      val = logf(softplus_f(__ldg(m.d_params + __ldg(LT + SBI_L_LU_DIAG) + i)) + 1e-3f);
+    scratch[t] = val;
+  }
+  consumer_sync();
   float tot = 0.f;
   for (int l = 0; l < m.T; ++l) {
-    const int* LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
-    if (!__ldg(LT + SBI_L_HAS_LU)) continue;
-    const float* dg = m.d_params + __ldg(LT + SBI_L_LU_DIAG);
-    float s = 0.f;
-    for (int i = 0; i < m.D; ++i) s += logf(lu_diag(dg, i));
-    tot += s;
+    float sacc = 0.f;
+    for (int i = 0; i < m.D; ++i) sacc += scratch[l * m.D + i];
+    tot += sacc;
   }
+  consumer_sync();
   return tot;
 }
 

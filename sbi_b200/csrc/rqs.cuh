@@ -43,31 +43,50 @@ SBI_HD float rqs_mul_add(float a, float b, float c) {
 #endif
 }
 
+constexpr int kRqsMaxBins = 16;   // bins kept in registers (num_bins <= 16)
+
 struct RqsLoc {
   int b;          // bin
   float klo, khi; // knots b, b+1
-  float m, s;     // softmax max and sum(exp(u-m))
 };
+
+// softmax numerators of one axis, computed once: e_i = exp(u_i - max u), s = sum e_i
+struct RqsAxis {
+  float e[kRqsMaxBins];
+  float s;
+};
+
+SBI_HD void rqs_axis_load(const float* p, int st, int K, float isq, RqsAxis& a) {
+  float u[kRqsMaxBins];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kRqsMaxBins; ++i)
+    if (i < K) { u[i] = p[i * st] * isq; m = fmaxf(m, u[i]); }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kRqsMaxBins; ++i)
+    if (i < K) { a.e[i] = expf(u[i] - m); s += a.e[i]; }
+  a.s = s;
+}
 
 // Knots of one normalised axis (widths or heights).  search=true: locate the bin of x;
 // search=false: return the knots of bin bsel.
-SBI_HD RqsLoc rqs_knots(const float* p, int st, int K, float isq, float minv, float B,
-                        bool search, float x, int bsel) {
-  float m = -INFINITY;
-  for (int i = 0; i < K; ++i) m = fmaxf(m, p[i * st] * isq);
-  float s = 0.f;
-  for (int i = 0; i < K; ++i) s += expf(p[i * st] * isq - m);
+SBI_HD RqsLoc rqs_knots(const RqsAxis& a, int K, float minv, float B, bool search, float x,
+                        int bsel) {
   const float scale = 1.f - minv * (float)K;
   float cum = 0.f, lo = -B;
   RqsLoc o;
-  o.b = 0; o.klo = -B; o.khi = B; o.m = m; o.s = s;
-  for (int i = 0; i < K; ++i) {
-    const float w = minv + scale * (expf(p[i * st] * isq - m) / s);
-    cum += w;
-    const float hi = (i == K - 1) ? B : rqs_mul_add(2.f * B, cum, -B);
-    const bool take = search ? (x >= lo) : (i == bsel);
-    if (take) { o.b = i; o.klo = lo; o.khi = hi; }
-    lo = hi;
+  o.b = 0; o.klo = -B; o.khi = B;
+#pragma unroll
+  for (int i = 0; i < kRqsMaxBins; ++i) {
+    if (i < K) {
+      const float w = minv + scale * (a.e[i] / a.s);
+      cum += w;
+      const float hi = (i == K - 1) ? B : rqs_mul_add(2.f * B, cum, -B);
+      const bool take = search ? (x >= lo) : (i == bsel);
+      if (take) { o.b = i; o.klo = lo; o.khi = hi; }
+      lo = hi;
+    }
   }
   return o;
 }
@@ -76,7 +95,7 @@ struct RqsBin {
   int b;
   float xk, wb, yk, hb, d0, d1;
   bool inside;
-  RqsLoc lw, lh;
+  RqsAxis aw, ah;   // softmax numerators (valid when inside)
 };
 
 SBI_HD RqsBin rqs_locate(const float* p, int st, const RqsConst& c, float x, bool inverse) {
@@ -85,17 +104,20 @@ SBI_HD RqsBin rqs_locate(const float* p, int st, const RqsConst& c, float x, boo
   o.b = 0; o.xk = o.yk = -c.B; o.wb = o.hb = 2.f * c.B; o.d0 = o.d1 = 1.f;
   if (!o.inside) return o;
   const int K = c.K;
+  rqs_axis_load(p, st, K, c.isq, o.aw);
+  rqs_axis_load(p + K * st, st, K, c.isq, o.ah);
+  RqsLoc lw, lh;
   if (!inverse) {
-    o.lw = rqs_knots(p, st, K, c.isq, c.min_w, c.B, true, x, 0);
-    o.lh = rqs_knots(p + K * st, st, K, c.isq, c.min_h, c.B, false, 0.f, o.lw.b);
-    o.b = o.lw.b;
+    lw = rqs_knots(o.aw, K, c.min_w, c.B, true, x, 0);
+    lh = rqs_knots(o.ah, K, c.min_h, c.B, false, 0.f, lw.b);
+    o.b = lw.b;
   } else {
-    o.lh = rqs_knots(p + K * st, st, K, c.isq, c.min_h, c.B, true, x, 0);
-    o.lw = rqs_knots(p, st, K, c.isq, c.min_w, c.B, false, 0.f, o.lh.b);
-    o.b = o.lh.b;
+    lh = rqs_knots(o.ah, K, c.min_h, c.B, true, x, 0);
+    lw = rqs_knots(o.aw, K, c.min_w, c.B, false, 0.f, lh.b);
+    o.b = lh.b;
   }
-  o.xk = o.lw.klo; o.wb = o.lw.khi - o.lw.klo;
-  o.yk = o.lh.klo; o.hb = o.lh.khi - o.lh.klo;
+  o.xk = lw.klo; o.wb = lw.khi - lw.klo;
+  o.yk = lh.klo; o.hb = lh.khi - lh.klo;
   const float* pd = p + 2 * K * st;
   const float de = c.min_d + rqs_softplus(c.edge_raw);
   o.d0 = (o.b == 0) ? de : c.min_d + rqs_softplus(pd[(o.b - 1) * st]);
@@ -196,32 +218,31 @@ SBI_HD float rqs_backward(const float* p, int st, const RqsConst& c, float x, fl
   // widths: g_w[m] = 2B*(gA*[m<b] + gB*[m<=b]); softmax backward
   {
     const float scale = (1.f - c.min_w * (float)K) * twoB;
+    const float is = 1.f / q.aw.s;
     float dot = 0.f;
-    for (int m = 0; m < K; ++m) {
-      const float sm = expf(p[m * st] * c.isq - q.lw.m) / q.lw.s;
-      const float gsm = scale * ((m < b ? gA_w : 0.f) + (m <= b ? gB_w : 0.f));
-      dot += sm * gsm;
-    }
-    for (int m = 0; m < K; ++m) {
-      const float sm = expf(p[m * st] * c.isq - q.lw.m) / q.lw.s;
-      const float gsm = scale * ((m < b ? gA_w : 0.f) + (m <= b ? gB_w : 0.f));
-      g[m * gst] = sm * (gsm - dot) * c.isq;
-    }
+#pragma unroll
+    for (int m = 0; m < kRqsMaxBins; ++m)
+      if (m < K) dot += (q.aw.e[m] * is) * (scale * ((m < b ? gA_w : 0.f) + (m <= b ? gB_w : 0.f)));
+#pragma unroll
+    for (int m = 0; m < kRqsMaxBins; ++m)
+      if (m < K) {
+        const float gsm = scale * ((m < b ? gA_w : 0.f) + (m <= b ? gB_w : 0.f));
+        g[m * gst] = (q.aw.e[m] * is) * (gsm - dot) * c.isq;
+      }
   }
   {
     const float scale = (1.f - c.min_h * (float)K) * twoB;
-    const float* ph = p + K * st;
+    const float is = 1.f / q.ah.s;
     float dot = 0.f;
-    for (int m = 0; m < K; ++m) {
-      const float sm = expf(ph[m * st] * c.isq - q.lh.m) / q.lh.s;
-      const float gsm = scale * ((m < b ? gA_h : 0.f) + (m <= b ? gB_h : 0.f));
-      dot += sm * gsm;
-    }
-    for (int m = 0; m < K; ++m) {
-      const float sm = expf(ph[m * st] * c.isq - q.lh.m) / q.lh.s;
-      const float gsm = scale * ((m < b ? gA_h : 0.f) + (m <= b ? gB_h : 0.f));
-      g[(K + m) * gst] = sm * (gsm - dot) * c.isq;
-    }
+#pragma unroll
+    for (int m = 0; m < kRqsMaxBins; ++m)
+      if (m < K) dot += (q.ah.e[m] * is) * (scale * ((m < b ? gA_h : 0.f) + (m <= b ? gB_h : 0.f)));
+#pragma unroll
+    for (int m = 0; m < kRqsMaxBins; ++m)
+      if (m < K) {
+        const float gsm = scale * ((m < b ? gA_h : 0.f) + (m <= b ? gB_h : 0.f));
+        g[(K + m) * gst] = (q.ah.e[m] * is) * (gsm - dot) * c.isq;
+      }
   }
   {
     const float* pd = p + 2 * K * st;

@@ -149,15 +149,17 @@ class NSFEstimator(nn.Module):
         return d
 
     # ---- kernel-side views --------------------------------------------------------------------
-    def _kernel_stats(self) -> Tuple[Tensor, float]:
-        """[shift(Dp) | scale(Dp) | ctx_mean(Cp) | ctx_std(Cp)] on the parameter device."""
+    def _kernel_stats(self, raw_condition: bool = False) -> Tuple[Tensor, float]:
+        """[shift(Dp) | scale(Dp) | ctx_mean(Cp) | ctx_std(Cp)] on the parameter device.
+        raw_condition: identity statistics for the condition (see inverse_transform)."""
         lay = self.layout
         net = self.net
         emb = net._embedding_net
         std_mod = emb[0] if isinstance(emb, nn.Sequential) and isinstance(emb[0], Standardize) else None
         srcs = [net._shift, net._scale] + ([std_mod._mean, std_mod._std] if std_mod is not None else [])
-        key = tuple((t.data_ptr(), t._version) for t in srcs) + (str(net.flat.device),)
-        hit = self._cache.get("stats")
+        key = tuple((t.data_ptr(), t._version) for t in srcs) + (str(net.flat.device), raw_condition)
+        ck = "stats_raw" if raw_condition else "stats"
+        hit = self._cache.get(ck)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
         dev = net.flat.device
@@ -166,17 +168,17 @@ class NSFEstimator(nn.Module):
         st[2 * lay.Dp + lay.Cp:] = 1.0
         st[:lay.D] = net._shift.expand(lay.D)
         st[lay.Dp:lay.Dp + lay.D] = net._scale.expand(lay.D)
-        if std_mod is not None and self._embed_identity:
+        if std_mod is not None and self._embed_identity and not raw_condition:
             st[2 * lay.Dp:2 * lay.Dp + lay.C] = std_mod._mean.reshape(-1).expand(lay.C)
             st[2 * lay.Dp + lay.Cp:2 * lay.Dp + lay.Cp + lay.C] = std_mod._std.reshape(-1).expand(lay.C)
         ld = float(torch.log(torch.abs(net._scale.double())).expand(lay.D).sum())
-        self._cache["stats"] = (key, st, ld)
+        self._cache[ck] = (key, st, ld)
         return st, ld
 
-    def _model(self, nbuf: int) -> L.NsfModel:
+    def _model(self, nbuf: int, raw_condition: bool = False) -> L.NsfModel:
         net = self.net
         L.require_cuda(net.flat, "estimator parameters")
-        st, ld = self._kernel_stats()
+        st, ld = self._kernel_stats(raw_condition)
         s = L.NsfModel()
         self.layout.fill_struct(s, nbuf)
         s.ld_zscore = ld
@@ -271,15 +273,20 @@ class NSFEstimator(nn.Module):
         return -self.log_prob(input.unsqueeze(0), condition)[0]
 
     def inverse_transform(self, input: Tensor, condition: Tensor) -> Tensor:
-        """Base-space noise of the inputs; nflows_flow.py:42-75."""
+        """Base-space noise of the inputs; nflows_flow.py:42-75.  Like the reference (:73), the
+        RAW condition feeds the transform here: neither the condition z-scoring nor the
+        embedding net is applied on this code path."""
         self._check_condition_shape(condition)
         cdims = len(self.condition_shape)
         bshape = torch.broadcast_shapes(input.shape[:-1], condition.shape[:-cdims])
         inp = input.expand(bshape + (input.shape[-1],)).reshape(-1, input.shape[-1])
         cond = condition.expand(bshape + self.condition_shape).reshape(-1, *self.condition_shape)
-        ctx = self._embed(cond)
+        ctx = cond.reshape(cond.shape[0], -1)
+        if ctx.shape[1] != self.layout.C:
+            raise ValueError("inverse_transform: the raw condition does not have the embedded "
+                             "context size (reference behaviour: no embedding on this path)")
         _, noise = self._logprob_raw(inp.contiguous().float(), ctx.contiguous().float(), False,
-                                     want_noise=True)
+                                     want_noise=True, raw_condition=True)
         return noise.reshape(bshape + (noise.shape[-1],))
 
     @torch.no_grad()
@@ -332,14 +339,15 @@ class NSFEstimator(nn.Module):
 
     # ---- raw kernel entry (no autograd) --------------------------------------------------------------
     def _logprob_raw(self, inp: Tensor, ctx: Tensor, shared: bool, want_noise=False,
-                     index: Optional[Tensor] = None, n_rows: Optional[int] = None):
+                     index: Optional[Tensor] = None, n_rows: Optional[int] = None,
+                     raw_condition: bool = False):
         lib = L.load()
         L.require_cuda(inp, "input")
         L.require_cuda(ctx, "condition")
         R = inp.shape[0] if n_rows is None else n_rows
         lp = torch.empty(R, dtype=torch.float32, device=inp.device)
         noise = torch.empty(R, self.layout.D, dtype=torch.float32, device=inp.device) if want_noise else None
-        m = self._model(nbuf=2)
+        m = self._model(nbuf=2, raw_condition=raw_condition)
         rows = L.Rows(inp.data_ptr(), ctx.data_ptr(),
                       None if index is None else index.data_ptr(), R, 1 if shared else 0)
         L.check(lib.sbi_b200_nsf_logprob(C.byref(m), C.byref(rows), L.ptr(lp), L.ptr(noise),

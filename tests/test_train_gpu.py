@@ -129,7 +129,8 @@ def test_train_step_host_entry(cuda_lib):
             assert torch.isfinite(h_lp).all()
         outs.append((est.flat.detach().cpu().clone(), loss))
     assert torch.equal(outs[0][0], outs[1][0])
-    assert torch.equal(outs[0][1], outs[1][1])
+    # the loss sum is accumulated with float atomics across CTAs: order-dependent last bits
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5)
 
 
 def test_npe_fit_linear_gaussian(cuda_lib):
