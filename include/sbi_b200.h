@@ -116,6 +116,44 @@ int sbi_b200_adam_clip_step(float* d_params, const float* d_grad, float* d_state
                             float beta1, float beta2, float eps, float max_norm,
                             float grad_scale, void* stream);
 
+/* ---- masked autoregressive flow (sbi `posterior_nn("maf")`, reference builder
+ * sbi/neural_nets/net_builders/flow.py:115-209: T x [MaskedAffineAutoregressiveTransform(MADE,
+ * feed-forward blocks, tanh) + RandomPermutation], z-scored input, standardised context).
+ * Masked weights are stored already multiplied by their masks. */
+#define SBI_MAF_LAYER_STRIDE 32
+enum {
+  SBI_M_W0 = 0,   /* [Hp][Dp] masked initial layer */
+  SBI_M_B0 = 1,
+  SBI_M_WC = 2,   /* [Hp][Cp] context layer */
+  SBI_M_BC = 3,
+  SBI_M_WF = 4,   /* [OUTp][Hp] masked final layer; row 2d = unconstrained scale, 2d+1 = shift */
+  SBI_M_BF = 5,
+  SBI_M_PERM = 6, /* offset into perm_tab: perm[D] then inverse perm[D] */
+  SBI_M_BLK0 = 8  /* per feed-forward block b: W at SBI_M_BLK0+2b ([Hp][Hp] masked), bias at +1 */
+};
+typedef struct {
+  int32_t D, C, H, NB, T;
+  int32_t Dp, Cp, Hp, OUTp;
+  int32_t rpc0, rpc1, rpcf;        /* rows per weight chunk: initial(+context), hidden, final */
+  int32_t wcap, nbuf, n_params;
+  int32_t scale_softplus;          /* 0: sigmoid(s+2)+1e-3 (nflows 0.14), 1: softplus(s)+1e-3 */
+  float ld_zscore;
+  const float* d_params;
+  const int32_t* d_layer_tab;      /* T * SBI_MAF_LAYER_STRIDE */
+  const int32_t* d_perm_tab;
+  const float* d_stats;            /* [shift(Dp) | scale(Dp) | ctx_mean(Cp) | ctx_std(Cp)] */
+} sbi_maf_model;
+
+/* same contracts as the sbi_b200_nsf_* entry points */
+int sbi_b200_maf_logprob(const sbi_maf_model* m, const sbi_rows* rows, float* d_logp,
+                         float* d_noise, void* stream);
+int sbi_b200_maf_vjp_parts(int64_t R);
+int sbi_b200_maf_vjp(const sbi_maf_model* m, const sbi_rows* rows, const float* d_gout,
+                     float g_const, float* d_logp, float* d_gpart, float* d_ginput,
+                     float* d_gcond, float* d_loss_acc, void* stream);
+int sbi_b200_maf_inverse(const sbi_maf_model* m, const sbi_rows* rows, float* d_out,
+                         float* d_logabsdet, void* stream);
+
 /* ---- host-buffer entry points (the end-to-end path a CPU caller binds) ------------------
  * Device staging / optimizer buffers are owned by the caller and passed in a workspace;
  * h_* buffers should be pinned for full PCIe bandwidth.  These calls copy host->device,

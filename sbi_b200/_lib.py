@@ -37,6 +37,22 @@ class NsfModel(C.Structure):
     ]
 
 
+class MafModel(C.Structure):
+    _fields_ = [
+        ("D", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("NB", C.c_int32), ("T", C.c_int32),
+        ("Dp", C.c_int32), ("Cp", C.c_int32), ("Hp", C.c_int32), ("OUTp", C.c_int32),
+        ("rpc0", C.c_int32), ("rpc1", C.c_int32), ("rpcf", C.c_int32),
+        ("wcap", C.c_int32), ("nbuf", C.c_int32), ("n_params", C.c_int32),
+        ("scale_softplus", C.c_int32), ("ld_zscore", C.c_float),
+        ("d_params", C.c_void_p), ("d_layer_tab", C.c_void_p), ("d_perm_tab", C.c_void_p),
+        ("d_stats", C.c_void_p),
+    ]
+
+
+SBI_MAF_LAYER_STRIDE = 32
+M_W0, M_B0, M_WC, M_BC, M_WF, M_BF, M_PERM, M_BLK0 = 0, 1, 2, 3, 4, 5, 6, 8
+
+
 class Rows(C.Structure):
     _fields_ = [
         ("d_input", C.c_void_p), ("d_cond", C.c_void_p), ("d_index", C.c_void_p),
@@ -63,6 +79,14 @@ _EXPORTS = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "sbi_b200_nsf_inverse": (C.c_int, [C.POINTER(NsfModel), C.POINTER(Rows), C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "sbi_b200_maf_logprob": (C.c_int, [C.POINTER(MafModel), C.POINTER(Rows), C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "sbi_b200_maf_vjp_parts": (C.c_int, [C.c_int64]),
+    "sbi_b200_maf_vjp": (C.c_int, [C.POINTER(MafModel), C.POINTER(Rows), C.c_void_p, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+    "sbi_b200_maf_inverse": (C.c_int, [C.POINTER(MafModel), C.POINTER(Rows), C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "sbi_b200_reduce_partials": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                            C.c_void_p]),

@@ -13,11 +13,9 @@
 #pragma once
 #include "../../include/sbi_b200.h"
 #include "rqs.cuh"
-#include "tile_gemm.cuh"
+#include "stages.cuh"
 
 namespace sbi {
-
-enum Role { kProducer = 0, kConsumer = 1 };
 
 // ---- shared memory plan (row counts are in rows of LD floats) --------------------------
 struct NsfSmem {
@@ -79,78 +77,6 @@ __host__ __device__ inline NsfSmem nsf_smem_layout(const sbi_nsf_model& m, int T
   return L;
 }
 
-// ---- stage helpers (both roles) -----------------------------------------------------------
-// forward GEMM stage: Y = W X, streamed in chunks of `rpc` rows.
-// epi(n0, g, ng, r0, acc): chunk first row n0, thread rows n0 + g + i*ng, tile rows r0..r0+3
-template <Role R, int TM, int RN, class Epi>
-__device__ __forceinline__ void fwd_stage(WPipe& pipe, const float* __restrict__ Wg, int N,
-                                          int Kp, int rpc, const float* X, Epi&& epi) {
-  for (int n0 = 0; n0 < N; n0 += rpc) {
-    const int cnt = min(rpc, N - n0);
-    if (R == kProducer) {
-      pipe.produce(Wg + (size_t)n0 * Kp, cnt * Kp);
-    } else {
-      const float* w = pipe.acquire();
-      gemm_fwd_chunk<TM, RN>(X, Kp >> 2, w, Kp, cnt,
-                             [&](int g, int ng, int r0, float(&acc)[RN][4]) {
-                               epi(n0, g, ng, r0, acc);
-                             });
-      pipe.release();
-    }
-  }
-  if (R == kConsumer) consumer_sync();
-}
-
-// GLU stage: t = W2 X1, gt = Wc X2 for the same output rows; one chunk = [W2 rows | Wc rows]
-template <Role R, int TM, int RN, class Epi>
-__device__ __forceinline__ void glu_stage(WPipe& pipe, const float* __restrict__ W2g, int Kp2,
-                                          const float* __restrict__ Wcg, int Kpc, int N, int rpc,
-                                          const float* X1, const float* X2, Epi&& epi) {
-  constexpr int NRG = Tile<TM>::NRG, NOG = Tile<TM>::NOG;
-  for (int n0 = 0; n0 < N; n0 += rpc) {
-    const int cnt = min(rpc, N - n0);
-    if (R == kProducer) {
-      pipe.produce(W2g + (size_t)n0 * Kp2, cnt * Kp2, Wcg + (size_t)n0 * Kpc, cnt * Kpc);
-    } else {
-      const float* w2 = pipe.acquire();
-      const float* wc = w2 + cnt * Kp2;
-      const int rg = threadIdx.x % NRG, og = threadIdx.x / NRG;
-      const int ng = cnt / RN;
-      for (int g = og; g < ng; g += NOG) {
-        float at[RN][4], ag[RN][4];
-#pragma unroll
-        for (int i = 0; i < RN; ++i)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) at[i][c] = ag[i][c] = 0.f;
-        gemm_fwd_acc<TM, RN>(at, X1, Kp2 >> 2, w2, Kp2, g, ng, rg);
-        gemm_fwd_acc<TM, RN>(ag, X2, Kpc >> 2, wc, Kpc, g, ng, rg);
-        epi(n0, g, ng, 4 * rg, at, ag);
-      }
-      pipe.release();
-    }
-  }
-  if (R == kConsumer) consumer_sync();
-}
-
-// backward-x stage over a weight matrix of N rows: dX = W^T dY (accumulated over chunks).
-// epi(k0, r0, acc, first) ; `first` = first chunk (overwrite vs. add is up to the epilogue).
-template <Role R, int TM, int RK, class Epi>
-__device__ __forceinline__ void dx_stage(WPipe& pipe, const float* __restrict__ Wg, int N, int Kp,
-                                         int rpc, const float* dY, int Kout, Epi&& epi) {
-  for (int n0 = 0; n0 < N; n0 += rpc) {
-    const int cnt = min(rpc, N - n0);
-    if (R == kProducer) {
-      pipe.produce(Wg + (size_t)n0 * Kp, cnt * Kp);
-    } else {
-      const float* w = pipe.acquire();
-      gemm_dx_chunk<TM, RK>(dY, n0, cnt, w, Kp, Kout,
-                            [&](int k0, int r0, float(&acc)[RK][4]) { epi(k0, r0, acc, n0 == 0); });
-      pipe.release();
-    }
-  }
-  if (R == kConsumer) consumer_sync();
-}
-
 // ---- per-layer pieces -----------------------------------------------------------------------
 struct NsfLayerView {
   const int* LT;    // layer table row
@@ -173,10 +99,6 @@ __device__ __forceinline__ RqsConst rqs_const(const sbi_nsf_model& m) {
   c.K = m.KB; c.B = m.tail_bound; c.isq = m.inv_sqrt_h;
   c.min_w = m.min_bw; c.min_h = m.min_bh; c.min_d = m.min_d; c.edge_raw = m.edge_raw;
   return c;
-}
-
-__device__ __forceinline__ float4 relu4(float4 v) {
-  return make_float4(relu_f(v.x), relu_f(v.y), relu_f(v.z), relu_f(v.w));
 }
 
 // U[Cp + i] = Zsrc[idf[i]] (identity features feeding the conditioner), pad rows zero
@@ -446,61 +368,19 @@ __device__ __forceinline__ float lu_logdet_total(const sbi_nsf_model& m, float* 
   return tot;
 }
 
-// ---- tile load / store ---------------------------------------------------------------------------
+// ---- tile load --------------------------------------------------------------------------------
 // Z = zscore(input rows), U[0:C] = standardize(cond rows); zero pads; LDACC = 0
 template <int TM>
 __device__ __forceinline__ void load_tile(const sbi_nsf_model& m, const sbi_rows& rows,
                                           int64_t row0, float* sm, const NsfSmem& L,
                                           bool raw_input) {
-  constexpr int LD = Tile<TM>::LD;
-  const float* __restrict__ st = m.d_stats;
-  float* Z = sm + L.Z;
-  float* U = sm + L.U;
-  const int D = m.D, C = m.C;
-  for (int e = threadIdx.x; e < TM * m.Dp; e += kConsumerThreads) {
-    const int r = e / m.Dp, d = e % m.Dp;
-    const int64_t gr = row0 + r;
-    float val = 0.f;
-    if (d < D && gr < rows.R) {
-      const int64_t src = rows.d_index ? __ldg(rows.d_index + gr) : gr;
-      const float x = __ldg(rows.d_input + src * D + d);
-      val = raw_input ? x : rqs_mul_add(x, __ldg(st + m.Dp + d), __ldg(st + d));
-    }
-    Z[d * LD + r] = val;
-  }
-  for (int e = threadIdx.x; e < TM * m.Cp; e += kConsumerThreads) {
-    const int r = e / m.Cp, c = e % m.Cp;
-    const int64_t gr = row0 + r;
-    float val = 0.f;
-    if (c < C && gr < rows.R) {
-      const int64_t src = rows.cond_shared ? 0 : (rows.d_index ? __ldg(rows.d_index + gr) : gr);
-      val = (__ldg(rows.d_cond + src * C + c) - __ldg(st + 2 * m.Dp + c)) /
-            __ldg(st + 2 * m.Dp + m.Cp + c);
-    }
-    U[c * LD + r] = val;
-  }
+  load_rows<TM>(m.D, m.Dp, m.C, m.Cp, m.d_stats, rows, row0, sm + L.Z, sm + L.U, raw_input);
   for (int r = threadIdx.x; r < TM; r += kConsumerThreads) sm[L.LDACC + r] = 0.f;
   consumer_sync();
 }
 
-// ---- shared-memory setup common to the three kernels ---------------------------------------------
 __device__ __forceinline__ WPipe make_pipe(const sbi_nsf_model& m, float* sm, const NsfSmem& L) {
-  WPipe p;
-  p.buf = sm + L.ring;
-  p.full = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(sm) + L.bar_bytes);
-  p.empty = p.full + m.nbuf;
-  p.cap = m.wcap;
-  p.nbuf = m.nbuf;
-  p.it = 0;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < m.nbuf; ++s) {
-      mbar_init(&p.full[s], 1);
-      mbar_init(&p.empty[s], kConsumerThreads / 32);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-  return p;
+  return make_pipe(m.nbuf, m.wcap, sm, L.ring, L.bar_bytes);
 }
 
 }  // namespace sbi

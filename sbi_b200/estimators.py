@@ -18,7 +18,23 @@ import torch
 from torch import Tensor, nn
 
 from . import _lib as L
-from .pack import NsfLayout
+from .pack import MafLayout, NsfLayout
+
+
+class _Family:
+    """C-ABI entry points + model struct of one flow family (include/sbi_b200.h)."""
+
+    def __init__(self, name, struct, tab_fields):
+        self.name, self.struct, self.tab_fields = name, struct, tab_fields
+
+    def fn(self, what):
+        return getattr(L.load(), f"sbi_b200_{self.name}_{what}")
+
+
+FAMILIES = {
+    "nsf": _Family("nsf", L.NsfModel, ("d_layer_tab", "d_feat_tab")),
+    "maf": _Family("maf", L.MafModel, ("d_layer_tab", "d_perm_tab")),
+}
 
 
 class Standardize(nn.Module):
@@ -34,21 +50,21 @@ class Standardize(nn.Module):
         return (tensor - self._mean) / self._std
 
 
-class _NsfNet(nn.Module):
+class _FlowNet(nn.Module):
     """Plays the role of the nflows `Flow` object that sits at `estimator.net`."""
 
-    def __init__(self, layout: NsfLayout, shift: Tensor, scale: Tensor,
-                 embedding_net: nn.Module):
+    def __init__(self, layout, shift: Tensor, scale: Tensor, embedding_net: nn.Module):
         super().__init__()
         self.layout = layout
         self.flat = nn.Parameter(torch.zeros(layout.n_params, dtype=torch.float32))
         self.register_buffer("_shift", shift.clone().float(), persistent=False)
         self.register_buffer("_scale", scale.clone().float(), persistent=False)
-        self.register_buffer("_layer_tab", torch.from_numpy(layout.layer_tab.reshape(-1).copy()),
-                             persistent=False)
-        self.register_buffer("_feat_tab", torch.from_numpy(layout.feat_tab.copy()),
-                             persistent=False)
+        tab_a, tab_b = layout.tables()
+        self.register_buffer("_layer_tab", torch.from_numpy(tab_a.copy()), persistent=False)
+        self.register_buffer("_feat_tab", torch.from_numpy(tab_b.copy()), persistent=False)
         self.register_buffer("_mask", layout.trainable_mask(), persistent=False)
+        # masked-out raw MADE weights, kept only so that state_dict() round-trips exactly
+        self.register_buffer("_raw", torch.zeros(layout.n_params if layout._wm() else 1), persistent=False)
         self._embedding_net = embedding_net
 
     # -- reference-compatible (de)serialisation ---------------------------------------------
@@ -57,7 +73,7 @@ class _NsfNet(nn.Module):
         if lay.zscore_input:
             destination[prefix + "_transform._transforms.0._shift"] = self._shift.detach().clone()
             destination[prefix + "_transform._transforms.0._scale"] = self._scale.detach().clone()
-        for k, t in lay.unpack(self.flat).items():
+        for k, t in lay.unpack(self.flat, self._raw if lay._wm() else None).items():
             destination[prefix + k[len("net."):]] = t
         for k, t in lay.buffers.items():
             destination[prefix + k[len("net."):]] = t.to(self.flat.device)
@@ -78,24 +94,34 @@ class _NsfNet(nn.Module):
                     missing_keys.append(kk)
             if len(src) == len(lay.index):
                 with torch.no_grad():
-                    lay.pack(src, out=self.flat.data)
+                    lay.pack(src, out=self.flat.data, raw_out=self._raw if lay._wm() else None)
         for name, buf in (("_shift", self._shift), ("_scale", self._scale)):
             kk = prefix + "_transform._transforms.0." + name
             if kk in state_dict:
                 with torch.no_grad():
                     buf.copy_(state_dict.pop(kk))
+        incoming = {}
         for k in lay.buffers:
-            state_dict.pop(prefix + k[len("net."):], None)
+            kk = prefix + k[len("net."):]
+            if kk in state_dict:
+                incoming[k] = state_dict.pop(kk)
+        if incoming and hasattr(lay, "load_buffers"):
+            # structural buffers that are data (MAF permutations): adopt them
+            new_tab_b = lay.load_buffers(incoming)
+            if new_tab_b is not None:
+                with torch.no_grad():
+                    self._feat_tab.copy_(torch.from_numpy(new_tab_b).to(self._feat_tab.device))
 
 
 def _is_identity(m: nn.Module) -> bool:
     return isinstance(m, nn.Identity)
 
 
-class NSFEstimator(nn.Module):
-    r"""Neural spline flow q(input | condition) evaluated by hand-written sm_100a kernels."""
+class FlowEstimator(nn.Module):
+    r"""Normalizing flow q(input | condition) evaluated by hand-written sm_100a kernels
+    (families: neural spline flow `nsf`, masked autoregressive flow `maf`)."""
 
-    def __init__(self, layout: NsfLayout, input_shape, condition_shape, shift: Tensor,
+    def __init__(self, layout, input_shape, condition_shape, shift: Tensor,
                  scale: Tensor, cond_mean: Optional[Tensor], cond_std: Optional[Tensor],
                  embedding_net: Optional[nn.Module] = None):
         super().__init__()
@@ -107,12 +133,13 @@ class NSFEstimator(nn.Module):
             emb = nn.Sequential(Standardize(cond_mean, cond_std), user_net)
         else:
             emb = user_net
-        self.net = _NsfNet(layout, shift, scale, emb)
+        self.net = _FlowNet(layout, shift, scale, emb)
         self._cache = {}
+        self.fam = FAMILIES[layout.family]
 
     # ---- properties of the reference interface ---------------------------------------------
     @property
-    def layout(self) -> NsfLayout:
+    def layout(self):
         return self.net.layout
 
     @property
@@ -175,16 +202,16 @@ class NSFEstimator(nn.Module):
         self._cache[ck] = (key, st, ld)
         return st, ld
 
-    def _model(self, nbuf: int, raw_condition: bool = False) -> L.NsfModel:
+    def _model(self, nbuf: int, raw_condition: bool = False):
         net = self.net
         L.require_cuda(net.flat, "estimator parameters")
         st, ld = self._kernel_stats(raw_condition)
-        s = L.NsfModel()
+        s = self.fam.struct()
         self.layout.fill_struct(s, nbuf)
         s.ld_zscore = ld
         s.d_params = net.flat.data_ptr()
-        s.d_layer_tab = net._layer_tab.data_ptr()
-        s.d_feat_tab = net._feat_tab.data_ptr()
+        setattr(s, self.fam.tab_fields[0], net._layer_tab.data_ptr())
+        setattr(s, self.fam.tab_fields[1], net._feat_tab.data_ptr())
         s.d_stats = st.data_ptr()
         s._keep = (st,)
         return s
@@ -333,8 +360,8 @@ class NSFEstimator(nn.Module):
         lad = torch.empty(R, dtype=torch.float32, device=noise.device)
         m = self._model(nbuf=2)
         rows = L.Rows(noise.data_ptr(), ctx.data_ptr(), None, R, 1 if shared else 0)
-        L.check(lib.sbi_b200_nsf_inverse(C.byref(m), C.byref(rows), L.ptr(out), L.ptr(lad),
-                                         L.stream_ptr()), "nsf_inverse")
+        L.check(self.fam.fn("inverse")(C.byref(m), C.byref(rows), L.ptr(out), L.ptr(lad),
+                                       L.stream_ptr()), f"{self.fam.name}_inverse")
         return out, lad
 
     # ---- raw kernel entry (no autograd) --------------------------------------------------------------
@@ -350,14 +377,14 @@ class NSFEstimator(nn.Module):
         m = self._model(nbuf=2, raw_condition=raw_condition)
         rows = L.Rows(inp.data_ptr(), ctx.data_ptr(),
                       None if index is None else index.data_ptr(), R, 1 if shared else 0)
-        L.check(lib.sbi_b200_nsf_logprob(C.byref(m), C.byref(rows), L.ptr(lp), L.ptr(noise),
-                                         L.stream_ptr()), "nsf_logprob")
+        L.check(self.fam.fn("logprob")(C.byref(m), C.byref(rows), L.ptr(lp), L.ptr(noise),
+                                       L.stream_ptr()), f"{self.fam.name}_logprob")
         return lp, noise
 
 
 class _NsfLogProb(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, flat, inp, cond, est: NSFEstimator, shared: bool):
+    def forward(ctx, flat, inp, cond, est, shared: bool):
         lp, _ = est._logprob_raw(inp, cond, shared)
         ctx.save_for_backward(inp, cond)
         ctx.est, ctx.shared = est, shared
@@ -370,15 +397,15 @@ class _NsfLogProb(torch.autograd.Function):
         lib = L.load()
         need_flat, need_inp, need_cond = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         R = inp.shape[0]
-        n_part = lib.sbi_b200_nsf_vjp_parts(R)
+        n_part = est.fam.fn("vjp_parts")(R)
         gpart = est._gpart(n_part)
         ginp = torch.empty_like(inp) if need_inp else None
         gcond = torch.empty(R, cond.shape[1], dtype=torch.float32, device=inp.device) if need_cond else None
         m = est._model(nbuf=3)
         rows = L.Rows(inp.data_ptr(), cond.data_ptr(), None, R, 1 if shared else 0)
         g = g.contiguous().float()
-        L.check(lib.sbi_b200_nsf_vjp(C.byref(m), C.byref(rows), L.ptr(g), 0.0, None, L.ptr(gpart),
-                                     L.ptr(ginp), L.ptr(gcond), None, L.stream_ptr()), "nsf_vjp")
+        L.check(est.fam.fn("vjp")(C.byref(m), C.byref(rows), L.ptr(g), 0.0, None, L.ptr(gpart),
+                                  L.ptr(ginp), L.ptr(gcond), None, L.stream_ptr()), f"{est.fam.name}_vjp")
         gflat = None
         if need_flat:
             gflat = torch.empty(est.layout.n_params, dtype=torch.float32, device=inp.device)
@@ -387,3 +414,7 @@ class _NsfLogProb(torch.autograd.Function):
         if need_cond and shared:
             gcond = gcond.sum(0, keepdim=True)
         return gflat, ginp, gcond, None, None
+
+
+NSFEstimator = FlowEstimator
+MAFEstimator = FlowEstimator

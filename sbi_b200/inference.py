@@ -29,7 +29,7 @@ import torch
 from torch import Tensor, nn
 
 from . import _lib as L
-from .estimators import NSFEstimator
+from .estimators import FlowEstimator, NSFEstimator
 from .neural_nets import likelihood_nn, posterior_nn
 
 
@@ -139,7 +139,7 @@ class _FlowTrainer:
             del th_cpu, x_cpu
         net = self._neural_net.to(dev)
         self._neural_net = net
-        if not isinstance(net, NSFEstimator):
+        if not isinstance(net, FlowEstimator):
             raise TypeError(f"{type(self).__name__} needs an sbi_b200 flow estimator, "
                             f"got {type(net).__name__}")
         lay = net.layout
@@ -169,7 +169,7 @@ class _FlowTrainer:
         perm_buf = torch.empty(steps * B, dtype=torch.int64, device=dev)
         vperm_buf = torch.empty(max(vsteps * Bv, 1), dtype=torch.int64, device=dev)
         grad = torch.zeros(P, dtype=torch.float32, device=dev)
-        n_part = lib.sbi_b200_nsf_vjp_parts(B)
+        n_part = net.fam.fn("vjp_parts")(B)
         gpart = net._gpart(n_part)
         loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
         val_lp = torch.empty(max(vsteps * Bv, 1), dtype=torch.float32, device=dev)
@@ -184,9 +184,9 @@ class _FlowTrainer:
             for s in range(steps):
                 idx = perm_buf[s * B:(s + 1) * B]
                 rows = L.Rows(inp_all.data_ptr(), cond_all.data_ptr(), idx.data_ptr(), B, 0)
-                L.check(lib.sbi_b200_nsf_vjp(C.byref(m_tr), C.byref(rows), None, -1.0 / (B * world),
-                                             None, L.ptr(gpart), None, None, L.ptr(loss_acc),
-                                             L.stream_ptr()), "nsf_vjp")
+                L.check(net.fam.fn("vjp")(C.byref(m_tr), C.byref(rows), None, -1.0 / (B * world),
+                                          None, L.ptr(gpart), None, None, L.ptr(loss_acc),
+                                          L.stream_ptr()), "flow_vjp")
                 L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad),
                                                      L.stream_ptr()), "reduce_partials")
                 if world > 1:
@@ -200,8 +200,8 @@ class _FlowTrainer:
                 m_ev = net._model(nbuf=2)
                 rows = L.Rows(inp_all.data_ptr(), cond_all.data_ptr(), vperm_buf.data_ptr(),
                               vsteps * Bv, 0)
-                L.check(lib.sbi_b200_nsf_logprob(C.byref(m_ev), C.byref(rows), L.ptr(val_lp), None,
-                                                 L.stream_ptr()), "nsf_logprob")
+                L.check(net.fam.fn("logprob")(C.byref(m_ev), C.byref(rows), L.ptr(val_lp), None,
+                                              L.stream_ptr()), "flow_logprob")
                 finite = torch.isfinite(val_lp)
                 stats[2] = -(torch.where(finite, val_lp, torch.zeros_like(val_lp))).sum()
                 stats[3] = (~finite).sum().float()

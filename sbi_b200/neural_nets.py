@@ -17,8 +17,8 @@ import torch
 from torch import Tensor, nn
 from torch.nn import init
 
-from .estimators import NSFEstimator
-from .pack import NsfLayout
+from .estimators import FlowEstimator, NSFEstimator
+from .pack import MafLayout, NsfLayout
 
 _NSF_MODELS = ("nsf",)
 
@@ -163,7 +163,56 @@ def build_nsf(
     return est
 
 
-_BUILDERS = {"nsf": build_nsf}
+def build_maf(
+    batch_x: Tensor, batch_y: Tensor, z_score_x="independent", z_score_y="independent",
+    hidden_features: int = 50, num_transforms: int = 5, embedding_net: nn.Module = nn.Identity(),
+    num_blocks: int = 2, dropout_probability: float = 0.0, use_batch_norm: bool = False,
+    num_bins: int = 10, **kwargs,
+) -> FlowEstimator:
+    """Builds MAF p(x|y); same arguments as the reference (flow.py:115-209): per transform a
+    `MaskedAffineAutoregressiveTransform(hidden, context, num_blocks, use_residual_blocks=False,
+    tanh)` followed by a `RandomPermutation`.  The global torch RNG is consumed in nflows' order
+    (MADE: initial masked layer, context layer, blocks, final layer; then `torch.randperm`), so
+    a seed yields the reference's initial weights AND permutations."""
+    check_data_device(batch_x, batch_y)
+    if z_score_x == "transform_to_unconstrained":
+        raise ValueError("`transform_to_unconstrained` is not supported by build_maf.")
+    if dropout_probability != 0.0 or use_batch_norm:
+        raise NotImplementedError("dropout / batch norm are not implemented in the sm_100a MAF kernels")
+    x_numel = batch_x[0].numel()
+    with torch.no_grad():
+        y_numel = embedding_net(batch_y[:1]).numel()
+    zx, sx = z_score_parser(z_score_x)
+    zy, sy = z_score_parser(z_score_y)
+    H, C, D = hidden_features, y_numel, x_numel
+    state, perms = {}, []
+    base = 1 if zx else 0
+    for l in range(num_transforms):
+        pa = f"net._transform._transforms.{base + 2 * l}.autoregressive_net."
+        state[pa + "initial_layer.weight"], state[pa + "initial_layer.bias"] = _linear_init(H, D)
+        state[pa + "context_layer.weight"], state[pa + "context_layer.bias"] = _linear_init(H, C)
+        for b in range(num_blocks):
+            state[pa + f"blocks.{b}.linear.weight"], state[pa + f"blocks.{b}.linear.bias"] = _linear_init(H, H)
+        state[pa + "final_layer.weight"], state[pa + "final_layer.bias"] = _linear_init(2 * D, H)
+        perms.append(torch.randperm(D).numpy())
+    lay = MafLayout(D=D, C=C, H=H, NB=num_blocks, T=num_transforms, perms=perms, zscore_input=zx,
+                    zscore_cond=zy, embed_is_identity=isinstance(embedding_net, nn.Identity),
+                    scale_softplus=bool(kwargs.get("maf_scale_softplus", False)))
+    if zx:
+        t_mean, t_std = z_standardization(batch_x.reshape(batch_x.shape[0], -1), sx)
+        shift, scale = -t_mean / t_std, 1 / t_std
+    else:
+        shift, scale = torch.zeros(()), torch.ones(())
+    c_mean, c_std = standardizing_stats(batch_y, sy) if zy else (None, None)
+    est = FlowEstimator(lay, input_shape=batch_x[0].shape, condition_shape=batch_y[0].shape,
+                        shift=shift, scale=scale, cond_mean=c_mean, cond_std=c_std,
+                        embedding_net=embedding_net)
+    with torch.no_grad():
+        lay.pack(state, out=est.net.flat.data, raw_out=est.net._raw)
+    return est
+
+
+_BUILDERS = {"nsf": build_nsf, "maf": build_maf}
 
 
 def _density_build_fn(model: str, input_is_theta: bool, **kw) -> Callable:

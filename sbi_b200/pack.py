@@ -25,8 +25,55 @@ def round4(x: int) -> int:
     return (x + 3) & ~3
 
 
+class _LayoutOps:
+    """pack / unpack between reference-named tensors and the flat kernel buffer.  `weight_masks`
+    holds, for masked (MADE) weights, the 0/1 mask: the flat buffer stores W*M, the masked-out raw
+    values are kept aside (`raw`) only so that state_dict() round-trips exactly."""
+
+    def _wm(self):
+        return getattr(self, "_weight_masks", None) or {}
+
+    def trainable_mask(self) -> torch.Tensor:
+        m = torch.zeros(self.n_params, dtype=torch.uint8)
+        for k, v in self.index.items():
+            ix = torch.as_tensor(v.reshape(-1))
+            if k in self._wm():
+                m[ix] = torch.as_tensor(self._wm()[k].reshape(-1)).to(torch.uint8)
+            else:
+                m[ix] = 1
+        return m
+
+    def pack(self, state: Dict[str, torch.Tensor], out: torch.Tensor = None,
+             raw_out: torch.Tensor = None) -> torch.Tensor:
+        """Reference-named tensors -> flat buffer (on out's device if given)."""
+        flat = torch.zeros(self.n_params, dtype=torch.float32) if out is None else out
+        for k, ix in self.index.items():
+            src = state[k].detach().to(dtype=torch.float32, device=flat.device).reshape(-1)
+            pos = torch.as_tensor(ix.reshape(-1), device=flat.device)
+            if k in self._wm():
+                mk = torch.as_tensor(self._wm()[k].reshape(-1), dtype=torch.float32, device=flat.device)
+                if raw_out is not None:
+                    raw_out[pos] = src * (1 - mk)
+                src = src * mk
+            flat[pos] = src
+        return flat
+
+    def unpack(self, flat: torch.Tensor, raw: torch.Tensor = None) -> Dict[str, torch.Tensor]:
+        out = {}
+        for k, ix in self.index.items():
+            pos = torch.as_tensor(ix.reshape(-1), device=flat.device)
+            t = flat.detach()[pos]
+            if raw is not None and k in self._wm():
+                t = t + raw[pos]
+            out[k] = t.reshape(ix.shape).clone()
+        return out
+
+    def num_real_params(self) -> int:
+        return int(sum(v.size for v in self.index.values()))
+
+
 @dataclass
-class NsfLayout:
+class NsfLayout(_LayoutOps):
     D: int
     C: int
     H: int = 50
@@ -156,29 +203,8 @@ class NsfLayout:
         self.edge_raw = float(np.log(np.exp(1 - 1e-3) - 1))
 
     # ------------------------------------------------------------------------------ helpers
-    def trainable_mask(self) -> torch.Tensor:
-        m = torch.zeros(self.n_params, dtype=torch.uint8)
-        for v in self.index.values():
-            m[torch.as_tensor(v.reshape(-1))] = 1
-        return m
-
-    def pack(self, state: Dict[str, torch.Tensor], out: torch.Tensor = None) -> torch.Tensor:
-        """Reference-named tensors -> flat buffer (on out's device if given)."""
-        flat = torch.zeros(self.n_params, dtype=torch.float32) if out is None else out
-        for k, ix in self.index.items():
-            src = state[k].detach().to(dtype=torch.float32, device=flat.device).reshape(-1)
-            flat[torch.as_tensor(ix.reshape(-1), device=flat.device)] = src
-        return flat
-
-    def unpack(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
-        out = {}
-        for k, ix in self.index.items():
-            t = flat.detach()[torch.as_tensor(ix.reshape(-1), device=flat.device)]
-            out[k] = t.reshape(ix.shape).clone()
-        return out
-
-    def num_real_params(self) -> int:
-        return int(sum(v.size for v in self.index.values()))
+    def tables(self):
+        return self.layer_tab.reshape(-1).astype(np.int32), self.feat_tab.astype(np.int32)
 
     def fill_struct(self, s: "L.NsfModel", nbuf: int):
         s.D, s.C, s.H, s.NB, s.KB, s.T = self.D, self.C, self.H, self.NB, self.KB, self.T
@@ -191,3 +217,150 @@ class NsfLayout:
         s.min_bw = s.min_bh = s.min_d = 1e-3
         s.edge_raw = self.edge_raw
         return s
+
+
+NsfLayout.family = "nsf"
+
+
+@dataclass
+class MafLayout(_LayoutOps):
+    """Packed layout of the MAF kernels (include/sbi_b200.h `sbi_maf_model`), mapping the tensors of
+    the reference module built by /root/reference/sbi/neural_nets/net_builders/flow.py:115-209 on
+    nflows 0.14 (MaskedAffineAutoregressiveTransform(MADE) + RandomPermutation per layer)."""
+    D: int
+    C: int
+    H: int = 50
+    NB: int = 2
+    T: int = 5
+    perms: List[np.ndarray] = None       # permutation of each layer (RandomPermutation buffer)
+    zscore_input: bool = True
+    zscore_cond: bool = True
+    embed_is_identity: bool = True
+    scale_softplus: bool = False         # nflows 0.14: sigmoid(s+2)+1e-3
+    wcap_target: int = 4096
+    n_params: int = 0
+    index: Dict[str, np.ndarray] = field(default_factory=dict, repr=False)
+
+    def __post_init__(self):
+        D, C, H, NB, T = self.D, self.C, self.H, self.NB, self.T
+        if NB > 8:
+            raise ValueError("num_blocks <= 8")
+        self.Dp, self.Cp, self.Hp = round4(D), round4(C), round4(H)
+        self.OUTp = round4(2 * D)
+        Hp, Dp, Cp = self.Hp, self.Dp, self.Cp
+        cap = max(self.wcap_target, 4 * (Dp + Cp), 4 * Hp)
+
+        def rows(rowlen, nmax):
+            return max(4, min(nmax, (cap // rowlen) & ~3))
+
+        self.rpc0, self.rpc1, self.rpcf = rows(Dp + Cp, Hp), rows(Hp, Hp), rows(Hp, self.OUTp)
+        used = max(self.rpc0 * (Dp + Cp), self.rpc1 * Hp, self.rpcf * Hp, 4 * Cp, 4 * Dp)
+        self.wcap = (used + 31) & ~31
+
+        # MADE degrees / masks (nflows transforms/made.py, sequential degrees)
+        in_deg = np.arange(1, D + 1)
+        max_, min_ = max(1, D - 1), min(1, D - 1)
+        hid_deg = np.arange(H) % max_ + min_
+        m_init = (hid_deg[:, None] >= in_deg[None, :]).astype(np.float32)      # (H, D)
+        m_hid = (hid_deg[:, None] >= hid_deg[None, :]).astype(np.float32)      # (H, H)
+        out_deg = np.repeat(in_deg, 2)                                         # tile(.., 2)
+        m_out = (out_deg[:, None] > hid_deg[None, :]).astype(np.float32)       # (2D, H)
+        self.degrees = dict(input=in_deg, hidden=hid_deg, output=out_deg)
+
+        off = 0
+
+        def take(n):
+            nonlocal off
+            o = off
+            off += round4(n)
+            return o
+
+        if self.perms is None:
+            self.perms = [np.arange(D) for _ in range(T)]
+        tab = np.zeros((T, L.SBI_MAF_LAYER_STRIDE), np.int32)
+        ptab = []
+        idx: Dict[str, np.ndarray] = {}
+        wm: Dict[str, np.ndarray] = {}
+        self.buffers: Dict[str, torch.Tensor] = {}
+        base = 1 if self.zscore_input else 0
+        for l in range(T):
+            pa = f"net._transform._transforms.{base + 2 * l}.autoregressive_net."
+            pp = f"net._transform._transforms.{base + 2 * l + 1}."
+            perm = np.asarray(self.perms[l], np.int64)
+            tab[l, L.M_PERM] = len(ptab)
+            ptab += list(perm) + list(np.argsort(perm))
+            self.buffers[pp + "_permutation"] = torch.as_tensor(perm)
+            o = take(Hp * Dp)
+            tab[l, L.M_W0] = o
+            idx[pa + "initial_layer.weight"] = o + np.arange(H)[:, None] * Dp + np.arange(D)[None, :]
+            wm[pa + "initial_layer.weight"] = m_init
+            self.buffers[pa + "initial_layer.mask"] = torch.as_tensor(m_init)
+            self.buffers[pa + "initial_layer.degrees"] = torch.as_tensor(hid_deg)
+            o = take(Hp)
+            tab[l, L.M_B0] = o
+            idx[pa + "initial_layer.bias"] = o + np.arange(H)
+            o = take(Hp * Cp)
+            tab[l, L.M_WC] = o
+            idx[pa + "context_layer.weight"] = o + np.arange(H)[:, None] * Cp + np.arange(C)[None, :]
+            o = take(Hp)
+            tab[l, L.M_BC] = o
+            idx[pa + "context_layer.bias"] = o + np.arange(H)
+            for b in range(NB):
+                pb = pa + f"blocks.{b}.linear."
+                o = take(Hp * Hp)
+                tab[l, L.M_BLK0 + 2 * b] = o
+                idx[pb + "weight"] = o + np.arange(H)[:, None] * Hp + np.arange(H)[None, :]
+                wm[pb + "weight"] = m_hid
+                self.buffers[pb + "mask"] = torch.as_tensor(m_hid)
+                self.buffers[pb + "degrees"] = torch.as_tensor(hid_deg)
+                o = take(Hp)
+                tab[l, L.M_BLK0 + 2 * b + 1] = o
+                idx[pb + "bias"] = o + np.arange(H)
+            o = take(self.OUTp * Hp)
+            tab[l, L.M_WF] = o
+            idx[pa + "final_layer.weight"] = o + np.arange(2 * D)[:, None] * Hp + np.arange(H)[None, :]
+            wm[pa + "final_layer.weight"] = m_out
+            self.buffers[pa + "final_layer.mask"] = torch.as_tensor(m_out)
+            self.buffers[pa + "final_layer.degrees"] = torch.as_tensor(out_deg)
+            o = take(self.OUTp)
+            tab[l, L.M_BF] = o
+            idx[pa + "final_layer.bias"] = o + np.arange(2 * D)
+        self.n_params = off
+        self.index = idx
+        self._weight_masks = wm
+        self.layer_tab = tab
+        self.perm_tab = np.asarray(ptab, np.int32)
+
+    def tables(self):
+        return self.layer_tab.reshape(-1).astype(np.int32), self.perm_tab.astype(np.int32)
+
+    def load_buffers(self, incoming: Dict[str, torch.Tensor]):
+        """Adopt the permutations of a loaded reference state_dict (RandomPermutation buffers are
+        drawn at construction, so they are data, not architecture).  Returns the new perm table."""
+        base = 1 if self.zscore_input else 0
+        changed = False
+        ptab = []
+        for l in range(self.T):
+            key = f"net._transform._transforms.{base + 2 * l + 1}._permutation"
+            if key in incoming:
+                perm = incoming[key].detach().cpu().numpy().astype(np.int64)
+                if perm.shape != (self.D,) or sorted(perm.tolist()) != list(range(self.D)):
+                    raise ValueError(f"{key}: not a permutation of {self.D} features")
+                if not np.array_equal(perm, self.perms[l]):
+                    changed = True
+                self.perms[l] = perm
+                self.buffers[key] = torch.as_tensor(perm)
+            ptab += list(self.perms[l]) + list(np.argsort(self.perms[l]))
+        self.perm_tab = np.asarray(ptab, np.int32)
+        return self.perm_tab if changed else None
+
+    def fill_struct(self, s: "L.MafModel", nbuf: int):
+        s.D, s.C, s.H, s.NB, s.T = self.D, self.C, self.H, self.NB, self.T
+        s.Dp, s.Cp, s.Hp, s.OUTp = self.Dp, self.Cp, self.Hp, self.OUTp
+        s.rpc0, s.rpc1, s.rpcf = self.rpc0, self.rpc1, self.rpcf
+        s.wcap, s.nbuf, s.n_params = self.wcap, nbuf, self.n_params
+        s.scale_softplus = 1 if self.scale_softplus else 0
+        return s
+
+
+MafLayout.family = "maf"

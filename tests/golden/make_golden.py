@@ -10,6 +10,8 @@ Fixtures (small, committed):
   nsf_d3c2.pt     same for theta-dim 3, x-dim 2 (the shape of tests/linearGaussian_snpe_test.py:312-372).
   npe_train.pt    a short reference `NPE(...).train()` run (seed 3, 2000 sims, batch 200, 4 epochs):
                   validation-loss trajectory, final state_dict, train/val indices.
+  maf_d3c2.pt     reference `posterior_nn("maf")` (theta-dim 3, x-dim 2; BASELINE configs[0]): state_dict,
+                  permutations, log_prob and inverse outputs.
   searchsorted.pt the reference's bin-search known-answer test vectors (tests/torchutils_test.py:135-157).
 """
 import os
@@ -51,6 +53,25 @@ def flow_fixture(D, C, seed, n=400):
                 inverse_logabsdet=lad, D=D, C=C, seed=seed)
 
 
+def maf_fixture(D, C, seed, n=400):
+    g = torch.Generator().manual_seed(seed)
+    theta = 0.7 * torch.randn(n, D, generator=g) + 0.3
+    x = 1.3 * torch.randn(n, C, generator=g) - 0.2
+    torch.manual_seed(seed)
+    est = posterior_nn("maf")(theta, x)
+    with torch.no_grad():
+        for name, p in est.named_parameters():
+            p.add_(0.1 * torch.randn(p.shape, generator=g))
+    inp, cond = theta[:64] * 1.5, x[:64]
+    noise = torch.randn(64, D, generator=g)
+    with torch.no_grad():
+        lp = est.log_prob(inp, cond)[0]
+        emb = est.net._embedding_net(cond)
+        samples, lad = est.net._transform.inverse(noise, context=emb)
+    return dict(state_dict=est.state_dict(), theta=theta, x=x, inp=inp, cond=cond, noise=noise,
+                log_prob=lp, samples=samples, inverse_logabsdet=lad, D=D, C=C, seed=seed)
+
+
 def train_fixture():
     torch.manual_seed(3)
     D = 4
@@ -83,6 +104,7 @@ if __name__ == "__main__":
     torch.save(flow_fixture(10, 10, 7), os.path.join(HERE, "nsf_d10.pt"))
     torch.save(flow_fixture(3, 2, 8), os.path.join(HERE, "nsf_d3c2.pt"))
     torch.save(train_fixture(), os.path.join(HERE, "npe_train.pt"))
+    torch.save(maf_fixture(3, 2, 9), os.path.join(HERE, "maf_d3c2.pt"))
     torch.save(searchsorted_fixture(), os.path.join(HERE, "searchsorted.pt"))
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -24,3 +24,22 @@ def b200_from_oracle(flow, theta, x, device="cuda", **kw):
     est = build_nsf(theta, x, **kw)
     est.load_state_dict(flow.state_dict())
     return est.to(device)
+
+
+def oracle_maf(D=3, C=2, n=2000, seed=0, perturb=0.1, **kw):
+    g = torch.Generator().manual_seed(seed)
+    theta = 0.7 * torch.randn(n, D, generator=g) + 0.3
+    x = 1.3 * torch.randn(n, C, generator=g) - 0.2
+    torch.manual_seed(seed)
+    flow = sbi_port.build_maf(theta, x, **kw)
+    with torch.no_grad():
+        for name, p in flow.named_parameters():
+            p.add_(perturb * torch.randn(p.shape, generator=g))
+    return flow, theta, x
+
+
+def b200_maf_from_oracle(flow, theta, x, device="cuda", **kw):
+    from sbi_b200.neural_nets import build_maf
+    est = build_maf(theta, x, **kw)
+    est.load_state_dict(flow.state_dict())
+    return est.to(device)

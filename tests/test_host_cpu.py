@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import sbi_port
-from sbi_b200.neural_nets import build_nsf, likelihood_nn, posterior_nn
+from sbi_b200.neural_nets import build_maf, build_nsf, likelihood_nn, posterior_nn
 from sbi_b200.pack import NsfLayout
 from sbi_b200.posteriors import accept_reject_sample, within_support
 
@@ -28,6 +28,30 @@ def test_builder_matches_reference_builder_bitwise(D, C):
     for k in sr:
         assert torch.equal(sr[k].float(), se[k].float().cpu()), k
     assert est.layout.num_real_params() == sum(p.numel() for p in ref.parameters())
+
+
+@pytest.mark.parametrize("D,C", [(3, 2), (10, 10), (1, 4)])
+def test_maf_builder_matches_reference_builder_bitwise(D, C):
+    theta, x = torch.randn(300, D) + 1, torch.randn(300, C) * 2
+    torch.manual_seed(8)
+    ref = sbi_port.build_maf(theta, x)
+    torch.manual_seed(8)
+    est = build_maf(theta, x)
+    sr, se = ref.state_dict(), est.state_dict()
+    assert set(sr) == set(se)
+    for k in sr:
+        assert torch.equal(sr[k].float(), se[k].float()), k
+    g = torch.load(os.path.join(GOLD, "maf_d3c2.pt"))
+    e2 = build_maf(g["theta"], g["x"])
+    e2.load_state_dict(g["state_dict"])
+    out = e2.state_dict()
+    for k, v in g["state_dict"].items():
+        assert torch.equal(out[k].float(), v.float()), k
+    # masked-out weights never reach the kernels: the packed buffer holds W * M
+    lay = e2.layout
+    for k, mk in lay._wm().items():
+        packed = e2.flat.detach()[torch.as_tensor(lay.index[k].reshape(-1))].reshape(mk.shape)
+        assert (packed[torch.as_tensor(mk) == 0] == 0).all()
 
 
 def test_state_dict_roundtrip_with_reference_fixture():

@@ -53,6 +53,21 @@ def test_port_reproduces_reference_fixture(name):
         assert torch.equal(fresh.state_dict()[k], g["state_dict"][k])
 
 
+def test_port_reproduces_reference_maf_fixture():
+    g = torch.load(os.path.join(GOLD, "maf_d3c2.pt"))
+    flow = sbi_port.build_maf(g["theta"], g["x"])
+    flow.load_state_dict(g["state_dict"])
+    with torch.no_grad():
+        assert torch.equal(flow.log_prob(g["inp"], g["cond"])[0], g["log_prob"])
+        s, lad = flow.net._transform.inverse(g["noise"], context=flow.net._embedding_net(g["cond"]))
+        assert torch.equal(s, g["samples"]) and torch.equal(lad, g["inverse_logabsdet"])
+    torch.manual_seed(g["seed"])
+    fresh = sbi_port.build_maf(g["theta"], g["x"])
+    for k, v in g["state_dict"].items():
+        if k.endswith("_permutation") or k.endswith("mask") or k.endswith("degrees"):
+            assert torch.equal(fresh.state_dict()[k], v), k   # same seed -> same permutations / masks
+
+
 def test_reference_training_trajectory():
     """oracle.sbi_port.ReferenceTrainer == the reference's NPE.train() (same seeds -> same split,
     same validation-loss trajectory, same final weights)."""
