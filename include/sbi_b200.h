@@ -154,6 +154,72 @@ int sbi_b200_maf_vjp(const sbi_maf_model* m, const sbi_rows* rows, const float* 
 int sbi_b200_maf_inverse(const sbi_maf_model* m, const sbi_rows* rows, float* d_out,
                          float* d_logabsdet, void* stream);
 
+/* ---- ratio estimator: NRE `classifier_nn("resnet")` (reference builder
+ * sbi/neural_nets/net_builders/classifier.py:172-235 -> nflows ResidualNet(in=Dt+Dx, out=1,
+ * hidden, context=None, num_blocks, relu); wrapper sbi/neural_nets/ratio_estimators.py:132-150:
+ * logit = net(cat(standardize(theta), standardize(x)))). */
+enum {
+  SBI_R_W0 = 0, SBI_R_B0 = 1,   /* [Hp][Dtp+Dxp], columns = [theta | pad | x | pad] */
+  SBI_R_WF = 2, SBI_R_BF = 3,   /* [4][Hp] (row 0 is the logit) */
+  SBI_R_BLK0 = 4                /* per block b: W1,B1,W2,B2 at SBI_R_BLK0 + 4b */
+};
+typedef struct {
+  int32_t Dt, Dx, H, NB;
+  int32_t Dtp, Dxp, Hp;
+  int32_t rpc0, rpc1;
+  int32_t wcap, nbuf, n_params;
+  const float* d_params;
+  const int32_t* d_tab;           /* SBI_R_* offsets */
+  const float* d_stats;           /* [theta_mean(Dtp) | theta_std(Dtp) | x_mean(Dxp) | x_std(Dxp)] */
+} sbi_ratio_model;
+
+/* rows of (theta, x) pairs: pair r = (theta[ti[r]], x[xi[r]]); NULL index = identity;
+ * x_shared = 1: every pair uses x row 0 (potential at a fixed observation). */
+typedef struct {
+  const float* d_theta;
+  const float* d_x;
+  const int64_t* d_theta_index;
+  const int64_t* d_x_index;
+  int64_t R;
+  int32_t x_shared;
+} sbi_pairs;
+
+/* unnormalised log-ratio logits (R,) -- RatioEstimator.forward, ratio_estimators.py:132-154 */
+int sbi_b200_ratio_forward(const sbi_ratio_model* m, const sbi_pairs* pairs, float* d_logits,
+                           void* stream);
+/* VJP of sum_r g_r logit_r: d_gpart (n_part, n_params) per-CTA partial parameter gradients,
+ * d_gtheta (R, Dt) optional gradient wrt the theta of each pair; d_logits optional. */
+int sbi_b200_ratio_vjp_parts(int64_t R);
+int sbi_b200_ratio_vjp(const sbi_ratio_model* m, const sbi_pairs* pairs, const float* d_gout,
+                       float* d_logits, float* d_gpart, float* d_gtheta, void* stream);
+
+/* ---- lock-step vectorized slice sampler (state machine of
+ * sbi/samplers/mcmc/slice_numpy.py:412-587 `SliceSamplerVectorized.run`): one thread per chain,
+ * chain state resident in HBM, one launch per lock-step between two potential evaluations.
+ * Coordinate-wise slice sampling with stepping-out (bracket width tuned as the running mean of the
+ * bracket sizes during the first `tuning` sweeps) and shrinkage; random dimension order per sweep. */
+enum { SBI_SLICE_BEGIN = 0, SBI_SLICE_LOWER = 1, SBI_SLICE_UPPER = 2, SBI_SLICE_SAMPLE = 3, SBI_SLICE_DONE = 4 };
+typedef struct {
+  int32_t C, D;                 /* chains, dimensions */
+  int32_t num_samples, tuning;  /* sweeps to record per chain, tuning sweeps before recording */
+  double init_width, max_width;
+  uint64_t seed;
+  double* d_x;                  /* (C, D) current position (in/out) */
+  double* d_width;              /* (C, D) */
+  int32_t* d_order;             /* (C, D) */
+  int32_t* d_istate;            /* (C, 4): state, i, t, - */
+  double* d_fstate;             /* (C, 8): cxi, wi, lx, ux, xi, logu, -, - */
+  void* d_rng;                  /* (C, 64 bytes) Philox state */
+  double* d_samples;            /* (C, num_samples, D) */
+} sbi_slice_chains;
+
+/* initialise chain state from d_x; writes the first parameters to evaluate into d_params (C, D) f32 */
+int sbi_b200_slice_init(const sbi_slice_chains* s, float* d_params, void* stream);
+/* one lock-step: consume d_logp (C,) evaluated at d_params, advance every chain, write the next
+ * d_params; d_n_done[0] = number of chains in state DONE after this step */
+int sbi_b200_slice_step(const sbi_slice_chains* s, const float* d_logp, float* d_params,
+                        int32_t* d_n_done, void* stream);
+
 /* ---- host-buffer entry points (the end-to-end path a CPU caller binds) ------------------
  * Device staging / optimizer buffers are owned by the caller and passed in a workspace;
  * h_* buffers should be pinned for full PCIe bandwidth.  These calls copy host->device,

@@ -304,6 +304,66 @@ def build_maf(
     return NFlowsFlow(neural_net, input_shape=batch_x[0].shape, condition_shape=batch_y[0].shape)
 
 
+# ----------------------------------------------------------------------------- ratio estimator (NRE)
+class RatioEstimator(nn.Module):
+    """sbi/neural_nets/ratio_estimators.py:11-157."""
+
+    def __init__(self, net, theta_shape, x_shape, embedding_net_theta=None, embedding_net_x=None):
+        super().__init__()
+        self.net = net
+        self.theta_shape, self.x_shape = torch.Size(theta_shape), torch.Size(x_shape)
+        self.embedding_net_theta = embedding_net_theta if embedding_net_theta is not None else nn.Identity()
+        self.embedding_net_x = embedding_net_x if embedding_net_x is not None else nn.Identity()
+
+    def combine_theta_and_x(self, theta: Tensor, x: Tensor) -> Tensor:
+        prefix = theta.shape[:-len(self.theta_shape)]
+        if prefix != x.shape[:-len(self.x_shape)]:
+            raise ValueError("The shape prefixes of `theta` and `x` must match")
+        et = self.embedding_net_theta(theta.reshape(-1, *self.theta_shape))
+        ex = self.embedding_net_x(x.reshape(-1, *self.x_shape))
+        return torch.cat([et, ex], dim=-1).reshape(*prefix, -1)
+
+    def unnormalized_log_ratio(self, theta: Tensor, x: Tensor) -> Tensor:
+        return self.net(self.combine_theta_and_x(theta, x)).squeeze(-1)
+
+    def forward(self, *args, **kwargs):
+        return self.unnormalized_log_ratio(*args, **kwargs)
+
+
+def build_resnet_classifier(batch_x: Tensor, batch_y: Tensor, z_score_x="independent",
+                            z_score_y="independent", hidden_features: int = 50, num_blocks: int = 2):
+    """sbi/neural_nets/net_builders/classifier.py:172-235 (x = theta, y = x in its view)."""
+    x_numel, y_numel = batch_x[0].numel(), batch_y[0].numel()
+    neural_net = nets.ResidualNet(in_features=x_numel + y_numel, out_features=1,
+                                  hidden_features=hidden_features, context_features=None,
+                                  num_blocks=num_blocks, activation=torch.relu)
+    zx, sx = z_score_parser(z_score_x)
+    zy, sy = z_score_parser(z_score_y)
+    ex = nn.Sequential(standardizing_net(batch_x, sx), nn.Identity()) if zx else nn.Identity()
+    ey = nn.Sequential(standardizing_net(batch_y, sy), nn.Identity()) if zy else nn.Identity()
+    return RatioEstimator(neural_net, batch_x[0].shape, batch_y[0].shape, ex, ey)
+
+
+def nre_b_logits(net: RatioEstimator, theta: Tensor, x: Tensor, num_atoms: int, choices: Tensor = None):
+    """sbi/inference/trainers/nre/nre_base.py:396-415 (`choices` may be supplied to pin the draw)."""
+    batch_size = theta.shape[0]
+    repeated_x = x.repeat_interleave(num_atoms, dim=0)
+    if choices is None:
+        probs = torch.ones(batch_size, batch_size) * (1 - torch.eye(batch_size)) / (batch_size - 1)
+        choices = torch.multinomial(probs, num_samples=num_atoms - 1, replacement=False)
+    contrasting_theta = theta[choices]
+    atomic_theta = torch.cat((theta[:, None, :], contrasting_theta), dim=1).reshape(batch_size * num_atoms, -1)
+    return net(atomic_theta, repeated_x)
+
+
+def nre_b_loss(net: RatioEstimator, theta: Tensor, x: Tensor, num_atoms: int, choices: Tensor = None):
+    """sbi/inference/trainers/nre/nre_b.py:157-182."""
+    batch_size = theta.shape[0]
+    logits = nre_b_logits(net, theta, x, num_atoms, choices).reshape(batch_size, num_atoms)
+    log_prob = logits[:, 0] - torch.logsumexp(logits, dim=-1)
+    return -torch.mean(log_prob)
+
+
 # ----------------------------------------------------------------------------- training loop
 class ReferenceTrainer:
     """First-round NPE/NLE training exactly as the reference runs it on one device:

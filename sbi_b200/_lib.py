@@ -53,6 +53,35 @@ SBI_MAF_LAYER_STRIDE = 32
 M_W0, M_B0, M_WC, M_BC, M_WF, M_BF, M_PERM, M_BLK0 = 0, 1, 2, 3, 4, 5, 6, 8
 
 
+class RatioModel(C.Structure):
+    _fields_ = [
+        ("Dt", C.c_int32), ("Dx", C.c_int32), ("H", C.c_int32), ("NB", C.c_int32),
+        ("Dtp", C.c_int32), ("Dxp", C.c_int32), ("Hp", C.c_int32),
+        ("rpc0", C.c_int32), ("rpc1", C.c_int32),
+        ("wcap", C.c_int32), ("nbuf", C.c_int32), ("n_params", C.c_int32),
+        ("d_params", C.c_void_p), ("d_tab", C.c_void_p), ("d_stats", C.c_void_p),
+    ]
+
+
+class Pairs(C.Structure):
+    _fields_ = [
+        ("d_theta", C.c_void_p), ("d_x", C.c_void_p), ("d_theta_index", C.c_void_p),
+        ("d_x_index", C.c_void_p), ("R", C.c_int64), ("x_shared", C.c_int32),
+    ]
+
+
+R_W0, R_B0, R_WF, R_BF, R_BLK0 = 0, 1, 2, 3, 4
+
+
+class SliceChains(C.Structure):
+    _fields_ = [
+        ("C", C.c_int32), ("D", C.c_int32), ("num_samples", C.c_int32), ("tuning", C.c_int32),
+        ("init_width", C.c_double), ("max_width", C.c_double), ("seed", C.c_uint64),
+        ("d_x", C.c_void_p), ("d_width", C.c_void_p), ("d_order", C.c_void_p), ("d_istate", C.c_void_p),
+        ("d_fstate", C.c_void_p), ("d_rng", C.c_void_p), ("d_samples", C.c_void_p),
+    ]
+
+
 class Rows(C.Structure):
     _fields_ = [
         ("d_input", C.c_void_p), ("d_cond", C.c_void_p), ("d_index", C.c_void_p),
@@ -88,6 +117,12 @@ _EXPORTS = {
                                    C.c_void_p]),
     "sbi_b200_maf_inverse": (C.c_int, [C.POINTER(MafModel), C.POINTER(Rows), C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
+    "sbi_b200_ratio_forward": (C.c_int, [C.POINTER(RatioModel), C.POINTER(Pairs), C.c_void_p, C.c_void_p]),
+    "sbi_b200_ratio_vjp_parts": (C.c_int, [C.c_int64]),
+    "sbi_b200_ratio_vjp": (C.c_int, [C.POINTER(RatioModel), C.POINTER(Pairs), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sbi_b200_slice_init": (C.c_int, [C.POINTER(SliceChains), C.c_void_p, C.c_void_p]),
+    "sbi_b200_slice_step": (C.c_int, [C.POINTER(SliceChains), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_reduce_partials": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                            C.c_void_p]),
     "sbi_b200_adam_clip_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -304,3 +304,184 @@ class NLE(_FlowTrainer):
 
 NLE_A = NLE
 SNLE = NLE
+
+
+# =================================================================================================
+def _nle_build_posterior(self, density_estimator=None, prior=None, sample_with: str = "mcmc",
+                         mcmc_method: str = "slice_np_vectorized", mcmc_parameters: Optional[dict] = None,
+                         rejection_sampling_parameters: Optional[dict] = None, **kwargs):
+    """nle_base.py:274-378 (`sample_with` in {"mcmc", "rejection"})."""
+    from .posteriors import MCMCPosterior, RejectionPosterior
+    from .potentials import likelihood_estimator_based_potential
+    est = deepcopy(density_estimator if density_estimator is not None else self._neural_net)
+    prior = prior if prior is not None else self._prior
+    potential_fn, theta_transform = likelihood_estimator_based_potential(est, prior, x_o=None)
+    if sample_with == "mcmc":
+        return MCMCPosterior(potential_fn, proposal=prior, theta_transform=theta_transform, method=mcmc_method,
+                             device=self._device, **(mcmc_parameters or {}))
+    if sample_with == "rejection":
+        return RejectionPosterior(potential_fn, proposal=prior, device=self._device,
+                                  **(rejection_sampling_parameters or {}))
+    raise NotImplementedError(sample_with)
+
+
+NLE.build_posterior = _nle_build_posterior
+
+
+class NRE_B(_FlowTrainer):
+    """Neural ratio estimation, NRE-B / SRE (reference: trainers/nre/nre_base.py:184-309 train,
+    :396-415 `_classifier_logits`; trainers/nre/nre_b.py:157-182 `_loss`): 1-out-of-`num_atoms`
+    classification of the jointly drawn (theta, x) pair against `num_atoms - 1` contrastive thetas
+    from the same batch.  The classifier forward / backward run in the ratio kernels; the contrastive
+    index draw and the softmax head are a handful of torch device ops."""
+
+    def __init__(self, prior=None, classifier: Union[str, Callable] = "resnet", device: str = "cuda",
+                 logging_level: Union[int, str] = "warning", summary_writer=None, tracker=None,
+                 show_progress_bars: bool = False):
+        from .ratio import classifier_nn
+        self._prior = prior
+        self._device = _process_device(device)
+        self._build_neural_net = classifier_nn(classifier) if isinstance(classifier, str) else classifier
+        self._neural_net = None
+        self._theta = self._x = None
+        self.epoch, self._val_loss = 0, float("Inf")
+        self._summary = dict(epochs_trained=[], best_validation_loss=[], validation_loss=[],
+                             training_loss=[], epoch_durations_sec=[])
+        self._dist = None
+
+    @staticmethod
+    def _contrastive_choices(B: int, k: int, device) -> Tensor:
+        """(B, k) indices j != i, distinct per row, uniform: same law as
+        `torch.multinomial((1 - eye) / (B - 1), k, replacement=False)` (nre_base.py:406-408) without the
+        O(B^2) probability matrix: k draws without replacement from range(B-1), shifted past i."""
+        if B - 1 <= 4096:
+            draws = torch.multinomial(torch.ones(B, B - 1, device=device), k, replacement=False)
+        else:
+            draws = torch.randint(0, B - 1, (B, k), device=device)
+            while True:
+                srt = draws.sort(dim=1).values
+                dup = (srt[:, 1:] == srt[:, :-1]).any(dim=1)
+                n = int(dup.sum().item())
+                if n == 0:
+                    break
+                draws[dup] = torch.randint(0, B - 1, (n, k), device=device)
+        rows = torch.arange(B, device=device).unsqueeze(1)
+        return draws + (draws >= rows).long()
+
+    def _loss_on(self, net, idx: Tensor, num_atoms: int, choices: Optional[Tensor] = None) -> Tensor:
+        from .ratio import _RatioFn
+        B = idx.shape[0]
+        if choices is None:
+            choices = self._contrastive_choices(B, num_atoms - 1, idx.device)
+        local = torch.cat([torch.arange(B, device=idx.device).unsqueeze(1), choices], dim=1)   # (B, A)
+        ti = idx[local].reshape(-1).contiguous()
+        xi = idx.repeat_interleave(num_atoms).contiguous()
+        logits = _RatioFn.apply(net.net.flat, self._theta, self._x2d, net, ti, xi, False).reshape(B, num_atoms)
+        log_prob = logits[:, 0] - torch.logsumexp(logits, dim=-1)
+        return -torch.mean(log_prob)
+
+    def train(self, num_atoms: int = 10, training_batch_size: int = 200, learning_rate: float = 5e-4,
+              validation_fraction: float = 0.1, stop_after_epochs: int = 20, max_num_epochs: int = 2 ** 31 - 1,
+              clip_max_norm: Optional[float] = 5.0, resume_training: bool = False,
+              discard_prior_samples: bool = False, retrain_from_scratch: bool = False,
+              show_train_summary: bool = False, dataloader_kwargs: Optional[dict] = None):
+        if self._theta is None:
+            raise RuntimeError("call append_simulations() first")
+        lib = L.load()
+        dev = self._device
+        N = self._theta.shape[0]
+        self._x2d = self._x.reshape(N, -1).contiguous()
+        n_train = int((1 - validation_fraction) * N)
+        n_val = N - n_train
+        if not resume_training or not hasattr(self, "train_indices"):
+            perm = torch.randperm(N)
+            self.train_indices, self.val_indices = perm[:n_train], perm[n_train:]
+        B = min(training_batch_size, n_train)
+        Bv = min(training_batch_size, n_val)
+        clipped = min(B, Bv)
+        num_atoms = int(min(max(num_atoms, 2), clipped))     # nre_base.py:236-238 (clamp to batch size)
+        if self._neural_net is None or retrain_from_scratch:
+            tr = self.train_indices.to(dev)
+            self._neural_net = self._build_neural_net(self._theta[tr].cpu(), self._x[tr].cpu())
+        net = self._neural_net.to(dev)
+        self._neural_net = net
+        P = net.layout.n_params
+        if not resume_training or not hasattr(self, "_opt_state"):
+            self._opt_state = torch.zeros(2 * P, dtype=torch.float32, device=dev)
+            self._opt_step = torch.zeros(2, dtype=torch.int32, device=dev)
+            self.epoch, self._val_loss = 0, float("Inf")
+            self._best_val_loss, self._best_flat, self._epochs_since_last_improvement = float("Inf"), None, 0
+        train_idx, val_idx = self.train_indices.to(dev), self.val_indices.to(dev)
+        steps, vsteps = n_train // B, (n_val // Bv if Bv > 0 else 0)
+        max_norm = float(clip_max_norm) if clip_max_norm is not None else 0.0
+
+        def converged() -> bool:
+            if self.epoch == 0 or self._val_loss < self._best_val_loss:
+                self._best_val_loss, self._epochs_since_last_improvement = self._val_loss, 0
+                self._best_flat = net.flat.data.clone()
+            else:
+                self._epochs_since_last_improvement += 1
+            if self._epochs_since_last_improvement > stop_after_epochs - 1:
+                net.flat.data.copy_(self._best_flat)
+                return True
+            return False
+
+        while self.epoch <= max_num_epochs and not converged():
+            t0 = time.time()
+            perm = train_idx[torch.randperm(n_train, device=dev)]
+            train_sum = torch.zeros((), device=dev)
+            for s in range(steps):
+                net.net.flat.grad = None
+                loss = self._loss_on(net, perm[s * B:(s + 1) * B], num_atoms)
+                loss.backward()
+                train_sum += loss.detach()
+                L.check(lib.sbi_b200_adam_clip_step(
+                    L.ptr(net.flat.data), L.ptr(net.flat.grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
+                    L.ptr(net.net._mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.stream_ptr()),
+                    "adam_clip_step")
+            val_sum = torch.zeros((), device=dev)
+            with torch.no_grad():
+                vperm = val_idx[torch.randperm(n_val, device=dev)]
+                for s in range(vsteps):
+                    val_sum += self._loss_on(net, vperm[s * Bv:(s + 1) * Bv], num_atoms)
+            tl, vl = float(train_sum.item()), float(val_sum.item())
+            if not (math.isfinite(tl) and math.isfinite(vl)):
+                raise AssertionError("NaN/Inf present in NRE-B loss.")
+            # the reference divides the sum of per-batch MEAN losses by steps * batch_size (SURVEY a15 quirk)
+            self._summary["training_loss"].append(tl / (steps * B))
+            self._val_loss = vl / (vsteps * Bv) if vsteps > 0 else float("nan")
+            self._summary["validation_loss"].append(self._val_loss)
+            self._summary["epoch_durations_sec"].append(time.time() - t0)
+            self.epoch += 1
+        if self.epoch > max_num_epochs:
+            if self._val_loss < self._best_val_loss:
+                self._best_val_loss, self._best_flat = self._val_loss, net.flat.data.clone()
+            elif self._best_flat is not None:
+                net.flat.data.copy_(self._best_flat)
+            warnings.warn(f"Maximum number of epochs `max_num_epochs={max_num_epochs}` reached, "
+                          "but network has not yet fully converged.", stacklevel=2)
+        self._summary["epochs_trained"].append(self.epoch)
+        self._summary["best_validation_loss"].append(self._best_val_loss)
+        net.zero_grad(set_to_none=True)
+        return deepcopy(net)
+
+    def build_posterior(self, density_estimator=None, prior=None, sample_with: str = "mcmc",
+                        mcmc_method: str = "slice_np_vectorized", mcmc_parameters: Optional[dict] = None,
+                        rejection_sampling_parameters: Optional[dict] = None, **kwargs):
+        """nre_base.py:311-394."""
+        from .posteriors import MCMCPosterior, RejectionPosterior
+        from .potentials import ratio_estimator_based_potential
+        est = deepcopy(density_estimator if density_estimator is not None else self._neural_net)
+        prior = prior if prior is not None else self._prior
+        potential_fn, theta_transform = ratio_estimator_based_potential(est, prior, x_o=None)
+        if sample_with == "mcmc":
+            return MCMCPosterior(potential_fn, proposal=prior, theta_transform=theta_transform, method=mcmc_method,
+                                 device=self._device, **(mcmc_parameters or {}))
+        if sample_with == "rejection":
+            return RejectionPosterior(potential_fn, proposal=prior, device=self._device,
+                                      **(rejection_sampling_parameters or {}))
+        raise NotImplementedError(sample_with)
+
+
+SNRE_B = NRE_B
+SNRE = NRE_B

@@ -364,3 +364,71 @@ class MafLayout(_LayoutOps):
 
 
 MafLayout.family = "maf"
+
+
+@dataclass
+class RatioLayout(_LayoutOps):
+    """Packed layout of the NRE `resnet` classifier (include/sbi_b200.h `sbi_ratio_model`): nflows
+    ResidualNet(in=Dt+Dx, out=1, hidden, context=None, num_blocks) as built by
+    /root/reference/sbi/neural_nets/net_builders/classifier.py:172-235."""
+    Dt: int
+    Dx: int
+    H: int = 50
+    NB: int = 2
+    wcap_target: int = 4096
+    n_params: int = 0
+    index: Dict[str, np.ndarray] = field(default_factory=dict, repr=False)
+
+    def __post_init__(self):
+        Dt, Dx, H, NB = self.Dt, self.Dx, self.H, self.NB
+        self.Dtp, self.Dxp, self.Hp = round4(Dt), round4(Dx), round4(H)
+        K0p, Hp = self.Dtp + self.Dxp, self.Hp
+        cap = max(self.wcap_target, 4 * K0p, 4 * Hp)
+        self.rpc0 = max(4, min(Hp, (cap // K0p) & ~3))
+        self.rpc1 = max(4, min(Hp, (cap // Hp) & ~3))
+        self.wcap = (max(self.rpc0 * K0p, self.rpc1 * Hp, 4 * Hp) + 31) & ~31
+        off = 0
+
+        def take(n):
+            nonlocal off
+            o = off
+            off += round4(n)
+            return o
+
+        tab = np.zeros(4 + 4 * 8, np.int32)
+        idx: Dict[str, np.ndarray] = {}
+        o = take(Hp * K0p)
+        tab[L.R_W0] = o
+        cols = np.concatenate([np.arange(Dt), self.Dtp + np.arange(Dx)])   # [theta | pad | x | pad]
+        idx["net.initial_layer.weight"] = o + np.arange(H)[:, None] * K0p + cols[None, :]
+        o = take(Hp)
+        tab[L.R_B0] = o
+        idx["net.initial_layer.bias"] = o + np.arange(H)
+        for b in range(NB):
+            for j in range(2):
+                o = take(Hp * Hp)
+                tab[L.R_BLK0 + 4 * b + 2 * j] = o
+                idx[f"net.blocks.{b}.linear_layers.{j}.weight"] = o + np.arange(H)[:, None] * Hp + np.arange(H)[None, :]
+                o = take(Hp)
+                tab[L.R_BLK0 + 4 * b + 2 * j + 1] = o
+                idx[f"net.blocks.{b}.linear_layers.{j}.bias"] = o + np.arange(H)
+        o = take(4 * Hp)
+        tab[L.R_WF] = o
+        idx["net.final_layer.weight"] = o + np.arange(H)[None, :]
+        o = take(4)
+        tab[L.R_BF] = o
+        idx["net.final_layer.bias"] = o + np.arange(1)
+        self.n_params = off
+        self.index = idx
+        self.tab = tab
+        self.buffers = {}
+
+    def fill_struct(self, s: "L.RatioModel", nbuf: int):
+        s.Dt, s.Dx, s.H, s.NB = self.Dt, self.Dx, self.H, self.NB
+        s.Dtp, s.Dxp, s.Hp = self.Dtp, self.Dxp, self.Hp
+        s.rpc0, s.rpc1 = self.rpc0, self.rpc1
+        s.wcap, s.nbuf, s.n_params = self.wcap, nbuf, self.n_params
+        return s
+
+
+RatioLayout.family = "ratio"

@@ -226,3 +226,141 @@ class DirectPosterior:
         if self._leakage_density_correction_factor is None or force_update:
             self._leakage_density_correction_factor = acceptance_at(self.default_x)
         return self._leakage_density_correction_factor
+
+
+# =================================================================================================
+class MCMCPosterior:
+    """Posterior sampled with the lock-step vectorized slice sampler (reference:
+    /root/reference/sbi/inference/posteriors/mcmc_posterior.py: sample :237-367, _slice_np_mcmc
+    :737-811, _get_initial_params :590-659).  Supported method: `slice_np_vectorized`."""
+
+    def __init__(self, potential_fn, proposal, theta_transform=None, method: str = "slice_np_vectorized",
+                 thin: int = -1, warmup_steps: int = 200, num_chains: int = 20,
+                 init_strategy: str = "resample", init_strategy_parameters: Optional[dict] = None,
+                 num_workers: int = 1, device: Optional[str] = None, x_shape=None):
+        if method not in ("slice_np_vectorized", "slice_np"):
+            raise NotImplementedError("sbi_b200.MCMCPosterior implements method='slice_np_vectorized'")
+        self.potential_fn = potential_fn
+        self._device = device or potential_fn.device
+        self.proposal = prior_to_device(proposal, self._device)
+        self.theta_transform = theta_transform
+        if self.theta_transform is None:
+            import torch.distributions.transforms as tt
+            self.theta_transform = tt.IndependentTransform(tt.identity_transform, reinterpreted_batch_ndims=1)
+        self.method, self.warmup_steps, self.num_chains = method, warmup_steps, num_chains
+        self.thin = 10 if thin == -1 else thin       # reference default (mcmc_posterior.py: thin=-1 -> 10)
+        self.init_strategy = init_strategy
+        self.init_strategy_parameters = init_strategy_parameters or {}
+        self._mcmc_init_params = None
+        self._posterior_sampler = None
+        self.default_x = None
+
+    def set_default_x(self, x):
+        self.default_x = x
+        return self
+
+    def _get_initial_params(self, init_strategy: str, num_chains: int) -> Tensor:
+        from .samplers import resample_given_potential_fn, sir_init
+        if init_strategy == "proposal":
+            return self.theta_transform(self.proposal.sample((num_chains,)))
+        if init_strategy == "resample":
+            return resample_given_potential_fn(self.proposal, self.potential_fn, self.theta_transform,
+                                               num_inits=num_chains, **self.init_strategy_parameters)
+        if init_strategy == "sir":
+            return sir_init(self.proposal, self.potential_fn, self.theta_transform, num_inits=num_chains,
+                            **self.init_strategy_parameters)
+        if init_strategy == "latest_sample":
+            if self._mcmc_init_params is None or self._mcmc_init_params.shape[0] != num_chains:
+                raise ValueError("No or mismatching previous samples for init_strategy='latest_sample'")
+            return self._mcmc_init_params
+        raise NotImplementedError(init_strategy)
+
+    @torch.no_grad()
+    def sample(self, sample_shape=torch.Size(), x: Optional[Tensor] = None, method: Optional[str] = None,
+               thin: Optional[int] = None, warmup_steps: Optional[int] = None, num_chains: Optional[int] = None,
+               init_strategy: Optional[str] = None, show_progress_bars: bool = False, **kwargs) -> Tensor:
+        from math import ceil
+        from .potentials import transformed_potential
+        from .samplers import SliceSamplerVectorized
+        x = x if x is not None else self.default_x
+        if x is None:
+            raise ValueError("Context `x` needed when a default has not been set.")
+        self.potential_fn.set_x(x, x_is_iid=True)
+        thin = self.thin if thin is None else thin
+        warmup_steps = self.warmup_steps if warmup_steps is None else warmup_steps
+        num_chains = self.num_chains if num_chains is None else num_chains
+        init_strategy = self.init_strategy if init_strategy is None else init_strategy
+        num_samples = torch.Size(sample_shape).numel()
+        initial_params = self._get_initial_params(init_strategy, num_chains)
+        dim = initial_params.shape[1]
+
+        def log_prob_fn(params):
+            return transformed_potential(params, self.potential_fn, self.theta_transform, self._device,
+                                         track_gradients=False).flatten()
+
+        sampler = SliceSamplerVectorized(log_prob_fn=log_prob_fn, init_params=initial_params.double().cpu().numpy(),
+                                         num_chains=num_chains, thin=thin, verbose=show_progress_bars,
+                                         device=self._device)
+        warmup_ = warmup_steps * thin
+        num_samples_ = ceil((num_samples * thin) / num_chains)
+        samples = sampler.run(warmup_ + num_samples_)          # (chains, n, dim), already thinned
+        samples = samples[:, warmup_steps:, :]
+        samples = torch.from_numpy(samples)
+        self._posterior_sampler = sampler
+        self._mcmc_init_params = samples[:, -1, :].reshape(num_chains, dim).float().to(self._device)
+        samples = samples.reshape(-1, dim)[:num_samples].type(torch.float32).to(self._device)
+        samples = self.theta_transform.inv(samples)
+        return samples.reshape((*torch.Size(sample_shape), -1))
+
+    def log_prob(self, theta: Tensor, x: Optional[Tensor] = None, track_gradients: bool = False) -> Tensor:
+        """Unnormalised potential (mcmc_posterior.py:205-235)."""
+        x = x if x is not None else self.default_x
+        self.potential_fn.set_x(x)
+        return self.potential_fn(torch.as_tensor(theta, dtype=torch.float32).to(self._device),
+                                 track_gradients=track_gradients)
+
+
+class RejectionPosterior:
+    """/root/reference/sbi/inference/posteriors/rejection_posterior.py:131-226."""
+
+    def __init__(self, potential_fn, proposal, theta_transform=None, max_sampling_batch_size: int = 10_000,
+                 num_samples_to_find_max: int = 10_000, num_iter_to_find_max: int = 100, m: float = 1.2,
+                 device: Optional[str] = None, x_shape=None):
+        self.potential_fn = potential_fn
+        self._device = device or potential_fn.device
+        self.proposal = prior_to_device(proposal, self._device)
+        self.theta_transform = theta_transform
+        self.max_sampling_batch_size = max_sampling_batch_size
+        self.num_samples_to_find_max = num_samples_to_find_max
+        self.num_iter_to_find_max = num_iter_to_find_max
+        self.m = m
+        self.default_x = None
+
+    def set_default_x(self, x):
+        self.default_x = x
+        return self
+
+    def sample(self, sample_shape=torch.Size(), x: Optional[Tensor] = None,
+               max_sampling_batch_size: Optional[int] = None, num_samples_to_find_max: Optional[int] = None,
+               num_iter_to_find_max: Optional[int] = None, m: Optional[float] = None,
+               show_progress_bars: bool = False, max_sampling_time: Optional[float] = None,
+               return_partial_on_timeout: bool = False) -> Tensor:
+        from .samplers import rejection_sample
+        num_samples = torch.Size(sample_shape).numel()
+        x = x if x is not None else self.default_x
+        self.potential_fn.set_x(x)
+        pot = lambda th: self.potential_fn(th, track_gradients=True)   # noqa: E731
+        samples, _ = rejection_sample(
+            pot, proposal=self.proposal, num_samples=num_samples,
+            max_sampling_batch_size=max_sampling_batch_size or self.max_sampling_batch_size,
+            num_samples_to_find_max=num_samples_to_find_max or self.num_samples_to_find_max,
+            num_iter_to_find_max=num_iter_to_find_max or self.num_iter_to_find_max, m=m or self.m,
+            max_sampling_time=max_sampling_time, return_partial_on_timeout=return_partial_on_timeout,
+            device=self._device)
+        return samples.reshape((*torch.Size(sample_shape), -1))
+
+    def log_prob(self, theta: Tensor, x: Optional[Tensor] = None, track_gradients: bool = False) -> Tensor:
+        x = x if x is not None else self.default_x
+        self.potential_fn.set_x(x)
+        return self.potential_fn(torch.as_tensor(theta, dtype=torch.float32).to(self._device),
+                                 track_gradients=track_gradients)

@@ -1,0 +1,245 @@
+"""Samplers that loop over the estimator kernels, mirroring the reference's sampler API.
+
+* `SliceSamplerVectorized` -- same constructor / `run(num_samples) -> (chains, samples, dim)` as
+  /root/reference/sbi/samplers/mcmc/slice_numpy.py:353-620, but the per-chain state machine is ONE
+  kernel launch per lock-step (`sbi_b200_slice_step`) instead of a Python loop over chains with a
+  host sync per chain: a lock-step costs the potential evaluation + one tiny kernel, and the host
+  looks at the device only every `check_every` steps (termination test).
+* `rejection_sample` -- /root/reference/sbi/samplers/rejection/rejection.py:18-227, incl. the
+  `gradient_ascent` search for max(potential - log q) (sbiutils.py:1160-1285); the acceptance
+  uniforms are drawn with the CPU generator and uploaded, exactly as the reference does (:178), so
+  accepted-index sets are comparable.
+* `resample_given_potential_fn` / `sir_init` -- init strategies of
+  /root/reference/sbi/samplers/mcmc/init_strategy.py:37-114.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import time
+import warnings
+from typing import Any, Callable, Optional, Tuple, Union
+from warnings import warn
+
+import numpy as np
+import torch
+from torch import Tensor
+from torch.distributions import transforms as torch_tf
+from torch.optim import Adam
+
+from . import _lib as L
+
+
+class SliceSamplerVectorized:
+    def __init__(self, log_prob_fn: Callable, init_params: Union[np.ndarray, Tensor], num_chains: int = 1,
+                 thin: int = 1, tuning: int = 50, verbose: bool = False,
+                 init_width: Union[float, np.ndarray] = 0.01, max_width: float = float("inf"),
+                 num_workers: int = 1, device: str = "cuda", seed: Optional[int] = None,
+                 check_every: int = 16):
+        self._log_prob_fn = log_prob_fn
+        self.x = init_params
+        self.num_chains = num_chains
+        self.thin = 1 if thin is None else thin
+        self.tuning = tuning
+        self.verbose = verbose
+        self.init_width = float(np.asarray(init_width).reshape(-1)[0])
+        self.max_width = max_width
+        self._samples = None
+        self._device = device
+        self._seed = seed
+        self._check_every = check_every
+        self.num_potential_evals = 0
+        if num_workers > 1:
+            warn("Parallelization of vectorized slice sampling not implement, running serially.", stacklevel=2)
+
+    def run(self, num_samples: int) -> np.ndarray:
+        assert num_samples >= 0
+        lib = L.load()
+        dev = self._device
+        x = torch.as_tensor(np.asarray(self.x.cpu() if isinstance(self.x, Tensor) else self.x),
+                            dtype=torch.float64).reshape(self.num_chains, -1).to(dev).contiguous()
+        Cn, D = x.shape
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self._seed is None else int(self._seed)
+        width = torch.empty(Cn, D, dtype=torch.float64, device=dev)
+        order = torch.empty(Cn, D, dtype=torch.int32, device=dev)
+        istate = torch.zeros(Cn, 4, dtype=torch.int32, device=dev)
+        fstate = torch.zeros(Cn, 8, dtype=torch.float64, device=dev)
+        rng = torch.zeros(Cn, 64, dtype=torch.uint8, device=dev)
+        samples = torch.empty(Cn, max(int(num_samples), 1), D, dtype=torch.float64, device=dev)
+        params = torch.empty(Cn, D, dtype=torch.float32, device=dev)
+        n_done = torch.zeros(1, dtype=torch.int32, device=dev)
+        s = L.SliceChains(Cn, D, int(num_samples), int(self.tuning), self.init_width,
+                          float(min(self.max_width, 1e300)), seed, x.data_ptr(), width.data_ptr(),
+                          order.data_ptr(), istate.data_ptr(), fstate.data_ptr(), rng.data_ptr(),
+                          samples.data_ptr())
+        L.check(lib.sbi_b200_slice_init(C.byref(s), L.ptr(params), L.stream_ptr()), "slice_init")
+        it = 0
+        while True:
+            lp = self._log_prob_fn(params)
+            lp = torch.as_tensor(lp, dtype=torch.float32).to(dev).reshape(-1).contiguous()
+            self.num_potential_evals += Cn
+            L.check(lib.sbi_b200_slice_step(C.byref(s), L.ptr(lp), L.ptr(params), L.ptr(n_done),
+                                            L.stream_ptr()), "slice_step")
+            it += 1
+            if it % self._check_every == 0 and int(n_done.item()) == Cn:
+                break
+        self.num_lock_steps = it
+        out = samples[:, :int(num_samples)].cpu().numpy()
+        out = out[:, :: self.thin, :]
+        self._samples = out
+        self._final_x = x
+        return out
+
+    def get_samples(self, num_samples: Optional[int] = None, group_by_chain: bool = True) -> np.ndarray:
+        if self._samples is None:
+            raise ValueError("No samples found from MCMC run.")
+        samples = self._samples if group_by_chain else self._samples.reshape(-1, self._samples.shape[2])
+        if num_samples is None:
+            return samples
+        return samples[:, -num_samples:, :] if group_by_chain else samples[-num_samples:, :]
+
+
+# ------------------------------------------------------------------------------------------------
+def gradient_ascent(potential_fn: Callable, inits: Tensor, theta_transform: Optional[torch_tf.Transform] = None,
+                    num_iter: int = 1_000, num_to_optimize: int = 100, learning_rate: float = 0.01,
+                    save_best_every: int = 10, show_progress_bars: bool = False,
+                    interruption_note: str = "") -> Tuple[Tensor, Tensor]:
+    """sbiutils.py:1160-1285: Adam ascent from the best `num_to_optimize` inits in transformed
+    space; returns (argmax, max).  Gradients flow through the estimator kernels' VJP."""
+    if theta_transform is None:
+        theta_transform = torch_tf.IndependentTransform(torch_tf.identity_transform, reinterpreted_batch_ndims=1)
+    init_probs = potential_fn(inits).detach()
+    inits = inits.to(init_probs.device)
+    sort_indices = torch.argsort(init_probs, dim=0)
+    sorted_inits = inits[sort_indices]
+    optimize_inits = sorted_inits[-num_to_optimize:]
+    best_log_prob_iter = torch.max(init_probs)
+    best_theta_iter = sorted_inits[-1]
+    best_theta_overall = best_theta_iter.detach().clone()
+    best_log_prob_overall = best_log_prob_iter.detach().clone()
+    optimize_inits = theta_transform(optimize_inits).detach().clone()
+    optimize_inits.requires_grad_(True)
+    optimizer = Adam([optimize_inits], lr=learning_rate)
+    iter_ = 0
+    while iter_ < num_iter:
+        optimizer.zero_grad()
+        probs = potential_fn(theta_transform.inv(optimize_inits)).squeeze()
+        loss = -probs.sum()
+        loss.backward()
+        optimizer.step()
+        with torch.no_grad():
+            if iter_ % save_best_every == 0 or iter_ == num_iter - 1:
+                log_probs_of_optimized = potential_fn(theta_transform.inv(optimize_inits))
+                best_theta_iter = optimize_inits[torch.argmax(log_probs_of_optimized)].unsqueeze(0)
+                best_log_prob_iter = potential_fn(theta_transform.inv(best_theta_iter))
+                if best_log_prob_iter > best_log_prob_overall:
+                    best_theta_overall = best_theta_iter.detach().clone()
+                    best_log_prob_overall = best_log_prob_iter.detach().clone()
+        iter_ += 1
+    return theta_transform.inv(best_theta_overall), best_log_prob_overall
+
+
+def rejection_sample(potential_fn: Callable, proposal: Any, theta_transform: Optional[torch_tf.Transform] = None,
+                     num_samples: int = 1, show_progress_bars: bool = False, warn_acceptance: float = 0.01,
+                     max_sampling_batch_size: int = 10_000, num_samples_to_find_max: int = 10_000,
+                     num_iter_to_find_max: int = 100, m: float = 1.2, max_sampling_time: Optional[float] = None,
+                     return_partial_on_timeout: bool = False, device: str = "cuda",
+                     return_indices: bool = False):
+    """rejection.py:18-227.  `return_indices=True` additionally returns the global proposal index of
+    every accepted draw (the accept-set contract of BASELINE configs[4])."""
+    if theta_transform is None:
+        theta_transform = torch_tf.IndependentTransform(torch_tf.identity_transform, reinterpreted_batch_ndims=1)
+    samples_to_find_max = proposal.sample((num_samples_to_find_max,))
+
+    def potential_over_proposal(theta):
+        return potential_fn(theta) - proposal.log_prob(theta)
+
+    _, max_log_ratio = gradient_ascent(
+        potential_fn=potential_over_proposal, inits=samples_to_find_max, theta_transform=theta_transform,
+        num_iter=num_iter_to_find_max, learning_rate=0.01,
+        num_to_optimize=max(1, int(num_samples_to_find_max / 10)))
+    if m < 1.0:
+        warnings.warn("A value of m < 1.0 will lead to systematically wrong results.", stacklevel=2)
+    log_m = torch.log(torch.as_tensor(m))
+
+    def scaled_log_prob(theta):
+        return proposal.log_prob(theta) + max_log_ratio + log_m
+
+    with torch.no_grad():
+        num_sampled_total, num_remaining = 0, num_samples
+        accepted, acc_idx, acceptance_rate = [], [], float("Nan")
+        leakage_warning_raised = False
+        sampling_batch_size = min(num_samples, max_sampling_batch_size)
+        start_time = time.time()
+        while num_remaining > 0:
+            if max_sampling_time is not None and (time.time() - start_time) > max_sampling_time:
+                num_collected = sum(s.shape[0] for s in accepted)
+                if return_partial_on_timeout and num_collected > 0:
+                    warnings.warn(f"Timeout exceeded after collecting {num_collected}/{num_samples} samples. "
+                                  "Returning partial results.", stacklevel=2)
+                    return torch.cat(accepted), torch.as_tensor(acceptance_rate)
+                raise RuntimeError("Sampling aborted early because rejection sampling exceeded max_sampling_time. "
+                                   "This is likely due to extremely low acceptance.")
+            candidates = proposal.sample((sampling_batch_size,)).reshape(sampling_batch_size, -1)
+            target_proposal_ratio = torch.exp(potential_fn(candidates) - scaled_log_prob(candidates))
+            uniform_rand = torch.rand(target_proposal_ratio.shape).to(target_proposal_ratio.device)
+            keep = target_proposal_ratio > uniform_rand
+            samples = candidates[keep]
+            accepted.append(samples)
+            if return_indices:
+                acc_idx.append(torch.nonzero(keep).reshape(-1) + num_sampled_total)
+            num_sampled_total += sampling_batch_size
+            num_remaining -= samples.shape[0]
+            acceptance_rate = (num_samples - num_remaining) / num_sampled_total
+            sampling_batch_size = min(max_sampling_batch_size,
+                                      max(int(1.5 * num_remaining / max(acceptance_rate, 1e-12)), 100))
+            if num_sampled_total > 1000 and acceptance_rate < warn_acceptance and not leakage_warning_raised:
+                logging.warning(f"Only {acceptance_rate:.3%} proposal samples were accepted. It may take a long "
+                                f"time to collect the remaining {num_remaining} samples.")
+                leakage_warning_raised = True
+        samples = torch.cat(accepted)[:num_samples]
+        assert samples.shape[0] == num_samples, "Number of accepted samples must match required samples."
+    if return_indices:
+        return samples, torch.as_tensor(acceptance_rate), torch.cat(acc_idx)[:num_samples]
+    return samples, torch.as_tensor(acceptance_rate)
+
+
+def resample_given_potential_fn(proposal: Any, potential_fn: Callable, transform: torch_tf.Transform,
+                                num_candidate_samples: int = 10_000, num_batches: int = 1,
+                                num_inits: int = 1, **kwargs: Any) -> Tensor:
+    """init_strategy.py:67-114, vectorised over `num_inits` chains: ONE batch of candidates is
+    weighted by the potential and `num_inits` independent multinomial draws are taken per chain
+    batch, instead of num_chains x 10 000 sequential potential evaluations."""
+    with torch.set_grad_enabled(False):
+        outs = []
+        for _ in range(num_inits):
+            log_weights, cands = [], []
+            for _ in range(num_batches):
+                batch_draws = proposal.sample((num_candidate_samples,)).detach()
+                cands.append(batch_draws)
+                log_weights.append(potential_fn(batch_draws).detach())
+            log_weights = torch.cat(log_weights)
+            cands = torch.cat(cands)
+            log_weights = log_weights - torch.logsumexp(log_weights, dim=0)
+            probs = torch.exp(log_weights.view(-1))
+            probs[torch.isnan(probs)] = 0.0
+            probs[torch.isinf(probs)] = 0.0
+            probs /= probs.sum()
+            idxs = torch.multinomial(probs, 1, replacement=False)
+            outs.append(transform(cands[idxs, :]))
+        return torch.cat(outs)
+
+
+def sir_init(proposal: Any, potential_fn: Callable, transform: torch_tf.Transform,
+             num_candidate_samples: int = 10_000, num_inits: int = 1, **kwargs: Any) -> Tensor:
+    """init_strategy.py:37-64 (sampling-importance-resampling with the proposal correction)."""
+    with torch.set_grad_enabled(False):
+        outs = []
+        for _ in range(num_inits):
+            cands = proposal.sample((num_candidate_samples,)).detach()
+            logw = potential_fn(cands).detach() - proposal.log_prob(cands)
+            probs = torch.softmax(logw.view(-1), 0)
+            probs[torch.isnan(probs)] = 0.0
+            idx = torch.multinomial(probs, 1, replacement=False)
+            outs.append(transform(cands[idx, :]))
+        return torch.cat(outs)
