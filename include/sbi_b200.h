@@ -136,7 +136,7 @@ typedef struct {
   int32_t Dp, Cp, Hp, OUTp;
   int32_t rpc0, rpc1, rpcf;        /* rows per weight chunk: initial(+context), hidden, final */
   int32_t wcap, nbuf, n_params;
-  int32_t scale_softplus;          /* 0: sigmoid(s+2)+1e-3 (nflows 0.14), 1: softplus(s)+1e-3 */
+  int32_t scale_softplus;          /* 1: softplus(s)+1e-3 (what sbi's maf computes), 0: sigmoid(s+2)+1e-3 */
   float ld_zscore;
   const float* d_params;
   const int32_t* d_layer_tab;      /* T * SBI_MAF_LAYER_STRIDE */

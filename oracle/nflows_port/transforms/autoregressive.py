@@ -11,11 +11,15 @@ from .splines.rational_quadratic import (
     rational_quadratic_spline, unconstrained_rational_quadratic_spline,
 )
 
-# nflows 0.14 (PyPI, Nov 2020) bounds the MAF scale with a shifted sigmoid; later
-# upstream commits switched to softplus.  sbi pins nflows==0.14, so "sigmoid" is the
-# restated default; the alternative is kept selectable so both can be checked
-# (SURVEY.md Appendix A.6 -- recollection, flagged "verify").
-MAF_SCALE_FN = "sigmoid"
+# Scale parametrisation of the affine autoregressive transform.  Two variants exist upstream:
+#   "softplus": scale = softplus(s) + 1e-3          "sigmoid": scale = sigmoid(s + 2) + 1e-3  (<= 1.001)
+# The sdist of the pinned nflows==0.14 is not available offline, so the choice is pinned by the
+# reference's own acceptance tests instead: with the sigmoid form every layer can only CONTRACT
+# (d noise / d theta <= 1.001), so a MAF could never represent a posterior narrower than the
+# z-scored prior -- yet /root/reference/tests/linearGaussian_snpe_test.py:312-372 (maf, posterior
+# variance 0.23 of the prior's) passes its c2st check in the reference CI.  Hence "softplus" is
+# what sbi's `maf` computes; the sigmoid form stays selectable (tests cover both).
+MAF_SCALE_FN = "softplus"
 
 
 class AutoregressiveTransform(Transform):

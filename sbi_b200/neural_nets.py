@@ -197,7 +197,7 @@ def build_maf(
         perms.append(torch.randperm(D).numpy())
     lay = MafLayout(D=D, C=C, H=H, NB=num_blocks, T=num_transforms, perms=perms, zscore_input=zx,
                     zscore_cond=zy, embed_is_identity=isinstance(embedding_net, nn.Identity),
-                    scale_softplus=bool(kwargs.get("maf_scale_softplus", False)))
+                    scale_softplus=bool(kwargs.get("maf_scale_softplus", True)))
     if zx:
         t_mean, t_std = z_standardization(batch_x.reshape(batch_x.shape[0], -1), sx)
         shift, scale = -t_mean / t_std, 1 / t_std

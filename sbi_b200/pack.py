@@ -236,7 +236,7 @@ class MafLayout(_LayoutOps):
     zscore_input: bool = True
     zscore_cond: bool = True
     embed_is_identity: bool = True
-    scale_softplus: bool = False         # nflows 0.14: sigmoid(s+2)+1e-3
+    scale_softplus: bool = True          # softplus(s)+1e-3 (see oracle/nflows_port/transforms/autoregressive.py)
     wcap_target: int = 4096
     n_params: int = 0
     index: Dict[str, np.ndarray] = field(default_factory=dict, repr=False)

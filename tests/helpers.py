@@ -26,7 +26,9 @@ def b200_from_oracle(flow, theta, x, device="cuda", **kw):
     return est.to(device)
 
 
-def oracle_maf(D=3, C=2, n=2000, seed=0, perturb=0.1, **kw):
+def oracle_maf(D=3, C=2, n=2000, seed=0, perturb=0.1, scale_fn="softplus", **kw):
+    from oracle.nflows_port.transforms import autoregressive as _ar
+    _ar.MAF_SCALE_FN = scale_fn
     g = torch.Generator().manual_seed(seed)
     theta = 0.7 * torch.randn(n, D, generator=g) + 0.3
     x = 1.3 * torch.randn(n, C, generator=g) - 0.2
@@ -38,8 +40,8 @@ def oracle_maf(D=3, C=2, n=2000, seed=0, perturb=0.1, **kw):
     return flow, theta, x
 
 
-def b200_maf_from_oracle(flow, theta, x, device="cuda", **kw):
+def b200_maf_from_oracle(flow, theta, x, device="cuda", scale_fn="softplus", **kw):
     from sbi_b200.neural_nets import build_maf
-    est = build_maf(theta, x, **kw)
+    est = build_maf(theta, x, maf_scale_softplus=(scale_fn == "softplus"), **kw)
     est.load_state_dict(flow.state_dict())
     return est.to(device)

@@ -27,6 +27,16 @@ def test_maf_logprob_matches_oracle(cuda_lib, D, C, R):
     assert err <= LOGP_TOL and (got_sh.double() - ref_sh).abs().max() <= LOGP_TOL
 
 
+def test_maf_sigmoid_scale_variant(cuda_lib):
+    flow, theta, x = oracle_maf(4, 3, scale_fn="sigmoid")
+    est = b200_maf_from_oracle(flow, theta, x, scale_fn="sigmoid")
+    with torch.no_grad():
+        ref = flow.double().log_prob(theta[:300].double(), x[:300].double())[0]
+        got = est.log_prob(theta[:300].cuda(), x[:300].cuda())[0].cpu()
+    oracle_maf(2, 2, n=10)   # restore the default scale fn for later tests
+    assert (got.double() - ref).abs().max() <= LOGP_TOL
+
+
 def _grads(flow, est, inp, cond, g, dtype):
     flow = flow.to(dtype)
     flow.zero_grad()

@@ -30,19 +30,28 @@ def test_ratio_logits_and_grads_match_oracle(cuda_lib, Dt, Dx, R):
     g0 = torch.Generator().manual_seed(1)
     th, xx = torch.randn(R, Dt, generator=g0), torch.randn(R, Dx, generator=g0)
     w = torch.randn(R, generator=g0)
-    ref64 = ref.double()
-    t64 = th.double().requires_grad_(True)
-    out64 = ref64(t64, xx.double())
-    (out64 * w.double()).sum().backward()
-    gref = est.layout.pack({"net." + k[len("net."):]: p.grad for k, p in ref64.named_parameters() if k.startswith("net.")}).double()
+    def oracle(dtype):
+        r = ref.to(dtype)
+        r.zero_grad()
+        t = th.detach().to(dtype).clone().requires_grad_(True)
+        o = r(t, xx.to(dtype))
+        (o * w.to(dtype)).sum().backward()
+        gp = est.layout.pack({k: p.grad for k, p in r.named_parameters() if k.startswith("net.")}).double()
+        return o.detach().double(), gp, t.grad.double()
+
+    o32, gp32, gt32 = oracle(torch.float32)
+    o64, gp64, gt64 = oracle(torch.float64)
     tc = th.cuda().requires_grad_(True)
     est.zero_grad()
     out = est(tc, xx.cuda())
     (out * w.cuda()).sum().backward()
-    assert (out.detach().cpu().double() - out64.detach()).abs().max() <= 1e-3
-    sc = gref.abs().max().item()
-    assert (est.flat.grad.cpu().double() - gref).abs().max().item() / sc <= 2e-3
-    assert (tc.grad.cpu().double() - t64.grad).abs().max().item() / t64.grad.abs().max().item() <= 2e-3
+    assert (out.detach().cpu().double() - o64).abs().max() <= 1e-3
+    # ReLU kinks: a pre-activation within fp32 noise of 0 flips its mask, so gradients are compared with
+    # the larger of 2e-3 and 4x the error torch's own fp32 autograd makes against fp64
+    for got, r32, r64 in ((est.flat.grad.cpu().double(), gp32, gp64), (tc.grad.cpu().double(), gt32, gt64)):
+        sc = r64.abs().max().item()
+        err, err32 = (got - r64).abs().max().item() / sc, (r32 - r64).abs().max().item() / sc
+        assert err <= max(2e-3, 4 * err32), (err, err32)
 
 
 def test_nre_b_loss_matches_oracle(cuda_lib):
