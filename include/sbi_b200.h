@@ -220,6 +220,42 @@ int sbi_b200_slice_init(const sbi_slice_chains* s, float* d_params, void* stream
 int sbi_b200_slice_step(const sbi_slice_chains* s, const float* d_logp, float* d_params,
                         int32_t* d_n_done, void* stream);
 
+/* ---- flow matching (FMPE): VectorFieldMLP behind FlowMatchingEstimator
+ * (net: sbi/neural_nets/net_builders/vector_field_nets.py:610-719, sinusoidal time embedding
+ * :367-421; estimator: sbi/neural_nets/estimators/flowmatching_estimator.py:205-347). */
+#define SBI_FM_MAX_LAYERS 12
+enum {
+  SBI_F_WI = 0, SBI_F_BI = 1,    /* input_layer        [Hp][Dp] */
+  SBI_F_WC = 2, SBI_F_BC = 3,    /* condition_layer    [Hp][Cp] */
+  SBI_F_WM = 4, SBI_F_BM = 5,    /* input_merge_layer  [Hp][2Hp], columns = [input emb | cond emb] */
+  SBI_F_WT = 6, SBI_F_BT = 7,    /* time_linear_layer  [Hp][TEp] */
+  SBI_F_WO = 8, SBI_F_BO = 9,    /* output_layer       [Dp][Hp] */
+  SBI_F_LAYER0 = 12              /* per hidden layer i: W, B, LN gamma, LN beta at SBI_F_LAYER0 + 4i */
+};
+typedef struct {
+  int32_t D, C, H, NL, TE;          /* theta dim, (embedded) condition dim, hidden, layers, time-emb dim */
+  int32_t Dp, Cp, Hp, TEp;
+  int32_t rpc_i, rpc_c, rpc_m, rpc_t, rpc_h, rpc_o;   /* rows per weight chunk of each matrix */
+  int32_t wcap, nbuf, n_params;
+  float noise_scale;                /* sigma_min = 1e-3 */
+  float ln_eps;
+  const float* d_params;
+  const int32_t* d_tab;
+  const float* d_stats;             /* [mean_0(Dp) | std_0(Dp) | ctx_mean(Cp) | ctx_std(Cp) | div_term(TEp/2)] */
+} sbi_fm_model;
+
+/* v(theta_t, t; x) in ORIGINAL space (FlowMatchingEstimator.forward :205-268): d_theta (R,D),
+ * d_cond (R,C) or (1,C) when cond_shared, d_time (R,) or (1,) when time_shared -> d_v (R,D). */
+int sbi_b200_fm_forward(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
+                        int32_t time_shared, float* d_v, void* stream);
+/* flow-matching loss of a batch and its parameter gradient (FlowMatchingEstimator.loss :270-347
+ * + backward): rows = (theta_0, x) pairs, d_time (R,) in [0,1], d_eps (R,D) ~ N(0,I).
+ * d_loss (R,) optional; d_gpart (n_part, n_params) partial gradients of sum_r g_r * loss_r. */
+int sbi_b200_fm_vjp_parts(int64_t R);
+int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
+                         const float* d_eps, const float* d_gout, float g_const, float* d_loss,
+                         float* d_gpart, float* d_loss_acc, void* stream);
+
 /* ---- host-buffer entry points (the end-to-end path a CPU caller binds) ------------------
  * Device staging / optimizer buffers are owned by the caller and passed in a workspace;
  * h_* buffers should be pinned for full PCIe bandwidth.  These calls copy host->device,

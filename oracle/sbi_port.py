@@ -364,6 +364,109 @@ def nre_b_loss(net: RatioEstimator, theta: Tensor, x: Tensor, num_atoms: int, ch
     return -torch.mean(log_prob)
 
 
+# ----------------------------------------------------------------------------- flow matching (FMPE)
+class SinusoidalTimeEmbedding(nn.Module):
+    """sbi/neural_nets/net_builders/vector_field_nets.py:367-421."""
+
+    def __init__(self, embed_dim: int = 16, max_freq: float = 0.01):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.register_buffer("div_term", torch.exp(torch.arange(0, embed_dim, 2) * (-math.log(max_freq) / embed_dim)))
+
+    def forward(self, t: Tensor) -> Tensor:
+        if t.ndim == 1:
+            t = t.unsqueeze(-1)
+        emb = torch.zeros(t.shape[:-1] + (self.embed_dim,), device=t.device, dtype=t.dtype)
+        emb[:, 0::2] = torch.sin(t * self.div_term)
+        emb[:, 1::2] = torch.cos(t * self.div_term)
+        return emb
+
+
+class VectorFieldMLP(nn.Module):
+    """sbi/neural_nets/net_builders/vector_field_nets.py:610-719 (GELU, LayerNorm, skip connections)."""
+
+    def __init__(self, input_dim, condition_dim, time_emb_dim, hidden_features=100, num_layers=5,
+                 sinusoidal_max_freq=1000.0):
+        super().__init__()
+        self.input_layer = nn.Linear(input_dim, hidden_features)
+        self.condition_layer = nn.Linear(condition_dim, hidden_features)
+        self.input_merge_layer = nn.Linear(2 * hidden_features, hidden_features)
+        self.time_emb = SinusoidalTimeEmbedding(time_emb_dim, sinusoidal_max_freq)
+        self.activation = nn.GELU()
+        self.layers = nn.ModuleList([nn.Linear(hidden_features, hidden_features) for _ in range(num_layers)])
+        self.layers_norm = nn.ModuleList([nn.LayerNorm(hidden_features) for _ in range(num_layers)])
+        self.time_linear_layer = nn.Linear(time_emb_dim, hidden_features)
+        self.output_layer = nn.Linear(hidden_features, input_dim)
+        nn.init.zeros_(self.output_layer.weight)
+
+    def forward(self, input, condition, t):
+        h = self.input_merge_layer(self.activation(torch.cat([self.input_layer(input), self.condition_layer(condition)], -1)))
+        t_emb = self.time_linear_layer(self.time_emb(t))
+        h = self.activation(h)
+        for lin, ln in zip(self.layers, self.layers_norm):
+            h_old = h
+            h = self.activation(lin(h))
+            h = h + t_emb
+            h = h + h_old
+            h = ln(h)
+        return self.output_layer(h)
+
+
+class FlowMatchingEstimator(nn.Module):
+    """sbi/neural_nets/estimators/flowmatching_estimator.py:120-347 (no gaussian baseline)."""
+
+    def __init__(self, net, input_shape, condition_shape, embedding_net, mean_0, std_0, noise_scale=1e-3):
+        super().__init__()
+        self.net, self._embedding_net, self.noise_scale = net, embedding_net, noise_scale
+        self.input_shape, self.condition_shape = torch.Size(input_shape), torch.Size(condition_shape)
+        self.register_buffer("mean_0", torch.as_tensor(mean_0, dtype=torch.float32).expand(input_shape).clone())
+        self.register_buffer("std_0", torch.as_tensor(std_0, dtype=torch.float32).expand(input_shape).clone())
+        # base distribution N(mean_base, std_base) of the ODE (estimators/base.py: ConditionalVectorFieldEstimator)
+        self.register_buffer("_mean_base", torch.zeros(1, *self.input_shape))
+        self.register_buffer("_std_base", torch.ones(1, *self.input_shape))
+        self.register_buffer("_theta_shift", torch.zeros(1, *self.input_shape, dtype=torch.float32))
+        self.register_buffer("_theta_scale", torch.ones(1, *self.input_shape, dtype=torch.float32))
+        self.register_buffer("_compose_standardization", torch.tensor(False), persistent=True)
+
+    def _stats(self, time):
+        t = time.view(-1, 1)
+        mu_t = (1 - t) * self.mean_0.view(1, -1)
+        std_t = torch.sqrt(((1 - t) * self.std_0.view(1, -1)) ** 2 + t ** 2 + 1e-6)
+        return mu_t, std_t
+
+    def forward(self, input, condition, time):
+        bshape = torch.broadcast_shapes(input.shape[:-1], condition.shape[:-1])
+        cond = torch.broadcast_to(self._embedding_net(condition), bshape + condition.shape[-1:]).reshape(-1, condition.shape[-1])
+        inp = torch.broadcast_to(input, bshape + self.input_shape).reshape(-1, input.shape[-1])
+        time = torch.broadcast_to(time, bshape).reshape(-1)
+        mu_t, std_t = self._stats(time)
+        v_out = self.net((inp - mu_t) / std_t, cond, time)
+        v = v_out * torch.sqrt(1 + self.std_0.view(1, -1) ** 2) - self.mean_0.view(1, -1)
+        return v.reshape(*bshape, *self.input_shape)
+
+    def loss(self, input, condition, times=None, theta_1=None):
+        if times is None:
+            times = torch.rand(input.shape[:-1], device=input.device, dtype=input.dtype)
+        times_ = times[..., None]
+        if theta_1 is None:
+            theta_1 = torch.randn_like(input)
+        theta_t = (1 - times_) * input + (times_ + self.noise_scale) * theta_1
+        vector_field = theta_1 - input
+        cond = self._embedding_net(condition)
+        mu_t, std_t = self._stats(times.reshape(-1))
+        v_out = self.net((theta_t - mu_t) / std_t, cond, times.reshape(-1))
+        target = (vector_field + self.mean_0.view(1, -1)) / torch.sqrt(1 + self.std_0.view(1, -1) ** 2)
+        return torch.mean((v_out - target) ** 2, dim=-1)
+
+
+def build_flow_matching_estimator(batch_x, batch_y, hidden_features=100, num_layers=5, time_embedding_dim=32):
+    """vector_field_nets.py:136-338 with the FMPE defaults (mlp, sinusoidal time embedding max_freq 1000)."""
+    net = VectorFieldMLP(batch_x[0].numel(), batch_y[0].numel(), time_embedding_dim, hidden_features, num_layers)
+    mean_0, std_0 = z_standardization(batch_x, False)
+    emb = nn.Sequential(standardizing_net(batch_y, False), nn.Identity())
+    return FlowMatchingEstimator(net, batch_x[0].shape, batch_y[0].shape, emb, mean_0, std_0)
+
+
 # ----------------------------------------------------------------------------- training loop
 class ReferenceTrainer:
     """First-round NPE/NLE training exactly as the reference runs it on one device:

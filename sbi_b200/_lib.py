@@ -73,6 +73,21 @@ class Pairs(C.Structure):
 R_W0, R_B0, R_WF, R_BF, R_BLK0 = 0, 1, 2, 3, 4
 
 
+class FmModel(C.Structure):
+    _fields_ = [
+        ("D", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("NL", C.c_int32), ("TE", C.c_int32),
+        ("Dp", C.c_int32), ("Cp", C.c_int32), ("Hp", C.c_int32), ("TEp", C.c_int32),
+        ("rpc_i", C.c_int32), ("rpc_c", C.c_int32), ("rpc_m", C.c_int32), ("rpc_t", C.c_int32),
+        ("rpc_h", C.c_int32), ("rpc_o", C.c_int32),
+        ("wcap", C.c_int32), ("nbuf", C.c_int32), ("n_params", C.c_int32),
+        ("noise_scale", C.c_float), ("ln_eps", C.c_float),
+        ("d_params", C.c_void_p), ("d_tab", C.c_void_p), ("d_stats", C.c_void_p),
+    ]
+
+
+F_WI, F_BI, F_WC, F_BC, F_WM, F_BM, F_WT, F_BT, F_WO, F_BO, F_LAYER0 = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 12
+
+
 class SliceChains(C.Structure):
     _fields_ = [
         ("C", C.c_int32), ("D", C.c_int32), ("num_samples", C.c_int32), ("tuning", C.c_int32),
@@ -121,6 +136,11 @@ _EXPORTS = {
     "sbi_b200_ratio_vjp_parts": (C.c_int, [C.c_int64]),
     "sbi_b200_ratio_vjp": (C.c_int, [C.POINTER(RatioModel), C.POINTER(Pairs), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sbi_b200_fm_forward": (C.c_int, [C.POINTER(FmModel), C.POINTER(Rows), C.c_void_p, C.c_int32, C.c_void_p,
+                                      C.c_void_p]),
+    "sbi_b200_fm_vjp_parts": (C.c_int, [C.c_int64]),
+    "sbi_b200_fm_loss_vjp": (C.c_int, [C.POINTER(FmModel), C.POINTER(Rows), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_slice_init": (C.c_int, [C.POINTER(SliceChains), C.c_void_p, C.c_void_p]),
     "sbi_b200_slice_step": (C.c_int, [C.POINTER(SliceChains), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_reduce_partials": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p,

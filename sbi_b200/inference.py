@@ -485,3 +485,140 @@ class NRE_B(_FlowTrainer):
 
 SNRE_B = NRE_B
 SNRE = NRE_B
+
+
+# =================================================================================================
+class FMPE(_FlowTrainer):
+    """Flow-matching posterior estimation (reference: trainers/vfpe/fmpe.py, base_vf_inference.py:
+    train :206-350, validation at fixed times :524-543, EMA-smoothed summaries :589-636, z-score of
+    the loss as stopping rule :352-420)."""
+
+    def __init__(self, prior=None, density_estimator: Union[str, Callable] = "mlp", device: str = "cuda",
+                 logging_level: Union[int, str] = "WARNING", summary_writer=None, tracker=None,
+                 show_progress_bars: bool = False):
+        from .flowmatching import posterior_flow_nn
+        self._prior = prior
+        self._device = _process_device(device)
+        self._build_neural_net = (posterior_flow_nn(model=density_estimator)
+                                  if isinstance(density_estimator, str) else density_estimator)
+        self._neural_net = None
+        self._theta = self._x = None
+        self.epoch, self._val_loss = 0, float("Inf")
+        self._summary = dict(epochs_trained=[], best_validation_loss=[], validation_loss=[], training_loss=[],
+                             epoch_durations_sec=[])
+        self._dist = None
+
+    def train(self, training_batch_size: int = 200, learning_rate: float = 5e-4, validation_fraction: float = 0.1,
+              stop_after_epochs: int = 20, max_num_epochs: int = 2 ** 31 - 1, clip_max_norm: Optional[float] = 5.0,
+              calibration_kernel=None, ema_loss_decay: float = 0.1, validation_times: Union[Tensor, int] = 10,
+              validation_times_nugget: float = 0.05, resume_training: bool = False, **kwargs):
+        if self._theta is None:
+            raise RuntimeError("call append_simulations() first")
+        lib = L.load()
+        dev = self._device
+        N = self._theta.shape[0]
+        x2d = self._x.reshape(N, -1).contiguous()
+        n_train = int((1 - validation_fraction) * N)
+        n_val = N - n_train
+        if not resume_training or not hasattr(self, "train_indices"):
+            perm = torch.randperm(N)
+            self.train_indices, self.val_indices = perm[:n_train], perm[n_train:]
+        if self._neural_net is None:
+            tr = self.train_indices.to(dev)
+            self._neural_net = self._build_neural_net(self._theta[tr].cpu(), self._x[tr].cpu())
+        net = self._neural_net.to(dev)
+        self._neural_net = net
+        P, D = net.layout.n_params, net.layout.D
+        B, Bv = min(training_batch_size, n_train), min(training_batch_size, n_val)
+        steps, vsteps = n_train // B, (n_val // Bv if Bv > 0 else 0)
+        if isinstance(validation_times, int):
+            validation_times = torch.linspace(net.t_min + validation_times_nugget,
+                                              net.t_max - validation_times_nugget, validation_times)
+        vt = validation_times.to(dev).float()
+        if not resume_training or not hasattr(self, "_opt_state"):
+            self._opt_state = torch.zeros(2 * P, dtype=torch.float32, device=dev)
+            self._opt_step = torch.zeros(2, dtype=torch.int32, device=dev)
+            self.epoch, self._val_loss = 0, float("Inf")
+        train_idx, val_idx = self.train_indices.to(dev), self.val_indices.to(dev)
+        grad = torch.zeros(P, dtype=torch.float32, device=dev)
+        loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
+        max_norm = float(clip_max_norm) if clip_max_norm is not None else 0.0
+        world = self._dist[1] if self._dist is not None else 1
+
+        def converged() -> bool:   # base_vf_inference.py:352-420
+            if self.epoch == 0:
+                self._best_val_loss, self._epochs_since_last_improvement, self._best_flat = float("inf"), 0, None
+            if self._val_loss < self._best_val_loss:
+                self._best_val_loss, self._epochs_since_last_improvement = self._val_loss, 0
+                self._best_flat = net.flat.data.clone()
+            else:
+                if len(self._summary["validation_loss"]) >= stop_after_epochs:
+                    recent = torch.tensor(self._summary["validation_loss"][-stop_after_epochs * 2:])
+                    z = (self._val_loss - self._best_val_loss) / recent.std().item()
+                    self._epochs_since_last_improvement = self._epochs_since_last_improvement + 1 if z > 2.0 else 0
+                else:
+                    return False
+            if self._epochs_since_last_improvement > stop_after_epochs - 1:
+                if self._best_flat is not None:
+                    net.flat.data.copy_(self._best_flat)
+                return True
+            return False
+
+        while self.epoch <= max_num_epochs and not converged():
+            t0 = time.time()
+            perm = train_idx[torch.randperm(n_train, device=dev)]
+            loss_acc.zero_()
+            for s in range(steps):
+                idx = perm[s * B:(s + 1) * B].contiguous()
+                tms = torch.rand(B, device=dev)
+                eps = torch.randn(B, D, device=dev)
+                _, gpart, n_part = net.loss_raw(self._theta, x2d, tms, eps, index=idx, g_const=1.0 / (B * world),
+                                                loss_acc=loss_acc, want_loss=False)
+                L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad), L.stream_ptr()), "reduce")
+                if world > 1:
+                    torch.distributed.all_reduce(grad)
+                L.check(lib.sbi_b200_adam_clip_step(L.ptr(net.flat.data), L.ptr(grad), L.ptr(self._opt_state),
+                                                    L.ptr(self._opt_step), L.ptr(net.net._mask), P, learning_rate,
+                                                    0.9, 0.999, 1e-8, max_norm, 1.0, L.stream_ptr()), "adam")
+            train_stats = loss_acc.clone()
+            # validation: every batch evaluated at all validation times (:524-543); g = 0 -> loss only
+            loss_acc.zero_()
+            if vsteps > 0:
+                vperm = val_idx[torch.randperm(n_val, device=dev)]
+                nt = vt.shape[0]
+                for s in range(vsteps):
+                    idx = vperm[s * Bv:(s + 1) * Bv].repeat(nt).contiguous()
+                    tms = vt.repeat_interleave(Bv).contiguous()
+                    eps = torch.randn(Bv * nt, D, device=dev)
+                    net.loss_raw(self._theta, x2d, tms, eps, index=idx, g_const=0.0, loss_acc=loss_acc, want_loss=False)
+            tl, tb = train_stats.tolist()
+            vl, vb = loss_acc.tolist()
+            if tb > 0 or vb > 0:
+                raise AssertionError("NaN/Inf present in FMPE loss.")
+            train_loss = tl / (steps * B)
+            val_loss = vl / (vsteps * Bv * vt.shape[0]) if vsteps > 0 else float("nan")
+            # the reference normalises by len(loader) * loader.batch_size, i.e. WITHOUT the repeat over times
+            val_loss *= vt.shape[0] if vsteps > 0 else 1.0
+            if self._summary["training_loss"]:
+                train_loss = (1 - ema_loss_decay) * self._summary["training_loss"][-1] + ema_loss_decay * train_loss
+                val_loss = (1 - ema_loss_decay) * self._summary["validation_loss"][-1] + ema_loss_decay * val_loss
+            self._val_loss = val_loss
+            self._summary["training_loss"].append(train_loss)
+            self._summary["validation_loss"].append(val_loss)
+            self._summary["epoch_durations_sec"].append(time.time() - t0)
+            self.epoch += 1
+        if self.epoch > max_num_epochs:
+            if self._val_loss < self._best_val_loss:
+                self._best_val_loss, self._best_flat = self._val_loss, net.flat.data.clone()
+            elif self._best_flat is not None:
+                net.flat.data.copy_(self._best_flat)
+        self._summary["epochs_trained"].append(self.epoch)
+        self._summary["best_validation_loss"].append(self._best_val_loss)
+        return deepcopy(net)
+
+    def build_posterior(self, density_estimator=None, prior=None, sample_with: str = "ode", **kwargs):
+        from .posteriors import VectorFieldPosterior
+        if sample_with != "ode":
+            raise NotImplementedError("FMPE.build_posterior implements sample_with='ode'")
+        est = deepcopy(density_estimator if density_estimator is not None else self._neural_net)
+        return VectorFieldPosterior(est, prior if prior is not None else self._prior, device=self._device)

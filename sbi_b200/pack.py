@@ -432,3 +432,88 @@ class RatioLayout(_LayoutOps):
 
 
 RatioLayout.family = "ratio"
+
+
+@dataclass
+class FmLayout(_LayoutOps):
+    """Packed layout of the flow-matching VectorFieldMLP (include/sbi_b200.h `sbi_fm_model`), tensor
+    names as in /root/reference/sbi/neural_nets/net_builders/vector_field_nets.py:610-719 under the
+    estimator attribute `net` (FlowMatchingEstimator.net)."""
+    D: int
+    C: int
+    H: int = 100
+    NL: int = 5
+    TE: int = 32
+    wcap_target: int = 3200
+    n_params: int = 0
+    index: Dict[str, np.ndarray] = field(default_factory=dict, repr=False)
+
+    def __post_init__(self):
+        D, C, H, NL, TE = self.D, self.C, self.H, self.NL, self.TE
+        if NL < 2 or NL > 12:
+            raise ValueError("2 <= num_layers <= 12")
+        if TE % 2:
+            raise ValueError("embedding dimension must be even")
+        self.Dp, self.Cp, self.Hp, self.TEp = round4(D), round4(C), round4(H), round4(TE)
+        Hp = self.Hp
+        cap = max(self.wcap_target, 4 * 2 * Hp)
+
+        def rows(rowlen, nmax):
+            return max(4, min(nmax, (cap // rowlen) & ~3))
+
+        self.rpc_i, self.rpc_c, self.rpc_m = rows(self.Dp, Hp), rows(self.Cp, Hp), rows(2 * Hp, Hp)
+        self.rpc_t, self.rpc_h, self.rpc_o = rows(self.TEp, Hp), rows(Hp, Hp), rows(Hp, self.Dp)
+        used = max(self.rpc_i * self.Dp, self.rpc_c * self.Cp, self.rpc_m * 2 * Hp, self.rpc_t * self.TEp,
+                   self.rpc_h * Hp, self.rpc_o * Hp)
+        self.wcap = (used + 31) & ~31
+        off = 0
+
+        def take(n):
+            nonlocal off
+            o = off
+            off += round4(n)
+            return o
+
+        tab = np.zeros(L.F_LAYER0 + 4 * 12, np.int32)
+        idx: Dict[str, np.ndarray] = {}
+
+        def lin(name, slot_w, slot_b, N, K, Kp, cols=None, Np=None):
+            Np = round4(N) if Np is None else Np
+            o = take(Np * Kp)
+            tab[slot_w] = o
+            c = np.arange(K) if cols is None else cols
+            idx[name + ".weight"] = o + np.arange(N)[:, None] * Kp + c[None, :]
+            o = take(Np)
+            tab[slot_b] = o
+            idx[name + ".bias"] = o + np.arange(N)
+
+        lin("net.input_layer", L.F_WI, L.F_BI, H, D, self.Dp)
+        lin("net.condition_layer", L.F_WC, L.F_BC, H, C, self.Cp)
+        lin("net.input_merge_layer", L.F_WM, L.F_BM, H, 2 * H, 2 * Hp,
+            cols=np.concatenate([np.arange(H), Hp + np.arange(H)]))
+        lin("net.time_linear_layer", L.F_WT, L.F_BT, H, TE, self.TEp)
+        lin("net.output_layer", L.F_WO, L.F_BO, D, H, Hp)
+        for i in range(NL):
+            lin(f"net.layers.{i}", L.F_LAYER0 + 4 * i, L.F_LAYER0 + 4 * i + 1, H, H, Hp)
+            o = take(Hp)
+            tab[L.F_LAYER0 + 4 * i + 2] = o
+            idx[f"net.layers_norm.{i}.weight"] = o + np.arange(H)
+            o = take(Hp)
+            tab[L.F_LAYER0 + 4 * i + 3] = o
+            idx[f"net.layers_norm.{i}.bias"] = o + np.arange(H)
+        self.n_params = off
+        self.index = idx
+        self.tab = tab
+        self.buffers = {}
+
+    def fill_struct(self, s: "L.FmModel", nbuf: int):
+        s.D, s.C, s.H, s.NL, s.TE = self.D, self.C, self.H, self.NL, self.TE
+        s.Dp, s.Cp, s.Hp, s.TEp = self.Dp, self.Cp, self.Hp, self.TEp
+        s.rpc_i, s.rpc_c, s.rpc_m = self.rpc_i, self.rpc_c, self.rpc_m
+        s.rpc_t, s.rpc_h, s.rpc_o = self.rpc_t, self.rpc_h, self.rpc_o
+        s.wcap, s.nbuf, s.n_params = self.wcap, nbuf, self.n_params
+        s.noise_scale, s.ln_eps = 1e-3, 1e-5
+        return s
+
+
+FmLayout.family = "fm"

@@ -364,3 +364,51 @@ class RejectionPosterior:
         self.potential_fn.set_x(x)
         return self.potential_fn(torch.as_tensor(theta, dtype=torch.float32).to(self._device),
                                  track_gradients=track_gradients)
+
+
+class VectorFieldPosterior:
+    """Posterior of a flow-matching estimator sampled by integrating its ODE (reference:
+    /root/reference/sbi/inference/posteriors/vector_field_posterior.py: sample :155-329,
+    sample_via_ode :436-465); draws outside the prior support are rejected like the reference
+    (`reject_outside_prior=True`)."""
+
+    def __init__(self, vector_field_estimator, prior, device: Optional[str] = None, max_sampling_batch_size: int = 10_000):
+        self.vector_field_estimator = vector_field_estimator
+        self._device = device or str(vector_field_estimator.flat.device)
+        self.prior = prior_to_device(prior, self._device)
+        self.max_sampling_batch_size = max_sampling_batch_size
+        self.default_x = None
+        self.num_function_evaluations = 0
+
+    def set_default_x(self, x):
+        self.default_x = x
+        return self
+
+    @torch.no_grad()
+    def sample(self, sample_shape=torch.Size(), x: Optional[Tensor] = None, sample_with: str = "ode",
+               reject_outside_prior: bool = True, max_sampling_batch_size: Optional[int] = None,
+               show_progress_bars: bool = False, **kwargs) -> Tensor:
+        from .flowmatching import sample_ode
+        if sample_with != "ode":
+            raise NotImplementedError("sample_with='ode' only")
+        x = x if x is not None else self.default_x
+        if x is None:
+            raise ValueError("Context `x` needed when a default has not been set.")
+        x = torch.as_tensor(x, dtype=torch.float32).to(self._device)
+        num_samples = torch.Size(sample_shape).numel()
+        est = self.vector_field_estimator
+
+        def proposal(shape, **kw):
+            s, nfe = sample_ode(est, torch.Size(shape).numel(), x, return_nfe=True)
+            self.num_function_evaluations += nfe
+            return s.unsqueeze(1)
+
+        if reject_outside_prior and self.prior is not None:
+            samples = accept_reject_sample(
+                proposal=proposal, accept_reject_fn=lambda th: within_support(self.prior, th.reshape(-1, th.shape[-1])),
+                num_samples=num_samples,
+                max_sampling_batch_size=max_sampling_batch_size or max(self.max_sampling_batch_size, num_samples))[0]
+            samples = samples[:, 0]
+        else:
+            samples = proposal((num_samples,))[:, 0]
+        return samples.reshape(*torch.Size(sample_shape), -1)
