@@ -337,41 +337,72 @@ def run_b200(args):
     h_loss = torch.zeros(2).pin_memory()
     perm_host = torch.randperm(n_train)
     e2e = None
-    if world == 1:
-        def host_step(i):
-            idx = perm_host[(i * B) % (n_train - B):][:B]
-            torch.index_select(theta, 0, idx, out=h_th)       # host batch assembly (the
-            torch.index_select(x, 0, idx, out=h_x)            # reference's DataLoader collation)
-            mm = est._model(nbuf=3)
+
+    def host_step(i):
+        """One optimisation step from a pinned host batch.  N=1: the single blocking C-ABI call
+        `sbi_b200_nsf_train_step_host` (H2D, kernels, D2H inside).  N>1: the same pieces with the
+        gradient all-reduce between reduce and Adam (H2D / D2H still inside the step)."""
+        idx = perm_host[(i * B) % (n_train - B):][:B]
+        torch.index_select(theta, 0, idx, out=h_th)       # host batch assembly (the reference's
+        torch.index_select(x, 0, idx, out=h_x)            # DataLoader collation)
+        mm = est._model(nbuf=3)
+        if world == 1:
             L.check(lib.sbi_b200_nsf_train_step_host(
                 C.byref(mm), C.byref(ws), h_th.data_ptr(), h_x.data_ptr(), B, 5e-4, 0.9, 0.999, 1e-8,
                 5.0, h_loss.data_ptr(), L.stream_ptr()), "train_step_host")
-        for i in range(W):
-            host_step(i)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(K):
-            host_step(i)
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / K
-        # log_prob e2e on 2^20 host rows
-        Rh = 1 << 20
-        h_eval = th_eval[:Rh].cpu().pin_memory()
-        h_xo = x_o.cpu().pin_memory()
-        h_out = torch.empty(Rh).pin_memory()
-        mm = est._model(nbuf=2)
-        for _ in range(2):
-            L.check(lib.sbi_b200_nsf_logprob_host(C.byref(mm), C.byref(ws), h_eval.data_ptr(), h_xo.data_ptr(),
-                                                  Rh, 1, h_out.data_ptr(), L.stream_ptr()), "logprob_host")
-        t0 = time.perf_counter()
-        for _ in range(5):
-            L.check(lib.sbi_b200_nsf_logprob_host(C.byref(mm), C.byref(ws), h_eval.data_ptr(), h_xo.data_ptr(),
-                                                  Rh, 1, h_out.data_ptr(), L.stream_ptr()), "logprob_host")
-        lp_e2e_s = (time.perf_counter() - t0) / 5
-        e2e = {"value": B / e2e_s, "unit": "samples/s", "ms_per_step": e2e_s * 1e3,
-               "h2d_bytes_per_step": B * 2 * DIM * 4, "d2h_bytes_per_step": 8,
-               "log_prob": {"value": Rh / lp_e2e_s, "unit": "evals/s", "rows": Rh,
-                            "h2d_bytes_per_step": Rh * DIM * 4 + DIM * 4, "d2h_bytes_per_step": Rh * 4}}
+            return
+        st_in[:B].copy_(h_th, non_blocking=True)
+        st_c[:B].copy_(h_x, non_blocking=True)
+        loss_acc.zero_()
+        rows = L.Rows(st_in.data_ptr(), st_c.data_ptr(), None, B, 0)
+        L.check(lib.sbi_b200_nsf_vjp(C.byref(mm), C.byref(rows), None, -1.0 / B, None, L.ptr(gpart), None, None,
+                                     L.ptr(loss_acc), L.stream_ptr()), "vjp")
+        L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad), L.stream_ptr()), "reduce")
+        dist.all_reduce(grad)
+        L.check(lib.sbi_b200_adam_clip_step(L.ptr(est.flat.data), L.ptr(grad), L.ptr(state), L.ptr(step_ctr),
+                                            L.ptr(mask), P, 5e-4, 0.9, 0.999, 1e-8, 5.0, 1.0 / world,
+                                            L.stream_ptr()), "adam")
+        h_loss.copy_(loss_acc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(W):
+        host_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        host_step(i)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / K
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    # log_prob e2e on 2^20 host rows per GPU
+    Rh = 1 << 20
+    h_eval = th_eval[:Rh].cpu().pin_memory()
+    h_xo = x_o.cpu().pin_memory()
+    h_out = torch.empty(Rh).pin_memory()
+    mm = est._model(nbuf=2)
+    for _ in range(2):
+        L.check(lib.sbi_b200_nsf_logprob_host(C.byref(mm), C.byref(ws), h_eval.data_ptr(), h_xo.data_ptr(),
+                                              Rh, 1, h_out.data_ptr(), L.stream_ptr()), "logprob_host")
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        L.check(lib.sbi_b200_nsf_logprob_host(C.byref(mm), C.byref(ws), h_eval.data_ptr(), h_xo.data_ptr(),
+                                              Rh, 1, h_out.data_ptr(), L.stream_ptr()), "logprob_host")
+    barrier()
+    lp_e2e_s = (time.perf_counter() - t0) / 5
+    t = torch.tensor([lp_e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    lp_e2e_s = float(t.item())
+    e2e = {"value": world * B / e2e_s, "unit": "samples/s", "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": world * B * 2 * DIM * 4, "d2h_bytes_per_step": world * 8,
+           "api": "sbi_b200_nsf_train_step_host (C ABI, pinned host batch)" if world == 1 else
+                  "host batch -> H2D -> vjp -> reduce -> NCCL all-reduce -> clip+Adam -> D2H loss, per rank",
+           "log_prob": {"value": world * Rh / lp_e2e_s, "unit": "evals/s", "rows": world * Rh,
+                        "h2d_bytes_per_step": world * (Rh * DIM * 4 + DIM * 4), "d2h_bytes_per_step": world * Rh * 4}}
     clk = clocks.stop()
 
     # ---- CPU baseline (bounded sample), rank 0 at N=1 only ---------------------------------------

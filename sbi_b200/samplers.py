@@ -207,9 +207,9 @@ def rejection_sample(potential_fn: Callable, proposal: Any, theta_transform: Opt
 def resample_given_potential_fn(proposal: Any, potential_fn: Callable, transform: torch_tf.Transform,
                                 num_candidate_samples: int = 10_000, num_batches: int = 1,
                                 num_inits: int = 1, **kwargs: Any) -> Tensor:
-    """init_strategy.py:67-114, vectorised over `num_inits` chains: ONE batch of candidates is
-    weighted by the potential and `num_inits` independent multinomial draws are taken per chain
-    batch, instead of num_chains x 10 000 sequential potential evaluations."""
+    """init_strategy.py:67-114 for `num_inits` chains: like the reference, every chain draws its own
+    batch of proposal candidates, weights them by the potential and resamples one; each batch is ONE
+    potential-kernel launch (10 000 rows) instead of a Python-level evaluation per chain."""
     with torch.set_grad_enabled(False):
         outs = []
         for _ in range(num_inits):
