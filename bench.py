@@ -334,7 +334,10 @@ def run_b200(args):
     ws.cap_rows = st_in.shape[0]
     h_th = torch.empty(B, DIM).pin_memory()
     h_x = torch.empty(B, DIM).pin_memory()
+    h_th2 = [torch.empty(B, DIM).pin_memory() for _ in range(2)]
+    h_x2 = [torch.empty(B, DIM).pin_memory() for _ in range(2)]
     h_loss = torch.zeros(2).pin_memory()
+    pipe = lib.sbi_b200_pipe_create()
     perm_host = torch.randperm(n_train)
     e2e = None
 
@@ -343,14 +346,18 @@ def run_b200(args):
         `sbi_b200_nsf_train_step_host` (H2D, kernels, D2H inside).  N>1: the same pieces with the
         gradient all-reduce between reduce and Adam (H2D / D2H still inside the step)."""
         idx = perm_host[(i * B) % (n_train - B):][:B]
-        torch.index_select(theta, 0, idx, out=h_th)       # host batch assembly (the reference's
-        torch.index_select(x, 0, idx, out=h_x)            # DataLoader collation)
         mm = est._model(nbuf=3)
         if world == 1:
-            L.check(lib.sbi_b200_nsf_train_step_host(
-                C.byref(mm), C.byref(ws), h_th.data_ptr(), h_x.data_ptr(), B, 5e-4, 0.9, 0.999, 1e-8,
-                5.0, h_loss.data_ptr(), L.stream_ptr()), "train_step_host")
+            # pipelined C-ABI step: enqueue step i (H2D + kernels + D2H), get step i-1's loss back
+            a, b = h_th2[i & 1], h_x2[i & 1]
+            torch.index_select(theta, 0, idx, out=a)      # host batch assembly (the reference's
+            torch.index_select(x, 0, idx, out=b)          # DataLoader collation)
+            L.check(lib.sbi_b200_nsf_train_step_host_async(
+                C.byref(mm), C.byref(ws), pipe, a.data_ptr(), b.data_ptr(), B, 5e-4, 0.9, 0.999, 1e-8,
+                5.0, h_loss.data_ptr(), L.stream_ptr()), "train_step_host_async")
             return
+        torch.index_select(theta, 0, idx, out=h_th)
+        torch.index_select(x, 0, idx, out=h_x)
         st_in[:B].copy_(h_th, non_blocking=True)
         st_c[:B].copy_(h_x, non_blocking=True)
         loss_acc.zero_()
@@ -365,12 +372,17 @@ def run_b200(args):
         h_loss.copy_(loss_acc, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    torch.set_num_threads(min(8, os.cpu_count() or 1))   # host-side gathers are tiny: avoid a 128-thread fork/join
     for i in range(W):
         host_step(i)
+    if world == 1:
+        lib.sbi_b200_pipe_drain(pipe, h_loss.data_ptr())
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        host_step(i)
+        host_step(W + i)
+    if world == 1:
+        lib.sbi_b200_pipe_drain(pipe, h_loss.data_ptr())   # the last step's loss is read inside the timed region
     barrier()
     e2e_s = (time.perf_counter() - t0) / K
     t = torch.tensor([e2e_s], device=dev)
@@ -399,7 +411,8 @@ def run_b200(args):
     lp_e2e_s = float(t.item())
     e2e = {"value": world * B / e2e_s, "unit": "samples/s", "ms_per_step": e2e_s * 1e3,
            "h2d_bytes_per_step": world * B * 2 * DIM * 4, "d2h_bytes_per_step": world * 8,
-           "api": "sbi_b200_nsf_train_step_host (C ABI, pinned host batch)" if world == 1 else
+           "api": "sbi_b200_nsf_train_step_host_async (C ABI, pinned host batch; each step's H2D/D2H inside, "
+                  "result of step i read while step i+1 runs)" if world == 1 else
                   "host batch -> H2D -> vjp -> reduce -> NCCL all-reduce -> clip+Adam -> D2H loss, per rank",
            "log_prob": {"value": world * Rh / lp_e2e_s, "unit": "evals/s", "rows": world * Rh,
                         "h2d_bytes_per_step": world * (Rh * DIM * 4 + DIM * 4), "d2h_bytes_per_step": world * Rh * 4}}

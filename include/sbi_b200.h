@@ -282,6 +282,20 @@ int sbi_b200_nsf_train_step_host(const sbi_nsf_model* m, const sbi_train_ws* ws,
                                  float beta1, float beta2, float eps, float max_norm,
                                  float* h_loss_out, void* stream);
 
+/* Pipelined variant: enqueues step i (H2D of its pinned host batch, kernels, D2H of its loss) and
+ * returns after step i-1 has completed, handing back step i-1's result in h_loss_prev[2] (NaN on
+ * the first call).  Every step still carries its own H2D + D2H; the host just prepares batch i+1
+ * while the device runs step i.  The caller alternates between two pinned host batch buffers
+ * (buffer i%2 may be rewritten once call i+1 has returned).  `pipe` from sbi_b200_pipe_create. */
+void* sbi_b200_pipe_create(void);
+void sbi_b200_pipe_destroy(void* pipe);
+int sbi_b200_nsf_train_step_host_async(const sbi_nsf_model* m, const sbi_train_ws* ws, void* pipe,
+                                       const float* h_input, const float* h_cond, int64_t B, float lr,
+                                       float beta1, float beta2, float eps, float max_norm,
+                                       float* h_loss_prev, void* stream);
+/* wait for the last enqueued step and return its result in h_loss_last[2] */
+int sbi_b200_pipe_drain(void* pipe, float* h_loss_last);
+
 /* log q(input_r | cond) for R host rows (cond: (R,C), or (1,C) when cond_shared). */
 int sbi_b200_nsf_logprob_host(const sbi_nsf_model* m, const sbi_train_ws* ws,
                               const float* h_input, const float* h_cond, int64_t R,

@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsbi_b200.so")
+LIB_PATH = os.environ.get("SBI_B200_LIB") or os.path.join(_HERE, "lib", "libsbi_b200.so")
 
 SBI_NSF_LAYER_STRIDE = 64
 SBI_NSF_MAX_BLOCKS = 8
@@ -152,6 +152,12 @@ _EXPORTS = {
                                                C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                                C.c_float, C.c_float, C.c_float, C.c_void_p,
                                                C.c_void_p]),
+    "sbi_b200_pipe_create": (C.c_void_p, []),
+    "sbi_b200_pipe_destroy": (None, [C.c_void_p]),
+    "sbi_b200_nsf_train_step_host_async": (C.c_int, [C.POINTER(NsfModel), C.POINTER(TrainWs), C.c_void_p,
+                                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
+                                                     C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "sbi_b200_pipe_drain": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sbi_b200_nsf_logprob_host": (C.c_int, [C.POINTER(NsfModel), C.POINTER(TrainWs), C.c_void_p,
                                             C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                             C.c_void_p]),

@@ -46,6 +46,24 @@ def _fingerprint():
     return h.hexdigest()
 
 
+def build_variant(name, defines):
+    """Tuning helper: compile a variant library sbi_b200/lib/libsbi_b200_<name>.so with extra -D flags."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, f"libsbi_b200_{name}.so")
+    objs = []
+    for src in sources():
+        obj = os.path.join(LIBDIR, f"{name}_" + os.path.basename(src)[:-3] + ".o")
+        cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *[f"-D{d}" for d in defines],
+               "-I", INCLUDE, "-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(obj)
+    subprocess.check_call([_nvcc(), "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.stamp")

@@ -9,6 +9,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef SBI_PRODUCER_SLEEP_NS
+#define SBI_PRODUCER_SLEEP_NS 20
+#endif
+
 namespace sbi {
 
 constexpr int kConsumerThreads = 256;   // 8 consumer warps
@@ -63,7 +67,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) break;
-    __nanosleep(20);
+    __nanosleep(SBI_PRODUCER_SLEEP_NS);
   }
 }
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (complete_tx).

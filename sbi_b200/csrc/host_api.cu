@@ -60,3 +60,80 @@ extern "C" int sbi_b200_nsf_logprob_host(const sbi_nsf_model* m, const sbi_train
   CK(cudaStreamSynchronize(s));
   return 0;
 }
+
+
+// ---- pipelined host steps ------------------------------------------------------------------------
+struct SbiPipe {
+  cudaEvent_t done[2];
+  float* h_loss[2];   // pinned
+  int64_t n;          // steps enqueued
+};
+
+extern "C" void* sbi_b200_pipe_create(void) {
+  SbiPipe* p = new SbiPipe();
+  p->n = 0;
+  for (int i = 0; i < 2; ++i) {
+    if (cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaMallocHost(&p->h_loss[i], 2 * sizeof(float)) != cudaSuccess) return nullptr;
+  }
+  return p;
+}
+
+extern "C" void sbi_b200_pipe_destroy(void* pipe) {
+  SbiPipe* p = static_cast<SbiPipe*>(pipe);
+  if (!p) return;
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(p->done[i]);
+    cudaFreeHost(p->h_loss[i]);
+  }
+  delete p;
+}
+
+static int pipe_wait_prev(SbiPipe* p, float* h_out) {
+  if (p->n == 0) {
+    if (h_out) h_out[0] = h_out[1] = nanf("");
+    return 0;
+  }
+  const int s = (int)((p->n - 1) & 1);
+  CK(cudaEventSynchronize(p->done[s]));
+  if (h_out) { h_out[0] = p->h_loss[s][0]; h_out[1] = p->h_loss[s][1]; }
+  return 0;
+}
+
+extern "C" int sbi_b200_nsf_train_step_host_async(const sbi_nsf_model* m, const sbi_train_ws* ws, void* pipe,
+                                                  const float* h_input, const float* h_cond, int64_t B,
+                                                  float lr, float beta1, float beta2, float eps,
+                                                  float max_norm, float* h_loss_prev, void* stream) {
+  SbiPipe* p = static_cast<SbiPipe*>(pipe);
+  if (!m || !ws || !p || !h_input || !h_cond || B < 1 || B > ws->cap_rows) return SBI_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int slot = (int)(p->n & 1);
+  CK(cudaMemcpyAsync(ws->d_input, h_input, sizeof(float) * B * m->D, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ws->d_cond, h_cond, sizeof(float) * B * m->C, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ws->d_loss_acc, 0, 2 * sizeof(float), s));
+  sbi_rows rows;
+  rows.d_input = ws->d_input;
+  rows.d_cond = ws->d_cond;
+  rows.d_index = nullptr;
+  rows.R = B;
+  rows.cond_shared = 0;
+  int rc = sbi_b200_nsf_vjp(m, &rows, nullptr, -1.0f / (float)B, nullptr, ws->d_gpart, nullptr, nullptr,
+                            ws->d_loss_acc, stream);
+  if (rc) return rc;
+  rc = sbi_b200_reduce_partials(ws->d_gpart, sbi_b200_nsf_vjp_parts(B), m->n_params, ws->d_grad, stream);
+  if (rc) return rc;
+  rc = sbi_b200_adam_clip_step(const_cast<float*>(m->d_params), ws->d_grad, ws->d_state, ws->d_step, ws->d_mask,
+                               m->n_params, lr, beta1, beta2, eps, max_norm, 1.0f, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(p->h_loss[slot], ws->d_loss_acc, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(p->done[slot], s));
+  rc = pipe_wait_prev(p, h_loss_prev);   // step i-1 (the other slot) -- this step keeps running
+  p->n += 1;
+  return rc;
+}
+
+extern "C" int sbi_b200_pipe_drain(void* pipe, float* h_loss_last) {
+  SbiPipe* p = static_cast<SbiPipe*>(pipe);
+  if (!p) return SBI_EINVAL;
+  return pipe_wait_prev(p, h_loss_last);
+}

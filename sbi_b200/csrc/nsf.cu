@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <algorithm>
+#include <cstdlib>
 
 #include "nsf.cuh"
 
@@ -10,8 +11,12 @@ namespace sbi {
 // =================================================================================================
 // log_prob:  persistent over row tiles
 // =================================================================================================
+#ifndef SBI_VJP_SINGLE_COND
+#define SBI_VJP_SINGLE_COND 0
+#endif
+
 template <int TM, int RN>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, (TM > 64 ? 1 : 2))
 nsf_logprob_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ sbi_rows rows,
                    float* __restrict__ logp, float* __restrict__ noise) {
   constexpr int LD = Tile<TM>::LD;
@@ -210,7 +215,7 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int l = 0; l < m.T; ++l) {
           const NsfLayerView v = layer_view(m, l);
-          float* hf = cond_forward<kProducer, TM, RN, false>(m, v, pipe, sm, L);
+          float* hf = cond_forward<kProducer, TM, RN, SBI_VJP_SINGLE_COND != 0>(m, v, pipe, sm, L);
           spline_forward<kProducer, TM, RN, false>(m, v, pipe, sm, L, hf);
         }
         for (int l = m.T - 1; l >= 0; --l) {
@@ -269,7 +274,7 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
         sm[L.ZS + l * m.Dp * LD + e] = Z[e];
       lu_prepare(m, v, sm, L);
       gather_identity<TM>(m, v, Z, U);
-      float* hf = cond_forward<kConsumer, TM, RN, false>(m, v, pipe, sm, L);
+      float* hf = cond_forward<kConsumer, TM, RN, SBI_VJP_SINGLE_COND != 0>(m, v, pipe, sm, L);
       spline_forward<kConsumer, TM, RN, false>(m, v, pipe, sm, L, hf);
       fold_ldf<TM>(v, sm, L);
       for (int e = threadIdx.x; e < m.Dp * LD; e += kConsumerThreads)
@@ -525,7 +530,18 @@ extern "C" int sbi_b200_nsf_logprob(const sbi_nsf_model* m, const sbi_rows* rows
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_logp) return SBI_EINVAL;
   if (rows->R == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (use_big_tile(rows->R)) {
+  static const int tm_env = getenv("SBI_B200_LOGPROB_TM") ? atoi(getenv("SBI_B200_LOGPROB_TM")) : 0;
+  if (tm_env == 128 && use_big_tile(rows->R)) {
+    constexpr int TM = 128;
+    const NsfSmem L = nsf_smem_layout(*m, TM, false);
+    auto k = nsf_logprob_kernel<TM, 4>;
+    if ((rc = set_smem<5>(k, L.total_bytes))) return rc;
+    const int64_t ntiles = (rows->R + TM - 1) / TM;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms());
+    k<<<grid, kThreads, L.total_bytes, s>>>(*m, *rows, d_logp, d_noise);
+    return (int)cudaGetLastError();
+  }
+  if (use_big_tile(rows->R) && tm_env != 32) {
     constexpr int TM = 64;
     const NsfSmem L = nsf_smem_layout(*m, TM, false);
     auto k = nsf_logprob_kernel<TM, 4>;

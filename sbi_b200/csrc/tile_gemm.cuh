@@ -15,6 +15,12 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef SBI_FWD_UNROLL
+#define SBI_FWD_UNROLL 2
+#endif
+#define SBI_PRAGMA(x) _Pragma(#x)
+#define SBI_UNROLL(n) SBI_PRAGMA(unroll n)
+
 namespace sbi {
 
 __device__ __forceinline__ float4 ld4(const float* p) {
@@ -40,7 +46,7 @@ __device__ __forceinline__ void gemm_fwd_acc(float (&acc)[RN][4], const float* _
   const float* xp = X + 4 * rg;
   const float* wp = W + (size_t)g * Kp;
   const int wstep = ng * Kp;
-#pragma unroll 2
+  SBI_UNROLL(SBI_FWD_UNROLL)
   for (int k4 = 0; k4 < K4; ++k4) {
     const float4 x0 = ld4(xp + (4 * k4 + 0) * LD);
     const float4 x1 = ld4(xp + (4 * k4 + 1) * LD);

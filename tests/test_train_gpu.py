@@ -133,6 +133,54 @@ def test_train_step_host_entry(cuda_lib):
     assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5)
 
 
+def test_pipelined_host_steps_equal_blocking_steps(cuda_lib):
+    """sbi_b200_nsf_train_step_host_async (result one step late) == the blocking host step."""
+    from sbi_b200 import _lib as L
+    flow, theta, x = oracle_nsf(6, 4, n=2000)
+    B, nsteps = 256, 5
+    finals, losses = [], []
+    for mode in ("blocking", "pipelined"):
+        est = b200_from_oracle(flow, theta, x)
+        P = est.layout.n_params
+        grad = torch.zeros(P, device="cuda"); state = torch.zeros(2 * P, device="cuda")
+        step = torch.zeros(2, dtype=torch.int32, device="cuda"); loss_acc = torch.zeros(2, device="cuda")
+        gpart = est._gpart(cuda_lib.sbi_b200_nsf_vjp_parts(B))
+        ws = L.TrainWs()
+        st_in = torch.empty(B, 6, device="cuda"); st_c = torch.empty(B, 4, device="cuda"); st_lp = torch.empty(B, device="cuda")
+        ws.d_input, ws.d_cond, ws.d_logp = st_in.data_ptr(), st_c.data_ptr(), st_lp.data_ptr()
+        ws.d_gpart, ws.d_grad, ws.d_state = gpart.data_ptr(), grad.data_ptr(), state.data_ptr()
+        ws.d_step, ws.d_mask, ws.d_loss_acc = step.data_ptr(), est.net._mask.data_ptr(), loss_acc.data_ptr()
+        ws.cap_rows = B
+        bufs = [(torch.empty(B, 6).pin_memory(), torch.empty(B, 4).pin_memory()) for _ in range(2)]
+        out = torch.zeros(2).pin_memory()
+        pipe = cuda_lib.sbi_b200_pipe_create()
+        ls = []
+        for i in range(nsteps):
+            a, b = bufs[i & 1]
+            a.copy_(theta[i * B:(i + 1) * B]); b.copy_(x[i * B:(i + 1) * B])
+            m = est._model(nbuf=3)
+            if mode == "blocking":
+                L.check(cuda_lib.sbi_b200_nsf_train_step_host(C.byref(m), C.byref(ws), a.data_ptr(), b.data_ptr(), B,
+                                                              5e-4, 0.9, 0.999, 1e-8, 5.0, out.data_ptr(), L.stream_ptr()), "s")
+                ls.append(out[0].item())
+            else:
+                L.check(cuda_lib.sbi_b200_nsf_train_step_host_async(C.byref(m), C.byref(ws), pipe, a.data_ptr(), b.data_ptr(),
+                                                                    B, 5e-4, 0.9, 0.999, 1e-8, 5.0, out.data_ptr(),
+                                                                    L.stream_ptr()), "a")
+                if i > 0:
+                    ls.append(out[0].item())
+                else:
+                    assert math.isnan(out[0].item())
+        if mode == "pipelined":
+            L.check(cuda_lib.sbi_b200_pipe_drain(pipe, out.data_ptr()), "drain")
+            ls.append(out[0].item())
+        cuda_lib.sbi_b200_pipe_destroy(pipe)
+        finals.append(est.flat.detach().cpu().clone())
+        losses.append(ls)
+    assert torch.equal(finals[0], finals[1])
+    assert losses[0] == pytest.approx(losses[1], rel=1e-5)
+
+
 def test_npe_fit_linear_gaussian(cuda_lib):
     """NPE + nsf on the linear-Gaussian task recovers the analytic posterior
     (reference acceptance test: tests/linearGaussian_snpe_test.py:53-152, c2st/KL checks)."""
