@@ -219,6 +219,7 @@ def run_b200(args):
     state = torch.zeros(2 * P, device=dev)
     step_ctr = torch.zeros(2, dtype=torch.int32, device=dev)
     loss_acc = torch.zeros(2, device=dev)
+    sumsq = torch.zeros(lib.sbi_b200_sumsq_blocks(P), device=dev)
     mask = est.net._mask
     idx_pool = torch.stack([torch.randperm(n_train, device=dev)[:B] for _ in range(16)])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -230,12 +231,18 @@ def run_b200(args):
         rows = L.Rows(theta_d.data_ptr(), x_d.data_ptr(), idx.data_ptr(), B, 0)
         L.check(lib.sbi_b200_nsf_vjp(C.byref(m), C.byref(rows), None, -1.0 / B, None, L.ptr(gpart),
                                      None, None, L.ptr(loss_acc), L.stream_ptr()), "vjp")
-        L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad), L.stream_ptr()), "reduce")
         if world > 1:
+            L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad), L.stream_ptr()), "reduce")
             dist.all_reduce(grad)
-        L.check(lib.sbi_b200_adam_clip_step(L.ptr(est.flat.data), L.ptr(grad), L.ptr(state),
-                                            L.ptr(step_ctr), L.ptr(mask), P, 5e-4, 0.9, 0.999, 1e-8,
-                                            5.0, 1.0 / world, L.stream_ptr()), "adam")
+            L.check(lib.sbi_b200_adam_clip_step(L.ptr(est.flat.data), L.ptr(grad), L.ptr(state),
+                                                L.ptr(step_ctr), L.ptr(mask), P, 5e-4, 0.9, 0.999, 1e-8,
+                                                5.0, 1.0 / world, L.stream_ptr()), "adam")
+        else:
+            L.check(lib.sbi_b200_reduce_partials_norm(L.ptr(gpart), n_part, P, L.ptr(grad), L.ptr(mask),
+                                                      L.ptr(sumsq), L.stream_ptr()), "reduce")
+            L.check(lib.sbi_b200_adam_clip_step_norm(L.ptr(est.flat.data), L.ptr(grad), L.ptr(state),
+                                                     L.ptr(step_ctr), L.ptr(mask), P, 5e-4, 0.9, 0.999, 1e-8,
+                                                     5.0, 1.0, L.ptr(sumsq), sumsq.shape[0], L.stream_ptr()), "adam")
         launches["n"] += 3
 
     def barrier():
@@ -332,6 +339,7 @@ def run_b200(args):
     ws.d_gpart, ws.d_grad, ws.d_state = gpart.data_ptr(), grad.data_ptr(), state.data_ptr()
     ws.d_step, ws.d_mask, ws.d_loss_acc = step_ctr.data_ptr(), mask.data_ptr(), loss_acc.data_ptr()
     ws.cap_rows = st_in.shape[0]
+    ws.d_sumsq = sumsq.data_ptr()
     h_th = torch.empty(B, DIM).pin_memory()
     h_x = torch.empty(B, DIM).pin_memory()
     h_th2 = [torch.empty(B, DIM).pin_memory() for _ in range(2)]

@@ -106,6 +106,13 @@ int sbi_b200_nsf_inverse(const sbi_nsf_model* m, const sbi_rows* rows, float* d_
 int sbi_b200_reduce_partials(const float* d_gpart, int n_part, int64_t n_params, float* d_grad,
                              void* stream);
 
+/* Same, additionally emitting one partial of sum(grad^2) per reduction block (d_sumsq_part,
+ * sbi_b200_sumsq_blocks(n_params) floats; masked-out entries excluded) so that the clip norm needs
+ * no second pass over the gradient (single-GPU path; after an all-reduce the norm must be retaken). */
+int sbi_b200_sumsq_blocks(int64_t n_params);
+int sbi_b200_reduce_partials_norm(const float* d_gpart, int n_part, int64_t n_params, float* d_grad,
+                                  const uint8_t* d_mask, float* d_sumsq_part, void* stream);
+
 /* clip_grad_norm_(max_norm) + Adam (torch defaults, no weight decay), in place.
  *   d_state: [m (n) | v (n)] ; d_step: int32 device counter (incremented here);
  *   grad_scale multiplies the gradient first (e.g. 1/world_size after an all-reduce);
@@ -115,6 +122,13 @@ int sbi_b200_adam_clip_step(float* d_params, const float* d_grad, float* d_state
                             int32_t* d_step, const uint8_t* d_mask, int64_t n, float lr,
                             float beta1, float beta2, float eps, float max_norm,
                             float grad_scale, void* stream);
+/* as above, taking the gradient's sum of squares from d_sumsq_part (n_sumsq partials) instead of
+ * recomputing it */
+int sbi_b200_adam_clip_step_norm(float* d_params, const float* d_grad, float* d_state,
+                                 int32_t* d_step, const uint8_t* d_mask, int64_t n, float lr,
+                                 float beta1, float beta2, float eps, float max_norm,
+                                 float grad_scale, const float* d_sumsq_part, int n_sumsq,
+                                 void* stream);
 
 /* ---- masked autoregressive flow (sbi `posterior_nn("maf")`, reference builder
  * sbi/neural_nets/net_builders/flow.py:115-209: T x [MaskedAffineAutoregressiveTransform(MADE,
@@ -271,6 +285,7 @@ typedef struct {
   const uint8_t* d_mask; /* (n_params) or NULL */
   float* d_loss_acc;     /* (2) */
   int64_t cap_rows;
+  float* d_sumsq;        /* (sbi_b200_sumsq_blocks(n_params)) scratch for the clip norm, or NULL */
 } sbi_train_ws;
 
 /* One optimisation step on a host batch (replaces one iteration of

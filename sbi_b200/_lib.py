@@ -109,7 +109,7 @@ class TrainWs(C.Structure):
         ("d_input", C.c_void_p), ("d_cond", C.c_void_p), ("d_logp", C.c_void_p),
         ("d_gpart", C.c_void_p), ("d_grad", C.c_void_p), ("d_state", C.c_void_p),
         ("d_step", C.c_void_p), ("d_mask", C.c_void_p), ("d_loss_acc", C.c_void_p),
-        ("cap_rows", C.c_int64),
+        ("cap_rows", C.c_int64), ("d_sumsq", C.c_void_p),
     ]
 
 
@@ -145,6 +145,13 @@ _EXPORTS = {
     "sbi_b200_slice_step": (C.c_int, [C.POINTER(SliceChains), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_reduce_partials": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                            C.c_void_p]),
+    "sbi_b200_sumsq_blocks": (C.c_int, [C.c_int64]),
+    "sbi_b200_reduce_partials_norm": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
+    "sbi_b200_adam_clip_step_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                               C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int,
+                                               C.c_void_p]),
     "sbi_b200_adam_clip_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                           C.c_float, C.c_float, C.c_float, C.c_void_p]),

@@ -9,6 +9,24 @@
     if (e_ != cudaSuccess) return (int)e_; \
   } while (0)
 
+// partial-gradient reduction (+ per-block sum of squares when the workspace has room) -> clip + Adam
+static int reduce_and_step(const sbi_nsf_model* m, const sbi_train_ws* ws, int64_t B, float lr, float beta1,
+                           float beta2, float eps, float max_norm, void* stream) {
+  const int n_part = sbi_b200_nsf_vjp_parts(B);
+  if (ws->d_sumsq != nullptr) {
+    int rc = sbi_b200_reduce_partials_norm(ws->d_gpart, n_part, m->n_params, ws->d_grad, ws->d_mask,
+                                           ws->d_sumsq, stream);
+    if (rc) return rc;
+    return sbi_b200_adam_clip_step_norm(const_cast<float*>(m->d_params), ws->d_grad, ws->d_state, ws->d_step,
+                                        ws->d_mask, m->n_params, lr, beta1, beta2, eps, max_norm, 1.0f,
+                                        ws->d_sumsq, sbi_b200_sumsq_blocks(m->n_params), stream);
+  }
+  int rc = sbi_b200_reduce_partials(ws->d_gpart, n_part, m->n_params, ws->d_grad, stream);
+  if (rc) return rc;
+  return sbi_b200_adam_clip_step(const_cast<float*>(m->d_params), ws->d_grad, ws->d_state, ws->d_step,
+                                 ws->d_mask, m->n_params, lr, beta1, beta2, eps, max_norm, 1.0f, stream);
+}
+
 extern "C" int sbi_b200_nsf_train_step_host(const sbi_nsf_model* m, const sbi_train_ws* ws,
                                             const float* h_input, const float* h_cond, int64_t B,
                                             float lr, float beta1, float beta2, float eps,
@@ -28,12 +46,7 @@ extern "C" int sbi_b200_nsf_train_step_host(const sbi_nsf_model* m, const sbi_tr
   int rc = sbi_b200_nsf_vjp(m, &rows, nullptr, -1.0f / (float)B, nullptr, ws->d_gpart, nullptr,
                             nullptr, ws->d_loss_acc, stream);
   if (rc) return rc;
-  rc = sbi_b200_reduce_partials(ws->d_gpart, sbi_b200_nsf_vjp_parts(B), m->n_params, ws->d_grad,
-                                stream);
-  if (rc) return rc;
-  rc = sbi_b200_adam_clip_step(const_cast<float*>(m->d_params), ws->d_grad, ws->d_state,
-                               ws->d_step, ws->d_mask, m->n_params, lr, beta1, beta2, eps,
-                               max_norm, 1.0f, stream);
+  rc = reduce_and_step(m, ws, B, lr, beta1, beta2, eps, max_norm, stream);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h_loss_out, ws->d_loss_acc, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -120,10 +133,7 @@ extern "C" int sbi_b200_nsf_train_step_host_async(const sbi_nsf_model* m, const 
   int rc = sbi_b200_nsf_vjp(m, &rows, nullptr, -1.0f / (float)B, nullptr, ws->d_gpart, nullptr, nullptr,
                             ws->d_loss_acc, stream);
   if (rc) return rc;
-  rc = sbi_b200_reduce_partials(ws->d_gpart, sbi_b200_nsf_vjp_parts(B), m->n_params, ws->d_grad, stream);
-  if (rc) return rc;
-  rc = sbi_b200_adam_clip_step(const_cast<float*>(m->d_params), ws->d_grad, ws->d_state, ws->d_step, ws->d_mask,
-                               m->n_params, lr, beta1, beta2, eps, max_norm, 1.0f, stream);
+  rc = reduce_and_step(m, ws, B, lr, beta1, beta2, eps, max_norm, stream);
   if (rc) return rc;
   CK(cudaMemcpyAsync(p->h_loss[slot], ws->d_loss_acc, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(p->done[slot], s));

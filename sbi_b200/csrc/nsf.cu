@@ -11,12 +11,15 @@ namespace sbi {
 // =================================================================================================
 // log_prob:  persistent over row tiles
 // =================================================================================================
+#ifndef SBI_EVAL_MINB32
+#define SBI_EVAL_MINB32 2
+#endif
 #ifndef SBI_VJP_SINGLE_COND
 #define SBI_VJP_SINGLE_COND 0
 #endif
 
 template <int TM, int RN>
-__global__ void __launch_bounds__(kThreads, (TM > 64 ? 1 : 2))
+__global__ void __launch_bounds__(kThreads, (TM > 64 ? 1 : (TM == 32 ? SBI_EVAL_MINB32 : 2)))
 nsf_logprob_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ sbi_rows rows,
                    float* __restrict__ logp, float* __restrict__ noise) {
   constexpr int LD = Tile<TM>::LD;
@@ -556,7 +559,7 @@ extern "C" int sbi_b200_nsf_logprob(const sbi_nsf_model* m, const sbi_rows* rows
     auto k = nsf_logprob_kernel<TM, 2>;
     if ((rc = set_smem<1>(k, L.total_bytes))) return rc;
     const int64_t ntiles = (rows->R + TM - 1) / TM;
-    const int per_sm = (L.total_bytes <= 110 * 1024) ? 2 : 1;
+    const int per_sm = std::max(1, std::min(SBI_EVAL_MINB32, (227 * 1024) / (L.total_bytes + 1024)));
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * per_sm);
     k<<<grid, kThreads, L.total_bytes, s>>>(*m, *rows, d_logp, d_noise);
   }

@@ -169,6 +169,7 @@ class _FlowTrainer:
         perm_buf = torch.empty(steps * B, dtype=torch.int64, device=dev)
         vperm_buf = torch.empty(max(vsteps * Bv, 1), dtype=torch.int64, device=dev)
         grad = torch.zeros(P, dtype=torch.float32, device=dev)
+        sumsq = torch.zeros(lib.sbi_b200_sumsq_blocks(P), dtype=torch.float32, device=dev)
         n_part = net.fam.fn("vjp_parts")(B)
         gpart = net._gpart(n_part)
         loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
@@ -187,14 +188,21 @@ class _FlowTrainer:
                 L.check(net.fam.fn("vjp")(C.byref(m_tr), C.byref(rows), None, -1.0 / (B * world),
                                           None, L.ptr(gpart), None, None, L.ptr(loss_acc),
                                           L.stream_ptr()), "flow_vjp")
-                L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad),
-                                                     L.stream_ptr()), "reduce_partials")
-                if world > 1:
+                if world > 1:   # the clip norm must be taken on the all-reduced gradient
+                    L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad),
+                                                         L.stream_ptr()), "reduce_partials")
                     torch.distributed.all_reduce(grad)
-                L.check(lib.sbi_b200_adam_clip_step(
-                    L.ptr(net.flat.data), L.ptr(grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
-                    L.ptr(mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0,
-                    L.stream_ptr()), "adam_clip_step")
+                    L.check(lib.sbi_b200_adam_clip_step(
+                        L.ptr(net.flat.data), L.ptr(grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
+                        L.ptr(mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0,
+                        L.stream_ptr()), "adam_clip_step")
+                else:           # single GPU: the reduction kernel also emits sum(g^2) partials
+                    L.check(lib.sbi_b200_reduce_partials_norm(L.ptr(gpart), n_part, P, L.ptr(grad), L.ptr(mask),
+                                                              L.ptr(sumsq), L.stream_ptr()), "reduce_partials")
+                    L.check(lib.sbi_b200_adam_clip_step_norm(
+                        L.ptr(net.flat.data), L.ptr(grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
+                        L.ptr(mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.ptr(sumsq),
+                        sumsq.shape[0], L.stream_ptr()), "adam_clip_step")
             stats[0:2].copy_(loss_acc)
             if vsteps > 0:
                 m_ev = net._model(nbuf=2)

@@ -84,7 +84,7 @@ class NsfLayout(_LayoutOps):
     zscore_input: bool = True
     zscore_cond: bool = True
     embed_is_identity: bool = True
-    wcap_target: int = 4096
+    wcap_target: int = int(__import__('os').environ.get('SBI_B200_WCAP', 4096))
 
     # derived
     n_params: int = 0

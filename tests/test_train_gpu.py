@@ -35,6 +35,24 @@ def test_adam_clip_kernel_matches_torch(cuda_lib):
         err = (p.cpu() - ref.detach()).abs().max().item()
         assert err <= 2e-7, (it, err)
     assert int(step[0].item()) == 5
+    # norm taken from the reduction kernel's per-block partials: same update as the self-computed norm
+    gp = torch.randn(3, n, device="cuda") * 4.0
+    outs = []
+    for mode in (0, 1):
+        pp = p0.clone().cuda(); st = torch.zeros(2 * n, device="cuda"); sc = torch.zeros(2, dtype=torch.int32, device="cuda")
+        g = torch.empty(n, device="cuda")
+        if mode == 0:
+            L.check(cuda_lib.sbi_b200_reduce_partials(L.ptr(gp), 3, n, L.ptr(g), L.stream_ptr()), "r")
+            L.check(cuda_lib.sbi_b200_adam_clip_step(L.ptr(pp), L.ptr(g), L.ptr(st), L.ptr(sc), None, n, 5e-4, 0.9, 0.999,
+                                                     1e-8, 5.0, 1.0, L.stream_ptr()), "a")
+        else:
+            ss = torch.zeros(cuda_lib.sbi_b200_sumsq_blocks(n), device="cuda")
+            L.check(cuda_lib.sbi_b200_reduce_partials_norm(L.ptr(gp), 3, n, L.ptr(g), None, L.ptr(ss), L.stream_ptr()), "r")
+            assert abs(ss.sum().item() / (gp.sum(0) ** 2).sum().item() - 1) < 1e-5
+            L.check(cuda_lib.sbi_b200_adam_clip_step_norm(L.ptr(pp), L.ptr(g), L.ptr(st), L.ptr(sc), None, n, 5e-4, 0.9,
+                                                          0.999, 1e-8, 5.0, 1.0, L.ptr(ss), ss.shape[0], L.stream_ptr()), "a")
+        outs.append(pp.cpu())
+    assert (outs[0] - outs[1]).abs().max() <= 1e-7
 
 
 def test_fused_train_step_matches_oracle_step(cuda_lib):
