@@ -306,6 +306,7 @@ def run_b200(args):
     flops = 2.0 * B * 3 * _nsf_macs(lay)                              # fwd + 2x bwd (no recompute counted)
     peaks = _peaks()
     achieved = alg_bytes / (vjp_ms * 1e-3) / 1e9
+    traffic = _traffic()
 
     # ---- log_prob leg (secondary metric) ---------------------------------------------------------
     R = LOGPROB_ROWS
@@ -446,7 +447,9 @@ def run_b200(args):
                        "launch": "cuda-graph per step" if graphs is not None else "eager"},
             "roofline": {"bound": "hbm", "kernel": "nsf_vjp_kernel<32,2,2>", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": None, "peak_source": peaks["source"],
+                         "traffic": traffic.get("nsf_vjp_kernel", {}).get("dram_bytes_per_launch"),
+                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, B=4096)",
+                         "peak_source": peaks["source"],
                          "alg_bytes_per_launch": alg_bytes, "kernel_ms": vjp_ms,
                          "fp32_fma": {"achieved_tflops": flops / (vjp_ms * 1e-3) / 1e12,
                                       "nominal_peak_tflops": 74.5,
@@ -474,6 +477,14 @@ def _nsf_macs(lay):
         tot += (n_id + lay.C) * lay.H + lay.NB * (2 * lay.H * lay.H + lay.C * lay.H)
         tot += lay.H * n_tr * lay.NPAR + lay.D * lay.D
     return tot
+
+
+def _traffic():
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def _peaks():
