@@ -130,6 +130,39 @@ int sbi_b200_adam_clip_step_norm(float* d_params, const float* d_grad, float* d_
                                  float grad_scale, const float* d_sumsq_part, int n_sumsq,
                                  void* stream);
 
+/* ---- tensor-core bulk evaluation of the NSF (tcgen05 kind::tf32, 3xTF32 split, accumulators in
+ * TMEM).  Same function as sbi_b200_nsf_logprob (NFlowsFlow.log_prob,
+ * sbi/neural_nets/estimators/nflows_flow.py:77-97) for large row counts: the ResidualNet linears
+ * (nflows ResidualNet; call site sbi/neural_nets/net_builders/flow.py:411-419) run on the tensor
+ * cores, one row per TMEM lane, everything else (spline, LU, base density) per thread.
+ *
+ * The linears' weights are re-packed from the flat parameter buffer into d_tcw by
+ * sbi_b200_nsf_tc_pack (call it whenever d_params changed): per coupling layer a sequence of
+ * stages [hi | lo], each half a concatenation of K-major no-swizzle UMMA operand blocks
+ * [K/4 slabs][N rows][4 floats] (hi = tf32-rounded weight, lo = weight - hi).
+ *   d_src   (n_words,) gather map built by the host (sbi_b200/pack.py NsfLayout.tc_plan):
+ *           -1 -> 0 ; s >= 0 -> hi(params[s]) ; s <= -2 -> lo(params[-2-s])
+ *   d_tab   T * SBI_NSF_TC_STRIDE ints; per layer: [0] number of stages, [1] round8(n_id),
+ *           then 4 ints per stage s at 4+4s: float offset into d_tcw, floats (hi+lo), N of the
+ *           main block, aux (final-layer passes: first feature | n_features << 16).
+ *           Stage order: initial layer, per block ([W1 | Wc], W2), final-layer passes.
+ * Supported when H == 50, H + C <= 64, n_id <= 48, 3*KB-1 <= 32 and the shared-memory plan fits
+ * (sbi_b200_nsf_tc_supported); callers use sbi_b200_nsf_logprob otherwise. */
+#define SBI_NSF_TC_STRIDE 192
+#define SBI_NSF_TC_MAX_STAGES 46
+typedef struct {
+  int32_t n_words;                 /* floats in d_tcw / entries in d_src */
+  int32_t stage_cap;               /* floats of the largest stage (hi + lo) */
+  const int32_t* d_src;
+  const int32_t* d_tab;
+  float* d_tcw;
+} sbi_nsf_tc;
+
+int sbi_b200_nsf_tc_supported(const sbi_nsf_model* m, const sbi_nsf_tc* tc);
+int sbi_b200_nsf_tc_pack(const sbi_nsf_model* m, const sbi_nsf_tc* tc, void* stream);
+int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc, const sbi_rows* rows,
+                            float* d_logp, float* d_noise, void* stream);
+
 /* ---- masked autoregressive flow (sbi `posterior_nn("maf")`, reference builder
  * sbi/neural_nets/net_builders/flow.py:115-209: T x [MaskedAffineAutoregressiveTransform(MADE,
  * feed-forward blocks, tanh) + RandomPermutation], z-scored input, standardised context).

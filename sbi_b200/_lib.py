@@ -37,6 +37,17 @@ class NsfModel(C.Structure):
     ]
 
 
+SBI_NSF_TC_STRIDE = 192
+SBI_NSF_TC_MAX_STAGES = 46
+
+
+class NsfTc(C.Structure):
+    _fields_ = [
+        ("n_words", C.c_int32), ("stage_cap", C.c_int32),
+        ("d_src", C.c_void_p), ("d_tab", C.c_void_p), ("d_tcw", C.c_void_p),
+    ]
+
+
 class MafModel(C.Structure):
     _fields_ = [
         ("D", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("NB", C.c_int32), ("T", C.c_int32),
@@ -124,6 +135,10 @@ _EXPORTS = {
                                    C.c_void_p]),
     "sbi_b200_nsf_inverse": (C.c_int, [C.POINTER(NsfModel), C.POINTER(Rows), C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
+    "sbi_b200_nsf_tc_supported": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc)]),
+    "sbi_b200_nsf_tc_pack": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc), C.c_void_p]),
+    "sbi_b200_nsf_logprob_tc": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc), C.POINTER(Rows),
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_maf_logprob": (C.c_int, [C.POINTER(MafModel), C.POINTER(Rows), C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "sbi_b200_maf_vjp_parts": (C.c_int, [C.c_int64]),

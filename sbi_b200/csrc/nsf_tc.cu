@@ -1,0 +1,642 @@
+// Tensor-core bulk evaluation of the neural spline flow: NFlowsFlow.log_prob
+// (/root/reference/sbi/neural_nets/estimators/nflows_flow.py:77-97) for large row counts.
+//
+// Same function, same parameter buffer and same evaluation order outside the linears as
+// nsf_logprob_kernel (nsf.cu); the ResidualNet linears (nflows ResidualNet, restated in
+// oracle/nflows_port/nn/nets/resnet.py; built at flow.py:411-419) run on the 5th-generation
+// tensor cores:
+//
+//   * one CTA = 4 row warps (128 rows, one row per thread = one row per TMEM lane) + 1 TMA warp,
+//     two CTAs per SM (256 TMEM columns each);
+//   * tcgen05.mma kind::tf32, M = 128, issued by one thread; A (activations) is read from TMEM,
+//     where the row threads put it with tcgen05.st after splitting every fp32 value into
+//     hi = tf32(x) and lo = x - hi; B (weights, pre-split hi/lo and pre-arranged in the K-major
+//     no-swizzle UMMA layout by nsf_tc_pack_kernel) is streamed by TMA bulk copies into a
+//     shared-memory ring; D = A_hi B_hi + A_lo B_hi + A_hi B_lo (3xTF32) accumulates in TMEM in
+//     fp32 and comes back with tcgen05.ld for the bias / relu / GLU / spline epilogues;
+//   * the context is a K-extension of the hidden operand: A columns are
+//     [ hidden (H) | context (C) | 0 ], so the GLU gate W_c ctx is one more small MMA on the
+//     same operand and the context never has to be re-staged;
+//   * spline, LU and base density are per-thread code on the thread's own row (no barriers),
+//     using the very same rqs.cuh routines as the SIMT kernels.
+//
+// TMEM columns of a CTA:  [0,64) A_hi | [64,128) A_lo | [128,192) D | [192,256) G (GLU gate);
+// the final layer's spline parameters P (32 columns per feature, <= 3 features per pass)
+// reuse [128,256).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <algorithm>
+#include <cstdlib>
+
+#include "nsf.cuh"
+
+namespace sbi {
+namespace tc {
+
+constexpr int kRows = 128;        // rows per tile
+constexpr int kRowThreads = 128;
+constexpr int kThreads = 160;     // 4 row warps + 1 TMA producer warp
+constexpr int kCols = 256;        // TMEM columns per CTA
+constexpr int cAhi = 0, cAlo = 64, cD = 128, cG = 192;
+constexpr int kMaxPassFeat = 3;   // spline features per final-layer pass (N = 96)
+
+// ---- tcgen05 wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ void fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T : one K = 8 step of kind::tf32
+__device__ __forceinline__ void mma_tf32(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d),
+      "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): fp32 accumulate @4,
+// A/B format tf32 @7/@10, both K-major, N>>3 @17, M>>4 @24
+__device__ __forceinline__ uint32_t make_idesc(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// shared-memory operand descriptor, SWIZZLE_NONE, K-major: core matrix = 8 rows x 16 B contiguous;
+// LBO = byte distance of K-adjacent core matrices, SBO = byte distance of 8-row groups
+// (field positions: cute/arch/mma_sm100_desc.hpp SmemDescriptor; the assignment was pinned on
+// hardware with profiles/micro/umma_probe.cu)
+__device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+      "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+      : "memory");
+}
+// 8 consecutive columns of the thread's lane -> v[0..8)   (no wait inside)
+__device__ __forceinline__ void ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int NCHUNK>
+__device__ __forceinline__ void ld_cols(uint32_t taddr, float* v) {
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) ld8(taddr + 8 * c, v + 8 * c);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = x - hi;
+}
+// split 8 values and put them into A_hi / A_lo columns [col, col+8) of the thread's lane
+__device__ __forceinline__ void store_a8(uint32_t tlane, int col, const float (&v)[8]) {
+  float hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_tf32(v[i], hi[i], lo[i]);
+  st8(tlane + cAhi + col, hi);
+  st8(tlane + cAlo + col, lo);
+}
+__device__ __forceinline__ void group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ---- shared memory plan -------------------------------------------------------------------------
+struct TcSmem {
+  int zs, ctx, lum, lu_stride, ring;   // float offsets
+  int bar_bytes, total_bytes;
+};
+__host__ __device__ inline TcSmem tc_smem_layout(const sbi_nsf_model& m, int stage_cap, int nslot) {
+  TcSmem L;
+  int fl = 0;
+  L.zs = fl;  fl += m.Dp * kRows;
+  L.ctx = fl; fl += m.Cp * kRows;
+  L.lu_stride = round4(2 * m.D * m.D + 2 * m.D);
+  L.lum = fl; fl += m.T * L.lu_stride;
+  fl = (fl + 31) & ~31;
+  L.ring = fl; fl += nslot * stage_cap;
+  L.bar_bytes = fl * 4;
+  L.total_bytes = L.bar_bytes + (2 * nslot + 1) * 8 + 16;
+  return L;
+}
+
+// ---- weight re-pack: flat fp32 parameters -> [hi | lo] UMMA operand blocks ---------------------
+__global__ void nsf_tc_pack_kernel(const float* __restrict__ params, const int32_t* __restrict__ src,
+                                   float* __restrict__ tcw, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = __ldg(src + i);
+  float v = 0.f;
+  if (s >= 0) {
+    float hi, lo;
+    split_tf32(__ldg(params + s), hi, lo);
+    v = hi;
+  } else if (s <= -2) {
+    float hi, lo;
+    split_tf32(__ldg(params + (-2 - s)), hi, lo);
+    v = lo;
+  }
+  tcw[i] = v;
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------
+struct Issuer {
+  uint32_t tbase;       // TMEM base (lane 0, column 0)
+  float* ring;
+  uint64_t *full, *empty, *dbar;
+  int cap, nslot;
+  uint32_t it;          // stage counter
+  uint32_t sbase, lo_off;   // current stage: shared address of the hi half, byte offset of lo half
+
+  __device__ __forceinline__ void begin(int stage_floats) {
+    const int s = it % nslot;
+    mbar_wait(&full[s], (it / nslot) & 1u);
+    sbase = smem_u32(ring + (size_t)s * cap);
+    lo_off = (uint32_t)stage_floats * 2u;     // (floats / 2) * 4 bytes
+    fence_after();
+  }
+  // one operand block of N rows starting `blk_floats` into the half: nk K-steps, A columns from a0
+  __device__ __forceinline__ void block(int dcol, int a0, int nk, int blk_floats, int N, uint32_t& acc) {
+    const uint32_t idesc = make_idesc(N);
+    const uint32_t slab = (uint32_t)N * 16u;
+    const uint32_t bh = sbase + (uint32_t)blk_floats * 4u;
+    for (int kk = 0; kk < nk; ++kk) {
+      const uint64_t dh = make_bdesc(bh + 2u * kk * slab, slab, 128u);
+      const uint64_t dl = make_bdesc(bh + lo_off + 2u * kk * slab, slab, 128u);
+      const uint32_t ah = tbase + cAhi + a0 + 8 * kk, al = tbase + cAlo + a0 + 8 * kk;
+      mma_tf32(tbase + dcol, ah, dh, idesc, acc);
+      mma_tf32(tbase + dcol, al, dh, idesc, 1u);
+      mma_tf32(tbase + dcol, ah, dl, idesc, 1u);
+      acc = 1u;
+    }
+  }
+  __device__ __forceinline__ void end() {
+    commit(&empty[it % nslot]);   // weight slot free once these MMAs have read it
+    commit(dbar);                 // accumulators ready
+  }
+};
+
+// h += (W2 a + b2) * sigmoid(Wc ctx + bc) for hidden chunks [C_LO, C_HI)
+template <int H, int HP8, int C_LO, int C_HI>
+__device__ __forceinline__ void glu_update(uint32_t tlane, const float* __restrict__ b2,
+                                           const float* __restrict__ bc, float (&h)[HP8]) {
+  constexpr int NC = C_HI - C_LO;
+  float d[8 * NC], g[8 * NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    ld8(tlane + cD + 8 * (C_LO + c), d + 8 * c);
+    ld8(tlane + cG + 8 * (C_LO + c), g + 8 * c);
+  }
+  wait_ld();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int j = 8 * (C_LO + c) + i;
+      if (j < H) {
+        const float t = d[8 * c + i] + __ldg(b2 + j);
+        const float s = sigmoid_f(g[8 * c + i] + __ldg(bc + j));
+        h[j] = h[j] + t * s;
+      }
+    }
+  }
+}
+
+template <int H, int KB>
+__global__ void __launch_bounds__(kThreads, 2)
+nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ sbi_nsf_tc tc,
+                      const __grid_constant__ sbi_rows rows, float* __restrict__ logp,
+                      float* __restrict__ noise, int nslot) {
+  constexpr int HP8 = (H + 7) & ~7;
+  constexpr int NCH = HP8 / 8;      // K-steps / 8-column chunks of the hidden operand
+  constexpr int KC0 = H / 8;        // first chunk that holds context columns
+  extern __shared__ __align__(128) float sm[];
+  const TcSmem L = tc_smem_layout(m, tc.stage_cap, nslot);
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(sm) + L.bar_bytes);
+  uint64_t* empty = full + nslot;
+  uint64_t* dbar = empty + nslot;
+  uint32_t* tbase_s = reinterpret_cast<uint32_t*>(dbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int C = m.C;
+  const int nkc = (H + C + 7) / 8 - KC0;     // K-steps that cover the context columns
+  const int64_t ntiles = (rows.R + kRows - 1) / kRows;
+
+  if (tid == 0) {
+    for (int s = 0; s < nslot; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(dbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tbase_s)),
+                 "r"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tbase = *tbase_s;
+
+  // ---------------- TMA producer warp: streams the stages in consumption order ----------------
+  if (warp == 4) {
+    if (tid == kRowThreads) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int l = 0; l < m.T; ++l) {
+          const int32_t* tab = tc.d_tab + l * SBI_NSF_TC_STRIDE;
+          const int ns = __ldg(tab);
+          for (int s = 0; s < ns; ++s) {
+            const int off = __ldg(tab + 4 + 4 * s), nfl = __ldg(tab + 5 + 4 * s);
+            const int slot = it % nslot;
+            mbar_wait_backoff(&empty[slot], ((it / nslot) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&full[slot], (uint32_t)nfl * 4u);
+            bulk_g2s(sm + L.ring + (size_t)slot * tc.stage_cap, tc.d_tcw + off, (uint32_t)nfl * 4u,
+                     &full[slot]);
+            ++it;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- row warps ------------------------------------------------------------------
+  const float* __restrict__ P = m.d_params;
+  float* zs = sm + L.zs;
+  float* ctx_s = sm + L.ctx;
+  const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);
+  RqsConst rc = rqs_const(m);
+  rc.K = KB;   // compile-time bin count keeps the spline parameters in registers
+  const int D = m.D;
+
+  // dense LU factors of every layer, once per CTA: [U D*D | L D*D | bias D | diag D]
+  for (int l = 0; l < m.T; ++l) {
+    const int* LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
+    if (!__ldg(LT + SBI_L_HAS_LU)) continue;
+    const float* lo = P + __ldg(LT + SBI_L_LU_LOWER);
+    const float* up = P + __ldg(LT + SBI_L_LU_UPPER);
+    const float* dg = P + __ldg(LT + SBI_L_LU_DIAG);
+    const float* bi = P + __ldg(LT + SBI_L_LU_BIAS);
+    float* U = sm + L.lum + l * L.lu_stride;
+    float* Lw = U + D * D;
+    for (int t = tid; t < D * D; t += kRowThreads) {
+      const int i = t / D, j = t % D;
+      float u = 0.f, lv = 0.f;
+      if (j > i) u = __ldg(up + i * D - i * (i + 1) / 2 + (j - i - 1));
+      else if (j < i) lv = __ldg(lo + i * (i - 1) / 2 + j);
+      else u = softplus_f(__ldg(dg + i)) + 1e-3f;
+      U[t] = u;
+      Lw[t] = lv;
+      if (j == i) {
+        Lw[D * D + i] = __ldg(bi + i);
+        Lw[D * D + D + i] = u;
+      }
+    }
+  }
+  // batch-constant part of the log-density, summed in the order of lu_logdet_total (nsf.cuh)
+  float ld_const;
+  {
+    float tot = 0.f;
+    for (int l = 0; l < m.T; ++l) {
+      const int* LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
+      float sacc = 0.f;
+      if (__ldg(LT + SBI_L_HAS_LU))
+        for (int i = 0; i < D; ++i)
+          sacc += logf(softplus_f(__ldg(P + __ldg(LT + SBI_L_LU_DIAG) + i)) + 1e-3f);
+      tot += sacc;
+    }
+    ld_const = tot + m.ld_zscore - 0.5f * (float)D * 1.8378770664093453f;
+  }
+
+  Issuer iss;
+  iss.tbase = tbase; iss.ring = sm + L.ring; iss.full = full; iss.empty = empty; iss.dbar = dbar;
+  iss.cap = tc.stage_cap; iss.nslot = nslot; iss.it = 0; iss.sbase = 0; iss.lo_off = 0;
+  uint32_t dpar = 0;
+
+  // hand the operands over to the tensor core, run one stage, wait for its accumulators
+#define SBI_TC_ROUND(STAGE_FLOATS, ISSUE_BODY)  \
+  do {                                          \
+    wait_st();                                  \
+    fence_before();                             \
+    group_sync();                               \
+    if (tid == 0) {                             \
+      iss.begin(STAGE_FLOATS);                  \
+      ISSUE_BODY;                               \
+      iss.end();                                \
+    }                                           \
+    ++iss.it;                                   \
+    mbar_wait(dbar, dpar);                      \
+    dpar ^= 1u;                                 \
+    __syncwarp();                               \
+    fence_after();                              \
+  } while (0)
+
+  // A-operand column j of a hidden layer: activation (j < H), context (H <= j < H+C), zero
+#define SBI_TC_ACOL(j, ACT) ((j) < H ? (ACT) : (((j) - H) < C ? ctx_s[((j) - H) * kRows + tid] : 0.f))
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kRows;
+    // ---- load + standardise the tile's rows (arithmetic of load_rows, stages.cuh) ----
+    {
+      const float* st = m.d_stats;
+      const int Dp = m.Dp, Cp = m.Cp;
+      for (int e = tid; e < kRows * Dp; e += kRowThreads) {
+        const int r = e / Dp, d = e % Dp;
+        const int64_t gr = row0 + r;
+        float val = 0.f;
+        if (d < D && gr < rows.R) {
+          const int64_t src = rows.d_index ? __ldg(rows.d_index + gr) : gr;
+          const float x = __ldg(rows.d_input + src * D + d);
+          val = __fadd_rn(__fmul_rn(x, __ldg(st + Dp + d)), __ldg(st + d));
+        }
+        zs[d * kRows + r] = val;
+      }
+      for (int e = tid; e < kRows * Cp; e += kRowThreads) {
+        const int r = e / Cp, c = e % Cp;
+        const int64_t gr = row0 + r;
+        float val = 0.f;
+        if (c < C && gr < rows.R) {
+          const int64_t src = rows.cond_shared ? 0 : (rows.d_index ? __ldg(rows.d_index + gr) : gr);
+          val = (__ldg(rows.d_cond + src * C + c) - __ldg(st + 2 * Dp + c)) / __ldg(st + 2 * Dp + Cp + c);
+        }
+        ctx_s[c * kRows + r] = val;
+      }
+      group_sync();
+    }
+    // context tail columns [HP8, 64) never change within a tile
+#pragma unroll
+    for (int c = NCH; c < 8; ++c) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = SBI_TC_ACOL(8 * c + i, 0.f);
+      store_a8(tlane, 8 * c, v);
+    }
+    float ldacc = 0.f;
+
+    for (int l = 0; l < m.T; ++l) {
+      const NsfLayerView v = layer_view(m, l);
+      const int32_t* tab = tc.d_tab + l * SBI_NSF_TC_STRIDE;
+      const int kid8 = __ldg(tab + 1);
+      int stage = 0;
+      float h[HP8];
+
+      // ---- initial layer: A = [identity features | 0 ... | context] ----
+      for (int kk = 0; kk < kid8 / 8; ++kk) {
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = 8 * kk + i;
+          a[i] = (j < v.n_id) ? zs[__ldg(v.idf + j) * kRows + tid] : 0.f;
+        }
+        store_a8(tlane, 8 * kk, a);
+      }
+#pragma unroll
+      for (int c = KC0; c < NCH; ++c) {
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = SBI_TC_ACOL(8 * c + i, 0.f);
+        store_a8(tlane, 8 * c, a);
+      }
+      {
+        const int nfl = __ldg(tab + 5 + 4 * stage);
+        SBI_TC_ROUND(nfl, {
+          uint32_t acc = 0u;
+          iss.block(cD, 0, kid8 / 8, 0, 64, acc);
+          iss.block(cD, 8 * KC0, nkc, 64 * kid8, 64, acc);
+        });
+        ++stage;
+      }
+      {
+        float d[HP8];
+        ld_cols<NCH>(tlane + cD, d);
+        wait_ld();
+        const float* b0 = P + __ldg(v.LT + SBI_L_B0);
+#pragma unroll
+        for (int j = 0; j < HP8; ++j) h[j] = (j < H) ? d[j] + __ldg(b0 + j) : 0.f;
+      }
+
+      // ---- residual blocks ----
+      for (int b = 0; b < m.NB; ++b) {
+        const int* BT = v.LT + SBI_L_BLK0 + 6 * b;
+        // A = [relu(h) | ctx]
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float a[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = SBI_TC_ACOL(8 * c + i, relu_f(h[8 * c + i]));
+          store_a8(tlane, 8 * c, a);
+        }
+        {
+          const int nfl = __ldg(tab + 5 + 4 * stage);
+          SBI_TC_ROUND(nfl, {
+            uint32_t acc = 0u;
+            uint32_t accg = 0u;
+            iss.block(cD, 0, NCH, 0, 64, acc);
+            iss.block(cG, 8 * KC0, nkc, 64 * HP8, 64, accg);
+          });
+          ++stage;
+        }
+        {
+          float d[HP8];
+          ld_cols<NCH>(tlane + cD, d);
+          wait_ld();
+          const float* b1 = P + __ldg(BT + 1);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              a[i] = SBI_TC_ACOL(8 * c + i, relu_f(d[8 * c + i] + __ldg(b1 + (8 * c + i < H ? 8 * c + i : 0))));
+            store_a8(tlane, 8 * c, a);
+          }
+        }
+        {
+          const int nfl = __ldg(tab + 5 + 4 * stage);
+          SBI_TC_ROUND(nfl, {
+            uint32_t acc = 0u;
+            iss.block(cD, 0, NCH, 0, 64, acc);
+          });
+          ++stage;
+        }
+        {
+          const float* b2 = P + __ldg(BT + 3);
+          const float* bc = P + __ldg(BT + 5);
+          // two halves to bound registers
+          glu_update<H, HP8, 0, (NCH + 1) / 2>(tlane, b2, bc, h);
+          glu_update<H, HP8, (NCH + 1) / 2, NCH>(tlane, b2, bc, h);
+        }
+      }
+
+      // ---- final layer passes + spline on the transformed features ----
+      {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float a[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = SBI_TC_ACOL(8 * c + i, h[8 * c + i]);
+          store_a8(tlane, 8 * c, a);
+        }
+        const float* bf = P + __ldg(v.LT + SBI_L_BF);
+        const int ns = __ldg(tab);
+        for (; stage < ns; ++stage) {
+          const int nfl = __ldg(tab + 5 + 4 * stage);
+          const int N = __ldg(tab + 6 + 4 * stage);
+          const int aux = __ldg(tab + 7 + 4 * stage);
+          const int f0 = aux & 0xffff, nf = aux >> 16;
+          SBI_TC_ROUND(nfl, {
+            uint32_t acc = 0u;
+            iss.block(cD, 0, NCH, 0, N, acc);
+          });
+          for (int f = 0; f < nf; ++f) {
+            float p[32];
+            ld_cols<4>(tlane + cD + 32 * f, p);
+            wait_ld();
+            const float* bff = bf + (f0 + f) * m.PR;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) p[i] = (i < 3 * KB - 1) ? p[i] + __ldg(bff + i) : 0.f;
+            const int j = __ldg(v.trf + f0 + f);
+            const float x = zs[j * kRows + tid];
+            float y, ld;
+            rqs_forward<true>(p, 1, rc, x, y, ld);
+            zs[j * kRows + tid] = y;
+            ldacc += ld;
+          }
+        }
+      }
+
+      // ---- LULinear on the thread's own row: z <- L (U z) + b, in place ----
+      if (__ldg(v.LT + SBI_L_HAS_LU)) {
+        const float* U = sm + L.lum + l * L.lu_stride;
+        const float* Lw = U + D * D;
+        const float* bias = Lw + D * D;
+        for (int i = 0; i < D; ++i) {
+          float a = 0.f;
+          for (int j = i; j < D; ++j) a = fmaf(U[i * D + j], zs[j * kRows + tid], a);
+          zs[i * kRows + tid] = a;
+        }
+        for (int i = D - 1; i >= 0; --i) {
+          float a = zs[i * kRows + tid];
+          for (int j = 0; j < i; ++j) a = fmaf(Lw[i * D + j], zs[j * kRows + tid], a);
+          zs[i * kRows + tid] = a + bias[i];
+        }
+      }
+    }
+
+    // ---- base density ----
+    if (row0 + tid < rows.R) {
+      float ss = 0.f;
+      for (int d = 0; d < D; ++d) ss = fmaf(zs[d * kRows + tid], zs[d * kRows + tid], ss);
+      logp[row0 + tid] = -0.5f * ss + ldacc + ld_const;
+      if (noise != nullptr)
+        for (int d = 0; d < D; ++d) noise[(row0 + tid) * D + d] = zs[d * kRows + tid];
+    }
+    group_sync();   // rows of the next tile are written cooperatively
+  }
+#undef SBI_TC_ROUND
+#undef SBI_TC_ACOL
+
+  fence_before();
+  group_sync();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(kCols)
+                 : "memory");
+}
+
+}  // namespace tc
+}  // namespace sbi
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace sbi;
+
+static int tc_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    cudaDeviceProp p;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess)
+      n = p.multiProcessorCount;
+    else
+      n = 148;
+  }
+  return n;
+}
+
+// slots of the weight ring: as many as fit next to a second CTA on the SM (2..4)
+static int tc_plan_slots(const sbi_nsf_model* m, const sbi_nsf_tc* tc) {
+  for (int nslot = 4; nslot >= 2; --nslot) {
+    const tc::TcSmem L = tc::tc_smem_layout(*m, tc->stage_cap, nslot);
+    if (L.total_bytes <= 112 * 1024) return nslot;
+  }
+  return 0;
+}
+
+extern "C" int sbi_b200_nsf_tc_supported(const sbi_nsf_model* m, const sbi_nsf_tc* tc) {
+  if (!m || !tc) return 0;
+  if (m->H != 50 || m->KB != 10) return 0;        // instantiated hidden width / bin count
+  if (m->H + m->C > 64) return 0;                 // context rides in the hidden operand's K range
+  if (m->IDp > 48 || m->PR > 32 || m->KB > sbi::kRqsMaxBins) return 0;
+  if (m->NB < 1 || m->NB > SBI_NSF_MAX_BLOCKS) return 0;
+  if (tc->stage_cap <= 0 || (tc->stage_cap & 31) || tc->n_words <= 0) return 0;
+  return tc_plan_slots(m, tc) >= 2 ? 1 : 0;
+}
+
+extern "C" int sbi_b200_nsf_tc_pack(const sbi_nsf_model* m, const sbi_nsf_tc* tc, void* stream) {
+  if (!m || !tc || !m->d_params || !tc->d_src || !tc->d_tcw || tc->n_words <= 0) return SBI_EINVAL;
+  const int threads = 256, blocks = (tc->n_words + threads - 1) / threads;
+  tc::nsf_tc_pack_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(m->d_params, tc->d_src,
+                                                                       tc->d_tcw, tc->n_words);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc,
+                                       const sbi_rows* rows, float* d_logp, float* d_noise,
+                                       void* stream) {
+  if (!m || !tc || !rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_logp)
+    return SBI_EINVAL;
+  if (!tc->d_tab || !tc->d_tcw) return SBI_EINVAL;
+  if (!sbi_b200_nsf_tc_supported(m, tc)) return SBI_ESMEM;
+  if (rows->R == 0) return 0;
+  const int nslot = tc_plan_slots(m, tc);
+  const tc::TcSmem L = tc::tc_smem_layout(*m, tc->stage_cap, nslot);
+  auto k = tc::nsf_logprob_tc_kernel<50, 10>;
+  static int smem_set = 0;
+  if (smem_set < L.total_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
+    if (e != cudaSuccess) return SBI_ESMEM;
+    smem_set = L.total_bytes;
+  }
+  const int64_t ntiles = (rows->R + tc::kRows - 1) / tc::kRows;
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)tc_num_sms() * 2);
+  k<<<grid, tc::kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *tc, *rows, d_logp, d_noise, nslot);
+  return (int)cudaGetLastError();
+}

@@ -98,6 +98,19 @@ struct RqsBin {
   RqsAxis aw, ah;   // softmax numerators (valid when inside)
 };
 
+// REG = true: `p` is a per-thread register array (st == 1); the two derivative reads are then
+// done with an unrolled select instead of a dynamic index, so the array never spills.
+template <bool REG>
+SBI_HD float rqs_pick(const float* pd, int st, int K, int idx) {
+  if (!REG) return pd[idx * st];
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < kRqsMaxBins; ++i)
+    if (i < K - 1 && i == idx) v = pd[i * st];
+  return v;
+}
+
+template <bool REG = false>
 SBI_HD RqsBin rqs_locate(const float* p, int st, const RqsConst& c, float x, bool inverse) {
   RqsBin o;
   o.inside = (x >= -c.B) && (x <= c.B);
@@ -120,14 +133,15 @@ SBI_HD RqsBin rqs_locate(const float* p, int st, const RqsConst& c, float x, boo
   o.yk = lh.klo; o.hb = lh.khi - lh.klo;
   const float* pd = p + 2 * K * st;
   const float de = c.min_d + rqs_softplus(c.edge_raw);
-  o.d0 = (o.b == 0) ? de : c.min_d + rqs_softplus(pd[(o.b - 1) * st]);
-  o.d1 = (o.b == K - 1) ? de : c.min_d + rqs_softplus(pd[o.b * st]);
+  o.d0 = (o.b == 0) ? de : c.min_d + rqs_softplus(rqs_pick<REG>(pd, st, K, o.b - 1));
+  o.d1 = (o.b == K - 1) ? de : c.min_d + rqs_softplus(rqs_pick<REG>(pd, st, K, o.b));
   return o;
 }
 
 // forward: y = spline(x), ld = log dy/dx
+template <bool REG = false>
 SBI_HD void rqs_forward(const float* p, int st, const RqsConst& c, float x, float& y, float& ld) {
-  const RqsBin q = rqs_locate(p, st, c, x, false);
+  const RqsBin q = rqs_locate<REG>(p, st, c, x, false);
   if (!q.inside) { y = x; ld = 0.f; return; }
   const float delta = q.hb / q.wb;
   const float th = (x - q.xk) / q.wb;

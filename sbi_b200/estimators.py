@@ -12,6 +12,7 @@ whose backward is the fused forward+backward (VJP) kernel.  No CPU path exists.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -364,6 +365,41 @@ class FlowEstimator(nn.Module):
                                        L.stream_ptr()), f"{self.fam.name}_inverse")
         return out, lad
 
+    # ---- tensor-core bulk path (nsf only) --------------------------------------------------------
+    #: rows from which log_prob goes through the tcgen05 kernel (csrc/nsf_tc.cu).  Below it the
+    #: SIMT kernel's smaller tiles fill the GPU better.  SBI_B200_TC=0 disables, =1 forces.
+    TC_MIN_ROWS = int(os.environ.get("SBI_B200_TC_MIN_ROWS", 32768))
+
+    def _tc_state(self, m):
+        """NsfTc struct for the current parameters, or None if the model is outside what the
+        tensor-core kernel instantiates.  The operands are re-packed from the flat parameter
+        buffer on every call (a ~1 MB elementwise kernel): the optimizer kernels update the
+        parameters through raw pointers, so no version counter could be trusted."""
+        if self.fam.name != "nsf" or os.environ.get("SBI_B200_TC", "") == "0":
+            return None
+        flat = self.net.flat
+        st = self._cache.get("tc")
+        if st is None or st["dev"] != flat.device:
+            plan = self.layout.tc_plan()
+            if plan is None:
+                self._cache["tc"] = {"dev": flat.device, "plan": None}
+                return None
+            dev = flat.device
+            st = {"dev": dev, "plan": plan,
+                  "src": torch.as_tensor(plan["src"], device=dev),
+                  "tab": torch.as_tensor(plan["tab"], device=dev),
+                  "tcw": torch.empty(plan["n_words"], dtype=torch.float32, device=dev)}
+            self._cache["tc"] = st
+        if st["plan"] is None:
+            return None
+        tc = L.NsfTc(st["plan"]["n_words"], st["plan"]["stage_cap"], st["src"].data_ptr(),
+                     st["tab"].data_ptr(), st["tcw"].data_ptr())
+        lib = L.load()
+        if not lib.sbi_b200_nsf_tc_supported(C.byref(m), C.byref(tc)):
+            return None
+        L.check(lib.sbi_b200_nsf_tc_pack(C.byref(m), C.byref(tc), L.stream_ptr()), "nsf_tc_pack")
+        return tc
+
     # ---- raw kernel entry (no autograd) --------------------------------------------------------------
     def _logprob_raw(self, inp: Tensor, ctx: Tensor, shared: bool, want_noise=False,
                      index: Optional[Tensor] = None, n_rows: Optional[int] = None,
@@ -377,6 +413,13 @@ class FlowEstimator(nn.Module):
         m = self._model(nbuf=2, raw_condition=raw_condition)
         rows = L.Rows(inp.data_ptr(), ctx.data_ptr(),
                       None if index is None else index.data_ptr(), R, 1 if shared else 0)
+        force = os.environ.get("SBI_B200_TC", "") == "1"
+        if self.fam.name == "nsf" and (R >= self.TC_MIN_ROWS or force):
+            tc = self._tc_state(m)
+            if tc is not None:
+                L.check(lib.sbi_b200_nsf_logprob_tc(C.byref(m), C.byref(tc), C.byref(rows), L.ptr(lp),
+                                                    L.ptr(noise), L.stream_ptr()), "nsf_logprob_tc")
+                return lp, noise
         L.check(self.fam.fn("logprob")(C.byref(m), C.byref(rows), L.ptr(lp), L.ptr(noise),
                                        L.stream_ptr()), f"{self.fam.name}_logprob")
         return lp, noise

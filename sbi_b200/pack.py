@@ -206,6 +206,99 @@ class NsfLayout(_LayoutOps):
     def tables(self):
         return self.layer_tab.reshape(-1).astype(np.int32), self.feat_tab.astype(np.int32)
 
+    # ------------------------------------------------------------- tensor-core operand plan
+    def tc_plan(self):
+        """Gather map + stage table for the tcgen05 evaluation path (include/sbi_b200.h,
+        `sbi_nsf_tc`; kernel sbi_b200/csrc/nsf_tc.cu), or None when the model is outside what
+        that kernel instantiates.
+
+        Every linear of the conditioner (nflows ResidualNet) becomes one or two K-major
+        no-swizzle UMMA operand blocks [K/4 slabs][N rows][4 floats].  The hidden operand's
+        columns are [hidden (H) | context (C) | 0] so that the context never needs its own
+        staging: the GLU gate reads the K-steps that cover columns H..H+C-1.
+        Returns dict(src=int32 (n_words,), tab=int32 (T*STRIDE,), stage_cap=int, n_words=int).
+        """
+        D, C, H, NB, T = self.D, self.C, self.H, self.NB, self.T
+        if H != 50 or self.KB != 10 or H + C > 64 or self.IDp > 48 or self.PR > 32:
+            return None
+        Hp, Cp, K0p, PR, NPAR = self.Hp, self.Cp, self.K0p, self.PR, self.NPAR
+        HP8 = (H + 7) & ~7
+        KC0 = H // 8
+        nkc = (H + C + 7) // 8 - KC0
+        tab = np.zeros((T, L.SBI_NSF_TC_STRIDE), np.int32)
+        chunks = []          # per stage: int64 array of the hi half (param index or -1)
+        off = 0
+        stage_cap = 0
+
+        def block(N, K, fill):
+            """fill(n, k) -> param index or -1 ; returns the flattened [K/4][N][4] block"""
+            blk = np.full((K // 4, N, 4), -1, np.int64)
+            n = np.arange(N)[:, None]
+            k = np.arange(K)[None, :]
+            vals = fill(n + 0 * k, k + 0 * n)
+            blk[(k // 4) + 0 * n, n + 0 * k, (k % 4) + 0 * n] = vals
+            return blk.reshape(-1)
+
+        def ctx_block(woff, rowlen):
+            def fill(n, k):
+                c = 8 * KC0 + k - H
+                ok = (n < H) & (c >= 0) & (c < C)
+                return np.where(ok, woff + n * rowlen + np.clip(c, 0, max(C - 1, 0)), -1)
+            return block(64, 8 * nkc, fill)
+
+        def hidden_block(woff, N, rowmap):
+            """rowmap(n) -> (valid, packed row index) of the [.,Hp] weight matrix"""
+            def fill(n, k):
+                valid, row = rowmap(n)
+                ok = valid & (k < H)
+                return np.where(ok, woff + row * Hp + np.minimum(k, H - 1), -1)
+            return block(N, HP8, fill)
+
+        for l in range(T):
+            lt = self.layer_tab[l]
+            n_id, n_tr = int(lt[L.L_NID]), int(lt[L.L_NTR])
+            kid8 = (n_id + 7) & ~7
+            stages = []      # (hi half, N, aux)
+            w0 = int(lt[L.L_W0])
+
+            def fill_id(n, k, w0=w0, n_id=n_id):
+                ok = (n < H) & (k < n_id)
+                return np.where(ok, w0 + n * K0p + Cp + np.minimum(k, max(n_id - 1, 0)), -1)
+
+            stages.append((np.concatenate([block(64, kid8, fill_id), ctx_block(w0, K0p)]), 64, 0))
+            ident = lambda n: (n < H, np.minimum(n, H - 1))
+            for b in range(NB):
+                t = L.L_BLK0 + 6 * b
+                w1, w2, wc = int(lt[t + 0]), int(lt[t + 2]), int(lt[t + 4])
+                stages.append((np.concatenate([hidden_block(w1, 64, ident), ctx_block(wc, Cp)]), 64, 0))
+                stages.append((hidden_block(w2, 64, ident), 64, 0))
+            wf = int(lt[L.L_WF])
+            f0 = 0
+            while f0 < n_tr:
+                nf = min(3, n_tr - f0)
+
+                def rowmap(n, f0=f0, nf=nf):
+                    f, i = n // 32, n % 32
+                    valid = (f < nf) & (i < NPAR)
+                    return valid, np.where(valid, (f0 + f) * PR + i, 0)
+
+                stages.append((hidden_block(wf, 32 * nf, rowmap), 32 * nf, f0 | (nf << 16)))
+                f0 += nf
+            if len(stages) > L.SBI_NSF_TC_MAX_STAGES:
+                return None
+            tab[l, 0], tab[l, 1] = len(stages), kid8
+            for s, (hi, N, aux) in enumerate(stages):
+                nfl = 2 * hi.size
+                tab[l, 4 + 4 * s: 8 + 4 * s] = (off, nfl, N, aux)
+                chunks.append(hi)
+                chunks.append(np.where(hi >= 0, -2 - hi, -1))
+                off += nfl
+                stage_cap = max(stage_cap, nfl)
+        src = np.concatenate(chunks).astype(np.int32)
+        assert src.size == off
+        return dict(src=src, tab=tab.reshape(-1).astype(np.int32),
+                    stage_cap=int((stage_cap + 31) & ~31), n_words=int(off))
+
     def fill_struct(self, s: "L.NsfModel", nbuf: int):
         s.D, s.C, s.H, s.NB, s.KB, s.T = self.D, self.C, self.H, self.NB, self.KB, self.T
         s.Dp, s.Cp, s.IDp, s.Hp, s.PR = self.Dp, self.Cp, self.IDp, self.Hp, self.PR
