@@ -6,8 +6,9 @@
 // oracle/nflows_port/nn/nets/resnet.py; built at flow.py:411-419) run on the 5th-generation
 // tensor cores:
 //
-//   * one CTA = 4 row warps (128 rows, one row per thread = one row per TMEM lane) + 1 TMA warp,
-//     two CTAs per SM (256 TMEM columns each);
+//   * one CTA = 8 warps (128 rows = 128 TMEM lanes, two threads per row splitting the columns
+//     of every epilogue), two CTAs per SM (256 TMEM columns each); thread 0 issues the MMAs
+//     and, right behind them, the TMA copy of the next stage's weights;
 //   * tcgen05.mma kind::tf32, M = 128, issued by one thread; A (activations) is read from TMEM,
 //     where the row threads put it with tcgen05.st after splitting every fp32 value into
 //     hi = tf32(x) and lo = x - hi; B (weights, pre-split hi/lo and pre-arranged in the K-major
@@ -17,8 +18,8 @@
 //   * the context is a K-extension of the hidden operand: A columns are
 //     [ hidden (H) | context (C) | 0 ], so the GLU gate W_c ctx is one more small MMA on the
 //     same operand and the context never has to be re-staged;
-//   * spline, LU and base density are per-thread code on the thread's own row (no barriers),
-//     using the very same rqs.cuh routines as the SIMT kernels.
+//   * spline, LU and base density are per-thread code on the thread's own row, using the very
+//     same rqs.cuh routines as the SIMT kernels.
 //
 // TMEM columns of a CTA:  [0,64) A_hi | [64,128) A_lo | [128,192) D | [192,256) G (GLU gate);
 // the final layer's spline parameters P (32 columns per feature, <= 3 features per pass)
@@ -34,8 +35,9 @@ namespace sbi {
 namespace tc {
 
 constexpr int kRows = 128;        // rows per tile
-constexpr int kRowThreads = 128;
-constexpr int kThreads = 160;     // 4 row warps + 1 TMA producer warp
+constexpr int kRowThreads = 256;  // two threads per row (column halves)
+constexpr int kThreads = 256;     // 8 row warps; thread 0 also issues the MMAs and the TMA copies
+constexpr int kSlots = 2;         // weight ring: the stage in use + the prefetched next one
 constexpr int kCols = 256;        // TMEM columns per CTA
 constexpr int cAhi = 0, cAlo = 64, cD = 128, cG = 192;
 constexpr int kMaxPassFeat = 3;   // spline features per final-layer pass (N = 96)
@@ -121,11 +123,11 @@ __device__ __forceinline__ void store_a8(uint32_t tlane, int col, const float (&
   st8(tlane + cAhi + col, hi);
   st8(tlane + cAlo + col, lo);
 }
-__device__ __forceinline__ void group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---- shared memory plan -------------------------------------------------------------------------
 struct TcSmem {
-  int zs, ctx, lum, lu_stride, ring;   // float offsets
+  int zs, ctx, lds, lum, bias, bias_stride, ring;   // float offsets
   int bar_bytes, total_bytes;
 };
 __host__ __device__ inline TcSmem tc_smem_layout(const sbi_nsf_model& m, int stage_cap, int nslot) {
@@ -133,12 +135,14 @@ __host__ __device__ inline TcSmem tc_smem_layout(const sbi_nsf_model& m, int sta
   int fl = 0;
   L.zs = fl;  fl += m.Dp * kRows;
   L.ctx = fl; fl += m.Cp * kRows;
-  L.lu_stride = round4(2 * m.D * m.D + 2 * m.D);
-  L.lum = fl; fl += m.T * L.lu_stride;
+  L.lds = fl; fl += kRows;
+  L.lum = fl; fl += round4(2 * m.D * m.D + 2 * m.D);
+  L.bias_stride = 64 + m.NB * 192 + m.TRmax * 32;
+  L.bias = fl; fl += m.T * L.bias_stride;
   fl = (fl + 31) & ~31;
   L.ring = fl; fl += nslot * stage_cap;
   L.bar_bytes = fl * 4;
-  L.total_bytes = L.bar_bytes + (2 * nslot + 1) * 8 + 16;
+  L.total_bytes = L.bar_bytes + (nslot + 1) * 8 + 16;
   return L;
 }
 
@@ -162,17 +166,40 @@ __global__ void nsf_tc_pack_kernel(const float* __restrict__ params, const int32
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
+// Thread 0 of the CTA drives the tensor core and the weight stream.  Stage s lives in ring slot
+// s % 2.  When the MMAs of stage s have been issued, the TMA copy of stage s+1 goes into the other
+// slot: that slot held stage s-1, whose MMAs completed before every thread left round s-1.
 struct Issuer {
   uint32_t tbase;       // TMEM base (lane 0, column 0)
   float* ring;
-  uint64_t *full, *empty, *dbar;
-  int cap, nslot;
+  uint64_t *full, *dbar;
+  const float* tcw;
+  const int32_t* tab;   // stage table (all layers)
+  int cap, T;
   uint32_t it;          // stage counter
   uint32_t sbase, lo_off;   // current stage: shared address of the hi half, byte offset of lo half
+  // next stage to fetch
+  int64_t f_tile, ntiles, tile_step;
+  int f_l, f_s;
+
+  __device__ __forceinline__ void fetch_next() {
+    if (f_tile >= ntiles) return;
+    const int32_t* t = tab + f_l * SBI_NSF_TC_STRIDE;
+    const int off = __ldg(t + 4 + 4 * f_s), nfl = __ldg(t + 5 + 4 * f_s);
+    const uint32_t slot = fetched & 1u;
+    mbar_arrive_expect_tx(&full[slot], (uint32_t)nfl * 4u);
+    bulk_g2s(ring + (size_t)slot * cap, tcw + off, (uint32_t)nfl * 4u, &full[slot]);
+    ++fetched;
+    if (++f_s == __ldg(t)) {
+      f_s = 0;
+      if (++f_l == T) { f_l = 0; f_tile += tile_step; }
+    }
+  }
+  uint32_t fetched;
 
   __device__ __forceinline__ void begin(int stage_floats) {
-    const int s = it % nslot;
-    mbar_wait(&full[s], (it / nslot) & 1u);
+    const uint32_t s = it & 1u;
+    mbar_wait(&full[s], (it >> 1) & 1u);
     sbase = smem_u32(ring + (size_t)s * cap);
     lo_off = (uint32_t)stage_floats * 2u;     // (floats / 2) * 4 bytes
     fence_after();
@@ -182,63 +209,108 @@ struct Issuer {
     const uint32_t idesc = make_idesc(N);
     const uint32_t slab = (uint32_t)N * 16u;
     const uint32_t bh = sbase + (uint32_t)blk_floats * 4u;
+    uint64_t dh = make_bdesc(bh, slab, 128u);
+    uint64_t dl = make_bdesc(bh + lo_off, slab, 128u);
+    const uint64_t dstep = (uint64_t)((2u * slab) >> 4);    // start-address field advance per K-step
+    uint32_t ah = tbase + cAhi + a0, al = tbase + cAlo + a0;
+    const uint32_t d = tbase + dcol;
     for (int kk = 0; kk < nk; ++kk) {
-      const uint64_t dh = make_bdesc(bh + 2u * kk * slab, slab, 128u);
-      const uint64_t dl = make_bdesc(bh + lo_off + 2u * kk * slab, slab, 128u);
-      const uint32_t ah = tbase + cAhi + a0 + 8 * kk, al = tbase + cAlo + a0 + 8 * kk;
-      mma_tf32(tbase + dcol, ah, dh, idesc, acc);
-      mma_tf32(tbase + dcol, al, dh, idesc, 1u);
-      mma_tf32(tbase + dcol, ah, dl, idesc, 1u);
+      mma_tf32(d, ah, dh, idesc, acc);
+      mma_tf32(d, al, dh, idesc, 1u);
+      mma_tf32(d, ah, dl, idesc, 1u);
       acc = 1u;
+      dh += dstep; dl += dstep; ah += 8; al += 8;
     }
   }
   __device__ __forceinline__ void end() {
-    commit(&empty[it % nslot]);   // weight slot free once these MMAs have read it
-    commit(dbar);                 // accumulators ready
+    commit(dbar);                 // accumulators ready (and the stage's weights fully read)
+    fetch_next();
   }
 };
 
-// h += (W2 a + b2) * sigmoid(Wc ctx + bc) for hidden chunks [C_LO, C_HI)
-template <int H, int HP8, int C_LO, int C_HI>
-__device__ __forceinline__ void glu_update(uint32_t tlane, const float* __restrict__ b2,
-                                           const float* __restrict__ bc, float (&h)[HP8]) {
-  constexpr int NC = C_HI - C_LO;
-  float d[8 * NC], g[8 * NC];
+// ---- epilogue math of the bulk-evaluation path ------------------------------------------------
+// Same formulas as the SIMT kernels (rqs.cuh, common.cuh) evaluated with the hardware
+// approximations ex2/lg2/rcp (about 2 ulp each) instead of the correctly rounded library calls:
+// after the 3xTF32 linears the log-density already carries ~1e-5 of rounding, and these
+// functions are 40% of the instructions of this kernel.  tests/test_nsf_tc_gpu.py holds the
+// result to the SIMT kernel within 5e-4 and to the fp64 oracle within the common 2e-3.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
+
+// Monotone rational-quadratic spline, forward direction, parameters in registers
+// (p[0,K) widths, [K,2K) heights, [2K,3K-1) derivatives; restates rqs_forward of rqs.cuh:
+// softmax -> min-size affine -> cumulative knots in [-B,B] -> bin = last knot <= x).
+template <int K>
+__device__ __forceinline__ void rqs_forward_fast(const float (&p)[32], const RqsConst& c, float x,
+                                                 float& y, float& ld) {
+  const float B = c.B;
+  if (!(x >= -B && x <= B)) { y = x; ld = 0.f; return; }
+  float ew[K], eh[K];
+  float mw = -INFINITY, mh = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    ld8(tlane + cD + 8 * (C_LO + c), d + 8 * c);
-    ld8(tlane + cG + 8 * (C_LO + c), g + 8 * c);
+  for (int i = 0; i < K; ++i) {
+    ew[i] = p[i] * c.isq;
+    eh[i] = p[K + i] * c.isq;
+    mw = fmaxf(mw, ew[i]);
+    mh = fmaxf(mh, eh[i]);
   }
-  wait_ld();
+  float sw = 0.f, sh = 0.f;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
+  for (int i = 0; i < K; ++i) {
+    ew[i] = __expf(ew[i] - mw);
+    eh[i] = __expf(eh[i] - mh);
+    sw += ew[i];
+    sh += eh[i];
+  }
+  const float rw = __fdividef(1.f - c.min_w * (float)K, sw);
+  const float rh = __fdividef(1.f - c.min_h * (float)K, sh);
+  float cw = 0.f, ch = 0.f, lo_w = -B, lo_h = -B;
+  float xk = -B, xk1 = B, yk = -B, yk1 = B, r0 = c.edge_raw, r1 = c.edge_raw;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      constexpr int dummy = 0;
-      (void)dummy;
-      const int j = 8 * (C_LO + c) + i;
-      if (j < H) {
-        const float t = d[8 * c + i] + __ldg(b2 + j);
-        const float s = sigmoid_f(g[8 * c + i] + __ldg(bc + j));
-        h[j] = h[j] + t * s;
-      }
+  for (int i = 0; i < K; ++i) {
+    cw += fmaf(rw, ew[i], c.min_w);
+    ch += fmaf(rh, eh[i], c.min_h);
+    const float hi_w = (i == K - 1) ? B : fmaf(2.f * B, cw, -B);
+    const float hi_h = (i == K - 1) ? B : fmaf(2.f * B, ch, -B);
+    if (x >= lo_w) {
+      xk = lo_w; xk1 = hi_w; yk = lo_h; yk1 = hi_h;
+      r0 = (i == 0) ? c.edge_raw : p[2 * K + (i > 0 ? i - 1 : 0)];
+      r1 = (i == K - 1) ? c.edge_raw : p[2 * K + (i < K - 1 ? i : 0)];
     }
+    lo_w = hi_w;
+    lo_h = hi_h;
   }
+  const float wb = xk1 - xk, hb = yk1 - yk;
+  const float d0 = c.min_d + softplus_fast(r0), d1 = c.min_d + softplus_fast(r1);
+  const float iw = __fdividef(1.f, wb);
+  const float delta = hb * iw;
+  const float th = (x - xk) * iw;
+  const float omt = 1.f - th;
+  const float tomt = th * omt;
+  const float num = hb * (delta * th * th + d0 * tomt);
+  const float den = delta + (d0 + d1 - 2.f * delta) * tomt;
+  y = yk + __fdividef(num, den);
+  const float dnum = delta * delta * (d1 * th * th + 2.f * delta * tomt + d0 * omt * omt);
+  ld = __logf(dnum) - 2.f * __logf(den);
 }
 
+// Two threads share a row: `half` 0 owns hidden chunks 0..3 (columns 0..31), `half` 1 owns
+// chunks 4.. (columns 32..HP8-1 and the context tail).  All epilogues are column-wise, so the
+// halves never exchange activations; the spline features of a layer alternate between them.
 template <int H, int KB>
 __global__ void __launch_bounds__(kThreads, 2)
 nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ sbi_nsf_tc tc,
                       const __grid_constant__ sbi_rows rows, float* __restrict__ logp,
-                      float* __restrict__ noise, int nslot) {
+                      float* __restrict__ noise) {
   constexpr int HP8 = (H + 7) & ~7;
   constexpr int NCH = HP8 / 8;      // K-steps / 8-column chunks of the hidden operand
   constexpr int KC0 = H / 8;        // first chunk that holds context columns
+  constexpr int NS = 4;             // chunk slots per thread
+  static_assert(NCH <= 2 * NS, "hidden width");
   extern __shared__ __align__(128) float sm[];
-  const TcSmem L = tc_smem_layout(m, tc.stage_cap, nslot);
+  const TcSmem L = tc_smem_layout(m, tc.stage_cap, kSlots);
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(sm) + L.bar_bytes);
-  uint64_t* empty = full + nslot;
-  uint64_t* dbar = empty + nslot;
+  uint64_t* dbar = full + kSlots;
   uint32_t* tbase_s = reinterpret_cast<uint32_t*>(dbar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int C = m.C;
@@ -246,10 +318,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
   const int64_t ntiles = (rows.R + kRows - 1) / kRows;
 
   if (tid == 0) {
-    for (int s = 0; s < nslot; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
+    for (int s = 0; s < kSlots; ++s) mbar_init(&full[s], 1);
     mbar_init(dbar, 1);
     fence_barrier_init();
   }
@@ -265,65 +334,42 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
   fence_after();
   const uint32_t tbase = *tbase_s;
 
-  // ---------------- TMA producer warp: streams the stages in consumption order ----------------
-  if (warp == 4) {
-    if (tid == kRowThreads) {
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int l = 0; l < m.T; ++l) {
-          const int32_t* tab = tc.d_tab + l * SBI_NSF_TC_STRIDE;
-          const int ns = __ldg(tab);
-          for (int s = 0; s < ns; ++s) {
-            const int off = __ldg(tab + 4 + 4 * s), nfl = __ldg(tab + 5 + 4 * s);
-            const int slot = it % nslot;
-            mbar_wait_backoff(&empty[slot], ((it / nslot) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&full[slot], (uint32_t)nfl * 4u);
-            bulk_g2s(sm + L.ring + (size_t)slot * tc.stage_cap, tc.d_tcw + off, (uint32_t)nfl * 4u,
-                     &full[slot]);
-            ++it;
-          }
-        }
-      }
-    }
-    return;
-  }
-
   // ---------------- row warps ------------------------------------------------------------------
   const float* __restrict__ P = m.d_params;
   float* zs = sm + L.zs;
   float* ctx_s = sm + L.ctx;
-  const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);
+  float* lds = sm + L.lds;
+  const float* bias_s = sm + L.bias;
+  const int half = warp >> 2;                          // which column half of the row
+  const int row = ((warp & 3) << 5) | (tid & 31);      // row of the tile = TMEM lane
+  const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
   RqsConst rc = rqs_const(m);
   rc.K = KB;   // compile-time bin count keeps the spline parameters in registers
   const int D = m.D;
 
-  // dense LU factors of every layer, once per CTA: [U D*D | L D*D | bias D | diag D]
-  for (int l = 0; l < m.T; ++l) {
-    const int* LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
-    if (!__ldg(LT + SBI_L_HAS_LU)) continue;
-    const float* lo = P + __ldg(LT + SBI_L_LU_LOWER);
-    const float* up = P + __ldg(LT + SBI_L_LU_UPPER);
-    const float* dg = P + __ldg(LT + SBI_L_LU_DIAG);
-    const float* bi = P + __ldg(LT + SBI_L_LU_BIAS);
-    float* U = sm + L.lum + l * L.lu_stride;
-    float* Lw = U + D * D;
-    for (int t = tid; t < D * D; t += kRowThreads) {
-      const int i = t / D, j = t % D;
-      float u = 0.f, lv = 0.f;
-      if (j > i) u = __ldg(up + i * D - i * (i + 1) / 2 + (j - i - 1));
-      else if (j < i) lv = __ldg(lo + i * (i - 1) / 2 + j);
-      else u = softplus_f(__ldg(dg + i)) + 1e-3f;
-      U[t] = u;
-      Lw[t] = lv;
-      if (j == i) {
-        Lw[D * D + i] = __ldg(bi + i);
-        Lw[D * D + D + i] = u;
+  // all biases of the conditioners, once per CTA (zero beyond the real widths):
+  //   per layer [b0 64 | per block: b1 64, b2 64, bc 64 | bf TRmax*32]
+  {
+    float* bs = sm + L.bias;
+    for (int e = tid; e < m.T * L.bias_stride; e += kRowThreads) {
+      const int l = e / L.bias_stride, o = e % L.bias_stride;
+      const int* LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
+      float v = 0.f;
+      if (o < 64) {
+        if (o < H) v = __ldg(P + __ldg(LT + SBI_L_B0) + o);
+      } else if (o < 64 + m.NB * 192) {
+        const int b = (o - 64) / 192, w = ((o - 64) % 192) / 64, j = (o - 64) % 64;
+        if (j < H) v = __ldg(P + __ldg(LT + SBI_L_BLK0 + 6 * b + 1 + 2 * w) + j);
+      } else {
+        const int q = o - 64 - m.NB * 192, f = q / 32, i = q % 32;
+        if (f < __ldg(LT + SBI_L_NTR) && i < 3 * KB - 1) v = __ldg(P + __ldg(LT + SBI_L_BF) + f * m.PR + i);
       }
+      bs[e] = v;
     }
   }
   // batch-constant part of the log-density, summed in the order of lu_logdet_total (nsf.cuh)
-  float ld_const;
-  {
+  float ld_const = 0.f;
+  if (half == 1) {
     float tot = 0.f;
     for (int l = 0; l < m.T; ++l) {
       const int* LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
@@ -337,8 +383,12 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
   }
 
   Issuer iss;
-  iss.tbase = tbase; iss.ring = sm + L.ring; iss.full = full; iss.empty = empty; iss.dbar = dbar;
-  iss.cap = tc.stage_cap; iss.nslot = nslot; iss.it = 0; iss.sbase = 0; iss.lo_off = 0;
+  iss.tbase = tbase; iss.ring = sm + L.ring; iss.full = full; iss.dbar = dbar;
+  iss.tcw = tc.d_tcw; iss.tab = tc.d_tab; iss.cap = tc.stage_cap; iss.T = m.T;
+  iss.it = 0; iss.sbase = 0; iss.lo_off = 0;
+  iss.f_tile = blockIdx.x; iss.ntiles = ntiles; iss.tile_step = gridDim.x; iss.f_l = 0; iss.f_s = 0;
+  iss.fetched = 0;
+  if (tid == 0) iss.fetch_next();     // first stage of the first tile
   uint32_t dpar = 0;
 
   // hand the operands over to the tensor core, run one stage, wait for its accumulators
@@ -360,7 +410,10 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
   } while (0)
 
   // A-operand column j of a hidden layer: activation (j < H), context (H <= j < H+C), zero
-#define SBI_TC_ACOL(j, ACT) ((j) < H ? (ACT) : (((j) - H) < C ? ctx_s[((j) - H) * kRows + tid] : 0.f))
+  auto acol = [&](int j, float act) -> float {
+    const int c = j - H;
+    return j < H ? act : ((c < C) ? ctx_s[c * kRows + row] : 0.f);
+  };
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * kRows;
@@ -392,38 +445,45 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
       group_sync();
     }
     // context tail columns [HP8, 64) never change within a tile
+    if (half == 1) {
 #pragma unroll
-    for (int c = NCH; c < 8; ++c) {
-      float v[8];
+      for (int c = NCH; c < 8; ++c) {
+        float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = SBI_TC_ACOL(8 * c + i, 0.f);
-      store_a8(tlane, 8 * c, v);
+        for (int i = 0; i < 8; ++i) v[i] = acol(8 * c + i, 0.f);
+        store_a8(tlane, 8 * c, v);
+      }
     }
     float ldacc = 0.f;
 
     for (int l = 0; l < m.T; ++l) {
       const NsfLayerView v = layer_view(m, l);
       const int32_t* tab = tc.d_tab + l * SBI_NSF_TC_STRIDE;
+      const float* bl = bias_s + l * L.bias_stride;
       const int kid8 = __ldg(tab + 1);
       int stage = 0;
-      float h[HP8];
+      float h[NS][8];
 
       // ---- initial layer: A = [identity features | 0 ... | context] ----
-      for (int kk = 0; kk < kid8 / 8; ++kk) {
-        float a[8];
+      // (half 1 ran the previous layer's LU on this row, so it also writes the identity columns)
+      if (half == 1) {
+        for (int kk = 0; kk < kid8 / 8; ++kk) {
+          float a[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = 8 * kk + i;
-          a[i] = (j < v.n_id) ? zs[__ldg(v.idf + j) * kRows + tid] : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            const int j = 8 * kk + i;
+            a[i] = (j < v.n_id) ? zs[__ldg(v.idf + j) * kRows + row] : 0.f;
+          }
+          store_a8(tlane, 8 * kk, a);
         }
-        store_a8(tlane, 8 * kk, a);
-      }
+      } else {
 #pragma unroll
-      for (int c = KC0; c < NCH; ++c) {
-        float a[8];
+        for (int c = KC0; c < NCH; ++c) {
+          float a[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = SBI_TC_ACOL(8 * c + i, 0.f);
-        store_a8(tlane, 8 * c, a);
+          for (int i = 0; i < 8; ++i) a[i] = acol(8 * c + i, 0.f);
+          store_a8(tlane, 8 * c, a);
+        }
       }
       {
         const int nfl = __ldg(tab + 5 + 4 * stage);
@@ -434,25 +494,59 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
         });
         ++stage;
       }
+      // dense LU factors of this layer: [U D*D | L D*D | bias D | diag D] (used after the spline;
+      // the previous layer's were last read before the barrier of the round above)
+      if (__ldg(v.LT + SBI_L_HAS_LU)) {
+        const float* lo = P + __ldg(v.LT + SBI_L_LU_LOWER);
+        const float* up = P + __ldg(v.LT + SBI_L_LU_UPPER);
+        const float* dg = P + __ldg(v.LT + SBI_L_LU_DIAG);
+        const float* bi = P + __ldg(v.LT + SBI_L_LU_BIAS);
+        float* U = sm + L.lum;
+        float* Lw = U + D * D;
+        for (int t = tid; t < D * D; t += kRowThreads) {
+          const int i = t / D, j = t % D;
+          float u = 0.f, lv = 0.f;
+          if (j > i) u = __ldg(up + i * D - i * (i + 1) / 2 + (j - i - 1));
+          else if (j < i) lv = __ldg(lo + i * (i - 1) / 2 + j);
+          else u = softplus_f(__ldg(dg + i)) + 1e-3f;
+          U[t] = u;
+          Lw[t] = lv;
+          if (j == i) {
+            Lw[D * D + i] = __ldg(bi + i);
+            Lw[D * D + D + i] = u;
+          }
+        }
+      }
       {
-        float d[HP8];
-        ld_cols<NCH>(tlane + cD, d);
-        wait_ld();
-        const float* b0 = P + __ldg(v.LT + SBI_L_B0);
+        float d[NS][8];
 #pragma unroll
-        for (int j = 0; j < HP8; ++j) h[j] = (j < H) ? d[j] + __ldg(b0 + j) : 0.f;
+        for (int s = 0; s < NS; ++s)
+          if (half * NS + s < NCH) ld8(tlane + cD + 8 * (half * NS + s), d[s]);
+        wait_ld();
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = 8 * (half * NS + s) + i;
+            h[s][i] = (j < H) ? d[s][i] + bl[j & 63] : 0.f;
+          }
       }
 
       // ---- residual blocks ----
       for (int b = 0; b < m.NB; ++b) {
-        const int* BT = v.LT + SBI_L_BLK0 + 6 * b;
+        const float* b1 = bl + 64 + b * 192;
+        const float* b2 = b1 + 64;
+        const float* bc = b1 + 128;
         // A = [relu(h) | ctx]
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          float a[8];
+        for (int s = 0; s < NS; ++s) {
+          const int c = half * NS + s;
+          if (c < NCH) {
+            float a[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) a[i] = SBI_TC_ACOL(8 * c + i, relu_f(h[8 * c + i]));
-          store_a8(tlane, 8 * c, a);
+            for (int i = 0; i < 8; ++i) a[i] = acol(8 * c + i, relu_f(h[s][i]));
+            store_a8(tlane, 8 * c, a);
+          }
         }
         {
           const int nfl = __ldg(tab + 5 + 4 * stage);
@@ -465,17 +559,23 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           ++stage;
         }
         {
-          float d[HP8];
-          ld_cols<NCH>(tlane + cD, d);
+          float d[NS][8];
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            if (half * NS + s < NCH) ld8(tlane + cD + 8 * (half * NS + s), d[s]);
           wait_ld();
-          const float* b1 = P + __ldg(BT + 1);
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float a[8];
+          for (int s = 0; s < NS; ++s) {
+            const int c = half * NS + s;
+            if (c < NCH) {
+              float a[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              a[i] = SBI_TC_ACOL(8 * c + i, relu_f(d[8 * c + i] + __ldg(b1 + (8 * c + i < H ? 8 * c + i : 0))));
-            store_a8(tlane, 8 * c, a);
+              for (int i = 0; i < 8; ++i) {
+                const int j = 8 * c + i;
+                a[i] = acol(j, relu_f(d[s][i] + b1[j & 63]));
+              }
+              store_a8(tlane, 8 * c, a);
+            }
           }
         }
         {
@@ -487,24 +587,42 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           ++stage;
         }
         {
-          const float* b2 = P + __ldg(BT + 3);
-          const float* bc = P + __ldg(BT + 5);
-          // two halves to bound registers
-          glu_update<H, HP8, 0, (NCH + 1) / 2>(tlane, b2, bc, h);
-          glu_update<H, HP8, (NCH + 1) / 2, NCH>(tlane, b2, bc, h);
+          // h += (W2 a + b2) * sigmoid(Wc ctx + bc)
+          float d[NS][8], g[NS][8];
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            if (half * NS + s < NCH) {
+              ld8(tlane + cD + 8 * (half * NS + s), d[s]);
+              ld8(tlane + cG + 8 * (half * NS + s), g[s]);
+            }
+          wait_ld();
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = 8 * (half * NS + s) + i;
+              if (j < H) {
+                const float t = d[s][i] + b2[j];
+                const float sg = sigmoid_fast(g[s][i] + bc[j]);
+                h[s][i] = h[s][i] + t * sg;
+              }
+            }
         }
       }
 
       // ---- final layer passes + spline on the transformed features ----
       {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          float a[8];
+        for (int s = 0; s < NS; ++s) {
+          const int c = half * NS + s;
+          if (c < NCH) {
+            float a[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) a[i] = SBI_TC_ACOL(8 * c + i, h[8 * c + i]);
-          store_a8(tlane, 8 * c, a);
+            for (int i = 0; i < 8; ++i) a[i] = acol(8 * c + i, h[s][i]);
+            store_a8(tlane, 8 * c, a);
+          }
         }
-        const float* bf = P + __ldg(v.LT + SBI_L_BF);
+        const float* bf = bl + 64 + m.NB * 192;
         const int ns = __ldg(tab);
         for (; stage < ns; ++stage) {
           const int nfl = __ldg(tab + 5 + 4 * stage);
@@ -516,52 +634,56 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
             iss.block(cD, 0, NCH, 0, N, acc);
           });
           for (int f = 0; f < nf; ++f) {
+            if (((f0 + f) & 1) != half) continue;     // warp-uniform: features alternate between halves
             float p[32];
             ld_cols<4>(tlane + cD + 32 * f, p);
             wait_ld();
-            const float* bff = bf + (f0 + f) * m.PR;
+            const float* bff = bf + (f0 + f) * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) p[i] = (i < 3 * KB - 1) ? p[i] + __ldg(bff + i) : 0.f;
+            for (int i = 0; i < 32; ++i) p[i] = (i < 3 * KB - 1) ? p[i] + bff[i] : 0.f;
             const int j = __ldg(v.trf + f0 + f);
-            const float x = zs[j * kRows + tid];
+            const float x = zs[j * kRows + row];
             float y, ld;
-            rqs_forward<true>(p, 1, rc, x, y, ld);
-            zs[j * kRows + tid] = y;
+            rqs_forward_fast<KB>(p, rc, x, y, ld);
+            zs[j * kRows + row] = y;
             ldacc += ld;
           }
         }
       }
 
-      // ---- LULinear on the thread's own row: z <- L (U z) + b, in place ----
-      if (__ldg(v.LT + SBI_L_HAS_LU)) {
-        const float* U = sm + L.lum + l * L.lu_stride;
+      // ---- LULinear on the row (half 1: it has one spline feature less, and it also writes the
+      //      next layer's identity columns):  z <- L (U z) + b, in place ----
+      group_sync();      // both halves' spline outputs are in zs
+      if (half == 1 && __ldg(v.LT + SBI_L_HAS_LU)) {
+        const float* U = sm + L.lum;
         const float* Lw = U + D * D;
         const float* bias = Lw + D * D;
         for (int i = 0; i < D; ++i) {
           float a = 0.f;
-          for (int j = i; j < D; ++j) a = fmaf(U[i * D + j], zs[j * kRows + tid], a);
-          zs[i * kRows + tid] = a;
+          for (int j = i; j < D; ++j) a = fmaf(U[i * D + j], zs[j * kRows + row], a);
+          zs[i * kRows + row] = a;
         }
         for (int i = D - 1; i >= 0; --i) {
-          float a = zs[i * kRows + tid];
-          for (int j = 0; j < i; ++j) a = fmaf(Lw[i * D + j], zs[j * kRows + tid], a);
-          zs[i * kRows + tid] = a + bias[i];
+          float a = zs[i * kRows + row];
+          for (int j = 0; j < i; ++j) a = fmaf(Lw[i * D + j], zs[j * kRows + row], a);
+          zs[i * kRows + row] = a + bias[i];
         }
       }
     }
 
     // ---- base density ----
-    if (row0 + tid < rows.R) {
+    if (half == 0) lds[row] = ldacc;
+    group_sync();
+    if (half == 1 && row0 + row < rows.R) {
       float ss = 0.f;
-      for (int d = 0; d < D; ++d) ss = fmaf(zs[d * kRows + tid], zs[d * kRows + tid], ss);
-      logp[row0 + tid] = -0.5f * ss + ldacc + ld_const;
+      for (int d = 0; d < D; ++d) ss = fmaf(zs[d * kRows + row], zs[d * kRows + row], ss);
+      logp[row0 + row] = -0.5f * ss + (lds[row] + ldacc) + ld_const;
       if (noise != nullptr)
-        for (int d = 0; d < D; ++d) noise[(row0 + tid) * D + d] = zs[d * kRows + tid];
+        for (int d = 0; d < D; ++d) noise[(row0 + row) * D + d] = zs[d * kRows + row];
     }
     group_sync();   // rows of the next tile are written cooperatively
   }
 #undef SBI_TC_ROUND
-#undef SBI_TC_ACOL
 
   fence_before();
   group_sync();
@@ -591,13 +713,10 @@ static int tc_num_sms() {
   return n;
 }
 
-// slots of the weight ring: as many as fit next to a second CTA on the SM (2..4)
+// the two-slot weight ring has to fit next to a second CTA on the SM
 static int tc_plan_slots(const sbi_nsf_model* m, const sbi_nsf_tc* tc) {
-  for (int nslot = 4; nslot >= 2; --nslot) {
-    const tc::TcSmem L = tc::tc_smem_layout(*m, tc->stage_cap, nslot);
-    if (L.total_bytes <= 112 * 1024) return nslot;
-  }
-  return 0;
+  const tc::TcSmem L = tc::tc_smem_layout(*m, tc->stage_cap, tc::kSlots);
+  return L.total_bytes <= 112 * 1024 ? tc::kSlots : 0;
 }
 
 extern "C" int sbi_b200_nsf_tc_supported(const sbi_nsf_model* m, const sbi_nsf_tc* tc) {
@@ -637,6 +756,6 @@ extern "C" int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc*
   }
   const int64_t ntiles = (rows->R + tc::kRows - 1) / tc::kRows;
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)tc_num_sms() * 2);
-  k<<<grid, tc::kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *tc, *rows, d_logp, d_noise, nslot);
+  k<<<grid, tc::kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *tc, *rows, d_logp, d_noise);
   return (int)cudaGetLastError();
 }
