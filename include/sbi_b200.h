@@ -145,7 +145,8 @@ int sbi_b200_adam_clip_step_norm(float* d_params, const float* d_grad, float* d_
  *   d_tab   T * SBI_NSF_TC_STRIDE ints; per layer: [0] number of stages, [1] round8(n_id),
  *           then 4 ints per stage s at 4+4s: float offset into d_tcw, floats (hi+lo), N of the
  *           main block, aux (final-layer passes: first feature | n_features << 16).
- *           Stage order: initial layer, per block ([W1 | Wc], W2), final-layer passes.
+ *           Stage order: initial layer, per block (Wc, W1, W2), final-layer passes of <= 2
+ *           spline features (32 rows per feature).
  * Supported when H == 50, H + C <= 64, n_id <= 48, 3*KB-1 <= 32 and the shared-memory plan fits
  * (sbi_b200_nsf_tc_supported); callers use sbi_b200_nsf_logprob otherwise. */
 #define SBI_NSF_TC_STRIDE 192

@@ -219,6 +219,113 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const 
                  : "memory");
 }
 
+
+// ---- cadence of the tensor pipe for the shapes the NSF kernel uses ------------------------------
+// var 0: one accumulation chain (same D)          var 1: two chains alternating (D0 / D1)
+// var 2: A from shared memory (SS), one chain     var 3: four chains
+__device__ __forceinline__ void tc_mma_tf32_ss(uint32_t d, uint64_t adesc, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__global__ void __launch_bounds__(128) cadence(long long* __restrict__ cyc, int N, int var, int nmma) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tbase_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* sf = reinterpret_cast<float*>(smem);
+  for (int i = tid; i < (256 * 64 + 128 * 64); i += 128) sf[i] = 0.001f * (float)(i % 97);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tbase_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tbase_s;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  {
+    float v[8];
+    for (int i = 0; i < 8; ++i) v[i] = 0.01f * (float)(tid + i);
+    for (int c = 0; c < 64; c += 8) tc_st8(tbase + lane_base + c, v);
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  const uint32_t idesc = make_idesc(128, N);
+  const uint32_t slab = (uint32_t)N * 16u;
+  const uint32_t bsm = smem_u32(smem);
+  const uint32_t asm_ = bsm + 256 * 64 * 4;       // A tile in smem for the SS variant: [K/4][128][4]
+  long long t0 = 0, t1 = 0;
+  if (var >= 4) {
+    // tight issue: descriptors precomputed, K-steps unrolled; var 5: whole warp converged + elect
+    uint64_t bd[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bd[k] = make_bdesc(bsm + (uint32_t)(2 * k) * slab, slab, 128u);
+    const uint32_t d = tbase + 64, a = tbase;
+    if (var == 4) {
+      if (tid == 0) {
+        tc_fence_after();
+        t0 = clock64();
+        for (int i = 0; i < nmma; i += 8) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) tc_mma_tf32_ts(d, a + 8 * k, bd[k], idesc, 1u);
+        }
+        tc_commit(&bar);
+      }
+    } else if (warp == 0) {
+      tc_fence_after();
+      uint32_t leader;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+      t0 = clock64();
+      for (int i = 0; i < nmma; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (leader) tc_mma_tf32_ts(d, a + 8 * k, bd[k], idesc, 1u);
+      }
+      if (leader) tc_commit(&bar);
+    }
+  } else
+  if (tid == 0) {
+    tc_fence_after();
+    t0 = clock64();
+    for (int i = 0; i < nmma; ++i) {
+      const int k = (i % 8);
+      const uint64_t bd = make_bdesc(bsm + (uint32_t)(2 * k) * slab, slab, 128u);
+      uint32_t d = tbase + 64;
+      if (var == 1) d = tbase + 64 + (i & 1) * 192;
+      if (var == 3) d = tbase + 64 + (i & 3) * 96;
+      if (var == 2) {
+        const uint64_t ad = make_bdesc(asm_ + (uint32_t)(2 * k) * 2048u, 2048u, 128u);
+        tc_mma_tf32_ss(d, ad, bd, idesc, i >= 4);
+      } else {
+        tc_mma_tf32_ts(d, tbase + 8 * k, bd, idesc, i >= 4);
+      }
+    }
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  t1 = clock64();
+  if (tid == 0) cyc[0] = (t1 - t0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512)
+                 : "memory");
+}
+
 static float tf32_trunc(float x) {
   uint32_t u;
   memcpy(&u, &x, 4);
@@ -280,5 +387,16 @@ int main() {
                  "max|ref|=%.2f  cycles/layer=%lld\n",
                  mode, N, K, swap, rterr, err, err1, ref_max, cyc);
         }
+  CK(cudaFuncSetAttribute(cadence, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  for (int var : {0, 4, 5})
+    for (int N : {64, 128, 256}) {
+      for (int nm : {48, 480}) {
+        cadence<<<1, 128, (256 * 64 + 128 * 64) * 4>>>(dC, N, var, nm);
+        CK(cudaDeviceSynchronize());
+        long long cyc;
+        CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+        printf("cadence var=%d N=%3d nmma=%3d: %lld cycles  (%.1f / MMA)\n", var, N, nm, cyc, (double)cyc / nm);
+      }
+    }
   return 0;
 }

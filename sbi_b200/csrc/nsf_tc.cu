@@ -37,10 +37,9 @@ namespace tc {
 constexpr int kRows = 128;        // rows per tile
 constexpr int kRowThreads = 256;  // two threads per row (column halves)
 constexpr int kThreads = 256;     // 8 row warps; thread 0 also issues the MMAs and the TMA copies
-constexpr int kSlots = 2;         // weight ring: the stage in use + the prefetched next one
+constexpr int kSlots = 3;         // weight ring: up to two stages in use + one prefetched
 constexpr int kCols = 256;        // TMEM columns per CTA
 constexpr int cAhi = 0, cAlo = 64, cD = 128, cG = 192;
-constexpr int kMaxPassFeat = 3;   // spline features per final-layer pass (N = 96)
 
 // ---- tcgen05 wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ void fence_before() {
@@ -103,6 +102,21 @@ __device__ __forceinline__ void ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void st4(uint32_t taddr, const float (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3]))
+               : "memory");
+}
+__device__ __forceinline__ void ld4(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 template <int NCHUNK>
 __device__ __forceinline__ void ld_cols(uint32_t taddr, float* v) {
 #pragma unroll
@@ -123,6 +137,13 @@ __device__ __forceinline__ void store_a8(uint32_t tlane, int col, const float (&
   st8(tlane + cAhi + col, hi);
   st8(tlane + cAlo + col, lo);
 }
+__device__ __forceinline__ void store_a4(uint32_t tlane, int col, const float (&v)[4]) {
+  float hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_tf32(v[i], hi[i], lo[i]);
+  st4(tlane + cAhi + col, hi);
+  st4(tlane + cAlo + col, lo);
+}
 __device__ __forceinline__ void group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---- shared memory plan -------------------------------------------------------------------------
@@ -142,7 +163,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(const sbi_nsf_model& m, int sta
   fl = (fl + 31) & ~31;
   L.ring = fl; fl += nslot * stage_cap;
   L.bar_bytes = fl * 4;
-  L.total_bytes = L.bar_bytes + (nslot + 1) * 8 + 16;
+  L.total_bytes = L.bar_bytes + (nslot + 2) * 8 + 16;
   return L;
 }
 
@@ -166,46 +187,59 @@ __global__ void nsf_tc_pack_kernel(const float* __restrict__ params, const int32
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-// Thread 0 of the CTA drives the tensor core and the weight stream.  Stage s lives in ring slot
-// s % 2.  When the MMAs of stage s have been issued, the TMA copy of stage s+1 goes into the other
-// slot: that slot held stage s-1, whose MMAs completed before every thread left round s-1.
+// Warp 0 of the CTA drives the tensor core and the weight stream: the whole warp runs this code
+// converged (so the descriptor arithmetic stays in the uniform datapath and the MMAs go out at
+// the tensor pipe's own cadence; a single divergent thread issues 2x slower, see
+// profiles/micro/umma_probe.cu), one elected lane executes the tcgen05 / TMA instructions.
+// Stage k lives in ring slot
+// k % kSlots.  A stage is fetched (TMA bulk copy, completion on full[slot]) as soon as the stage
+// that used its slot kSlots stages earlier is known to be complete, which warp 0 learns each
+// time it passes an accumulator barrier (a tcgen05.commit covers every MMA issued before it).
 struct Issuer {
   uint32_t tbase;       // TMEM base (lane 0, column 0)
+  bool leader;          // the elected lane
   float* ring;
-  uint64_t *full, *dbar;
+  uint64_t *full, *bars;
   const float* tcw;
   const int32_t* tab;   // stage table (all layers)
   int cap, T;
-  uint32_t it;          // stage counter
+  uint32_t it;          // stages issued
+  uint32_t done;        // stages known complete
+  uint32_t fetched;     // stages fetched
+  uint32_t cov0, cov1;  // stages covered by the last commit on each accumulator barrier
   uint32_t sbase, lo_off;   // current stage: shared address of the hi half, byte offset of lo half
-  // next stage to fetch
-  int64_t f_tile, ntiles, tile_step;
+  int64_t f_tile, ntiles, tile_step;   // next stage to fetch
   int f_l, f_s;
 
-  __device__ __forceinline__ void fetch_next() {
-    if (f_tile >= ntiles) return;
-    const int32_t* t = tab + f_l * SBI_NSF_TC_STRIDE;
-    const int off = __ldg(t + 4 + 4 * f_s), nfl = __ldg(t + 5 + 4 * f_s);
-    const uint32_t slot = fetched & 1u;
-    mbar_arrive_expect_tx(&full[slot], (uint32_t)nfl * 4u);
-    bulk_g2s(ring + (size_t)slot * cap, tcw + off, (uint32_t)nfl * 4u, &full[slot]);
-    ++fetched;
-    if (++f_s == __ldg(t)) {
-      f_s = 0;
-      if (++f_l == T) { f_l = 0; f_tile += tile_step; }
+  __device__ __forceinline__ void pump() {
+    while (fetched < done + kSlots && f_tile < ntiles) {
+      const int32_t* t = tab + f_l * SBI_NSF_TC_STRIDE;
+      const int off = __ldg(t + 4 + 4 * f_s), nfl = __ldg(t + 5 + 4 * f_s);
+      const uint32_t slot = fetched % kSlots;
+      if (leader) {
+        mbar_arrive_expect_tx(&full[slot], (uint32_t)nfl * 4u);
+        bulk_g2s(ring + (size_t)slot * cap, tcw + off, (uint32_t)nfl * 4u, &full[slot]);
+      }
+      ++fetched;
+      if (++f_s == __ldg(t)) {
+        f_s = 0;
+        if (++f_l == T) { f_l = 0; f_tile += tile_step; }
+      }
     }
   }
-  uint32_t fetched;
-
   __device__ __forceinline__ void begin(int stage_floats) {
-    const uint32_t s = it & 1u;
-    mbar_wait(&full[s], (it >> 1) & 1u);
-    sbase = smem_u32(ring + (size_t)s * cap);
-    lo_off = (uint32_t)stage_floats * 2u;     // (floats / 2) * 4 bytes
+    const uint32_t s = it % kSlots;
+    mbar_wait(&full[s], (it / kSlots) & 1u);
+    // (the shuffles only tell the compiler that these values are warp-uniform)
+    sbase = __shfl_sync(0xffffffffu, smem_u32(ring + (size_t)s * cap), 0);
+    lo_off = __shfl_sync(0xffffffffu, (uint32_t)stage_floats * 2u, 0);   // (floats / 2) * 4 bytes
     fence_after();
   }
   // one operand block of N rows starting `blk_floats` into the half: nk K-steps, A columns from a0
   __device__ __forceinline__ void block(int dcol, int a0, int nk, int blk_floats, int N, uint32_t& acc) {
+    N = __shfl_sync(0xffffffffu, N, 0);
+    nk = __shfl_sync(0xffffffffu, nk, 0);
+    blk_floats = __shfl_sync(0xffffffffu, blk_floats, 0);
     const uint32_t idesc = make_idesc(N);
     const uint32_t slab = (uint32_t)N * 16u;
     const uint32_t bh = sbase + (uint32_t)blk_floats * 4u;
@@ -214,17 +248,28 @@ struct Issuer {
     const uint64_t dstep = (uint64_t)((2u * slab) >> 4);    // start-address field advance per K-step
     uint32_t ah = tbase + cAhi + a0, al = tbase + cAlo + a0;
     const uint32_t d = tbase + dcol;
+#pragma unroll 8
     for (int kk = 0; kk < nk; ++kk) {
-      mma_tf32(d, ah, dh, idesc, acc);
-      mma_tf32(d, al, dh, idesc, 1u);
-      mma_tf32(d, ah, dl, idesc, 1u);
+      if (leader) {
+        mma_tf32(d, ah, dh, idesc, acc);
+        mma_tf32(d, al, dh, idesc, 1u);
+        mma_tf32(d, ah, dl, idesc, 1u);
+      }
       acc = 1u;
       dh += dstep; dl += dstep; ah += 8; al += 8;
     }
   }
-  __device__ __forceinline__ void end() {
-    commit(dbar);                 // accumulators ready (and the stage's weights fully read)
-    fetch_next();
+  // close the stage: its accumulators are signalled on accumulator barrier `b`
+  __device__ __forceinline__ void end(int b) {
+    if (leader) commit(&bars[b]);
+    ++it;
+    if (b == 0) cov0 = it; else cov1 = it;
+  }
+  // warp 0 has just passed accumulator barrier b
+  __device__ __forceinline__ void passed(int b) {
+    const uint32_t c = (b == 0) ? cov0 : cov1;
+    if (c > done) done = c;
+    pump();
   }
 };
 
@@ -294,9 +339,16 @@ __device__ __forceinline__ void rqs_forward_fast(const float (&p)[32], const Rqs
   ld = __logf(dnum) - 2.f * __logf(den);
 }
 
-// Two threads share a row: `half` 0 owns hidden chunks 0..3 (columns 0..31), `half` 1 owns
-// chunks 4.. (columns 32..HP8-1 and the context tail).  All epilogues are column-wise, so the
+// Two threads share a row: `half` 0 owns hidden columns [0, HP8/2), `half` 1 owns [HP8/2, HP8)
+// (which end in the first context columns).  All epilogues are column-wise, so the
 // halves never exchange activations; the spline features of a layer alternate between them.
+//
+// Per coupling layer the tensor core sees these stages (accumulator barrier in brackets):
+//   initial layer -> D [0]
+//   per block:  W_c ctx -> G [1],  W_1 relu(h) -> D [0]   (issued together: the gate's sigmoid is
+//               evaluated while W_1 runs),  W_2 relu(.) -> D [0]
+//   final layer in passes of <= 2 spline features, pass p -> P_(p&1) [p&1]; two passes are in
+//               flight, so the spline of pass p runs while pass p+1 is computed.
 template <int H, int KB>
 __global__ void __launch_bounds__(kThreads, 2)
 nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ sbi_nsf_tc tc,
@@ -305,13 +357,15 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
   constexpr int HP8 = (H + 7) & ~7;
   constexpr int NCH = HP8 / 8;      // K-steps / 8-column chunks of the hidden operand
   constexpr int KC0 = H / 8;        // first chunk that holds context columns
-  constexpr int NS = 4;             // chunk slots per thread
-  static_assert(NCH <= 2 * NS, "hidden width");
+  constexpr int NC = HP8 / 2;       // hidden columns per thread (half 0: [0,NC), half 1: [NC,HP8))
+  constexpr int NG = NC / 4;        // groups of 4 columns
+  constexpr int QC = H - NC;        // first column offset of half 1 that is a context column
+  static_assert(HP8 % 8 == 0 && NC % 4 == 0 && H > NC && H <= 64, "hidden width");
   extern __shared__ __align__(128) float sm[];
   const TcSmem L = tc_smem_layout(m, tc.stage_cap, kSlots);
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(sm) + L.bar_bytes);
-  uint64_t* dbar = full + kSlots;
-  uint32_t* tbase_s = reinterpret_cast<uint32_t*>(dbar + 1);
+  uint64_t* bars = full + kSlots;             // two accumulator barriers
+  uint32_t* tbase_s = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int C = m.C;
   const int nkc = (H + C + 7) / 8 - KC0;     // K-steps that cover the context columns
@@ -319,7 +373,8 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
 
   if (tid == 0) {
     for (int s = 0; s < kSlots; ++s) mbar_init(&full[s], 1);
-    mbar_init(dbar, 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -334,7 +389,6 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
   fence_after();
   const uint32_t tbase = *tbase_s;
 
-  // ---------------- row warps ------------------------------------------------------------------
   const float* __restrict__ P = m.d_params;
   float* zs = sm + L.zs;
   float* ctx_s = sm + L.ctx;
@@ -343,9 +397,26 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
   const int half = warp >> 2;                          // which column half of the row
   const int row = ((warp & 3) << 5) | (tid & 31);      // row of the tile = TMEM lane
   const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+  const int cbase = half * NC;                          // first hidden column of this thread
+  const uint32_t tmine = tlane + cbase;
   RqsConst rc = rqs_const(m);
-  rc.K = KB;   // compile-time bin count keeps the spline parameters in registers
+  rc.K = KB;
   const int D = m.D;
+
+  Issuer iss;
+  iss.tbase = __shfl_sync(0xffffffffu, tbase, 0); iss.ring = sm + L.ring; iss.full = full; iss.bars = bars;
+  iss.tcw = tc.d_tcw; iss.tab = tc.d_tab; iss.cap = tc.stage_cap; iss.T = m.T;
+  iss.it = 0; iss.done = 0; iss.fetched = 0; iss.cov0 = iss.cov1 = 0;
+  iss.sbase = 0; iss.lo_off = 0;
+  iss.f_tile = blockIdx.x; iss.ntiles = ntiles; iss.tile_step = gridDim.x; iss.f_l = 0; iss.f_s = 0;
+  {
+    uint32_t el = 0;
+    if (warp == 0)
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+    iss.leader = el != 0;
+  }
+  if (warp == 0) iss.pump();     // first kSlots stages
+  uint32_t bpar = 0u;          // phase parity of the two accumulator barriers (bit b)
 
   // all biases of the conditioners, once per CTA (zero beyond the real widths):
   //   per layer [b0 64 | per block: b1 64, b2 64, bc 64 | bf TRmax*32]
@@ -382,37 +453,44 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
     ld_const = tot + m.ld_zscore - 0.5f * (float)D * 1.8378770664093453f;
   }
 
-  Issuer iss;
-  iss.tbase = tbase; iss.ring = sm + L.ring; iss.full = full; iss.dbar = dbar;
-  iss.tcw = tc.d_tcw; iss.tab = tc.d_tab; iss.cap = tc.stage_cap; iss.T = m.T;
-  iss.it = 0; iss.sbase = 0; iss.lo_off = 0;
-  iss.f_tile = blockIdx.x; iss.ntiles = ntiles; iss.tile_step = gridDim.x; iss.f_l = 0; iss.f_s = 0;
-  iss.fetched = 0;
-  if (tid == 0) iss.fetch_next();     // first stage of the first tile
-  uint32_t dpar = 0;
-
-  // hand the operands over to the tensor core, run one stage, wait for its accumulators
-#define SBI_TC_ROUND(STAGE_FLOATS, ISSUE_BODY)  \
-  do {                                          \
-    wait_st();                                  \
-    fence_before();                             \
-    group_sync();                               \
-    if (tid == 0) {                             \
-      iss.begin(STAGE_FLOATS);                  \
-      ISSUE_BODY;                               \
-      iss.end();                                \
-    }                                           \
-    ++iss.it;                                   \
-    mbar_wait(dbar, dpar);                      \
-    dpar ^= 1u;                                 \
-    __syncwarp();                               \
-    fence_after();                              \
-  } while (0)
-
+  // operands written / accumulators read: hand TMEM over to the issuing thread
+  auto hand_over = [&]() {
+    wait_st();
+    fence_before();
+    group_sync();
+  };
+  // wait for the accumulators signalled on barrier b
+  auto wait_acc = [&](int b) {
+    mbar_wait(&bars[b], (bpar >> b) & 1u);
+    bpar ^= 1u << b;
+    __syncwarp();
+    fence_after();
+    if (warp == 0) iss.passed(b);
+  };
   // A-operand column j of a hidden layer: activation (j < H), context (H <= j < H+C), zero
   auto acol = [&](int j, float act) -> float {
     const int c = j - H;
     return j < H ? act : ((c < C) ? ctx_s[c * kRows + row] : 0.f);
+  };
+
+  // this thread's NC columns of a hidden-layer A operand; half 1's last columns are context
+  auto write_a = [&](const float (&act)[NC]) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      float a[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = 4 * g + i;
+        if (q < QC) a[i] = act[q];
+        else a[i] = half ? ((q - QC < C) ? ctx_s[(q - QC) * kRows + row] : 0.f) : act[q];
+      }
+      store_a4(tlane, cbase + 4 * g, a);
+    }
+  };
+  auto read_acc = [&](int region, float (&d)[NC]) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) ld4(tmine + region + 4 * g, d + 4 * g);
+    wait_ld();
   };
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -445,7 +523,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
       group_sync();
     }
     // context tail columns [HP8, 64) never change within a tile
-    if (half == 1) {
+    if (half == 0) {
 #pragma unroll
       for (int c = NCH; c < 8; ++c) {
         float v[8];
@@ -462,7 +540,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
       const float* bl = bias_s + l * L.bias_stride;
       const int kid8 = __ldg(tab + 1);
       int stage = 0;
-      float h[NS][8];
+      float h[NC];
 
       // ---- initial layer: A = [identity features | 0 ... | context] ----
       // (half 1 ran the previous layer's LU on this row, so it also writes the identity columns)
@@ -485,17 +563,17 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           store_a8(tlane, 8 * c, a);
         }
       }
-      {
-        const int nfl = __ldg(tab + 5 + 4 * stage);
-        SBI_TC_ROUND(nfl, {
-          uint32_t acc = 0u;
-          iss.block(cD, 0, kid8 / 8, 0, 64, acc);
-          iss.block(cD, 8 * KC0, nkc, 64 * kid8, 64, acc);
-        });
-        ++stage;
+      hand_over();
+      if (warp == 0) {
+        iss.begin(__ldg(tab + 5 + 4 * stage));
+        uint32_t acc = 0u;
+        iss.block(cD, 0, kid8 / 8, 0, 64, acc);
+        iss.block(cD, 8 * KC0, nkc, 64 * kid8, 64, acc);
+        iss.end(0);
       }
+      ++stage;
       // dense LU factors of this layer: [U D*D | L D*D | bias D | diag D] (used after the spline;
-      // the previous layer's were last read before the barrier of the round above)
+      // the previous layer's were last read before the barrier above)
       if (__ldg(v.LT + SBI_L_HAS_LU)) {
         const float* lo = P + __ldg(v.LT + SBI_L_LU_LOWER);
         const float* up = P + __ldg(v.LT + SBI_L_LU_UPPER);
@@ -517,136 +595,117 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           }
         }
       }
+      wait_acc(0);
+      const float* blh = bl + cbase;
       {
-        float d[NS][8];
+        float d[NC];
+        read_acc(cD, d);
 #pragma unroll
-        for (int s = 0; s < NS; ++s)
-          if (half * NS + s < NCH) ld8(tlane + cD + 8 * (half * NS + s), d[s]);
-        wait_ld();
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int j = 8 * (half * NS + s) + i;
-            h[s][i] = (j < H) ? d[s][i] + bl[j & 63] : 0.f;
-          }
+        for (int q = 0; q < NC; ++q) h[q] = d[q] + blh[q];     // columns >= H: zero weights + zero bias
       }
 
       // ---- residual blocks ----
       for (int b = 0; b < m.NB; ++b) {
-        const float* b1 = bl + 64 + b * 192;
+        const float* b1 = blh + 64 + b * 192;
         const float* b2 = b1 + 64;
         const float* bc = b1 + 128;
         // A = [relu(h) | ctx]
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          const int c = half * NS + s;
-          if (c < NCH) {
-            float a[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = acol(8 * c + i, relu_f(h[s][i]));
-            store_a8(tlane, 8 * c, a);
-          }
-        }
         {
-          const int nfl = __ldg(tab + 5 + 4 * stage);
-          SBI_TC_ROUND(nfl, {
-            uint32_t acc = 0u;
-            uint32_t accg = 0u;
-            iss.block(cD, 0, NCH, 0, 64, acc);
-            iss.block(cG, 8 * KC0, nkc, 64 * HP8, 64, accg);
-          });
-          ++stage;
+          float a[NC];
+#pragma unroll
+          for (int q = 0; q < NC; ++q) a[q] = relu_f(h[q]);
+          write_a(a);
         }
-        {
-          float d[NS][8];
-#pragma unroll
-          for (int s = 0; s < NS; ++s)
-            if (half * NS + s < NCH) ld8(tlane + cD + 8 * (half * NS + s), d[s]);
-          wait_ld();
-#pragma unroll
-          for (int s = 0; s < NS; ++s) {
-            const int c = half * NS + s;
-            if (c < NCH) {
-              float a[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int j = 8 * c + i;
-                a[i] = acol(j, relu_f(d[s][i] + b1[j & 63]));
-              }
-              store_a8(tlane, 8 * c, a);
-            }
-          }
+        hand_over();
+        if (warp == 0) {
+          uint32_t accg = 0u;
+          iss.begin(__ldg(tab + 5 + 4 * stage));
+          iss.block(cG, 8 * KC0, nkc, 0, 64, accg);
+          iss.end(1);
+          uint32_t acc = 0u;
+          iss.begin(__ldg(tab + 5 + 4 * (stage + 1)));
+          iss.block(cD, 0, NCH, 0, 64, acc);
+          iss.end(0);
         }
+        stage += 2;
+        // gate = sigmoid(Wc ctx + bc) while W1 relu(h) is on the tensor core
+        float sg[NC];
+        wait_acc(1);
         {
-          const int nfl = __ldg(tab + 5 + 4 * stage);
-          SBI_TC_ROUND(nfl, {
-            uint32_t acc = 0u;
-            iss.block(cD, 0, NCH, 0, 64, acc);
-          });
-          ++stage;
+          float g[NC];
+          read_acc(cG, g);
+#pragma unroll
+          for (int q = 0; q < NC; ++q) sg[q] = sigmoid_fast(g[q] + bc[q]);
         }
+        wait_acc(0);
         {
-          // h += (W2 a + b2) * sigmoid(Wc ctx + bc)
-          float d[NS][8], g[NS][8];
+          float d[NC];
+          read_acc(cD, d);
 #pragma unroll
-          for (int s = 0; s < NS; ++s)
-            if (half * NS + s < NCH) {
-              ld8(tlane + cD + 8 * (half * NS + s), d[s]);
-              ld8(tlane + cG + 8 * (half * NS + s), g[s]);
-            }
-          wait_ld();
+          for (int q = 0; q < NC; ++q) d[q] = relu_f(d[q] + b1[q]);
+          write_a(d);
+        }
+        hand_over();
+        if (warp == 0) {
+          uint32_t acc = 0u;
+          iss.begin(__ldg(tab + 5 + 4 * stage));
+          iss.block(cD, 0, NCH, 0, 64, acc);
+          iss.end(0);
+        }
+        ++stage;
+        wait_acc(0);
+        {
+          // h += (W2 a + b2) * gate
+          float d[NC];
+          read_acc(cD, d);
 #pragma unroll
-          for (int s = 0; s < NS; ++s)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = 8 * (half * NS + s) + i;
-              if (j < H) {
-                const float t = d[s][i] + b2[j];
-                const float sg = sigmoid_fast(g[s][i] + bc[j]);
-                h[s][i] = h[s][i] + t * sg;
-              }
-            }
+          for (int q = 0; q < NC; ++q) h[q] = fmaf(d[q] + b2[q], sg[q], h[q]);
         }
       }
 
       // ---- final layer passes + spline on the transformed features ----
       {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          const int c = half * NS + s;
-          if (c < NCH) {
-            float a[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = acol(8 * c + i, h[s][i]);
-            store_a8(tlane, 8 * c, a);
-          }
-        }
+        write_a(h);
         const float* bf = bl + 64 + m.NB * 192;
         const int ns = __ldg(tab);
-        for (; stage < ns; ++stage) {
-          const int nfl = __ldg(tab + 5 + 4 * stage);
-          const int N = __ldg(tab + 6 + 4 * stage);
-          const int aux = __ldg(tab + 7 + 4 * stage);
-          const int f0 = aux & 0xffff, nf = aux >> 16;
-          SBI_TC_ROUND(nfl, {
+        const int np = ns - stage;            // passes
+        hand_over();
+        if (warp == 0) {
+          for (int p = 0; p < 2 && p < np; ++p) {
             uint32_t acc = 0u;
-            iss.block(cD, 0, NCH, 0, N, acc);
-          });
+            iss.begin(__ldg(tab + 5 + 4 * (stage + p)));
+            iss.block(cD + 64 * p, 0, NCH, 0, __ldg(tab + 6 + 4 * (stage + p)), acc);
+            iss.end(p);
+          }
+        }
+        for (int p = 0; p < np; ++p) {
+          const int aux = __ldg(tab + 7 + 4 * (stage + p));
+          const int f0 = aux & 0xffff, nf = aux >> 16;
+          wait_acc(p & 1);
           for (int f = 0; f < nf; ++f) {
             if (((f0 + f) & 1) != half) continue;     // warp-uniform: features alternate between halves
-            float p[32];
-            ld_cols<4>(tlane + cD + 32 * f, p);
+            float q[32];
+            ld_cols<4>(tlane + cD + 64 * (p & 1) + 32 * f, q);
             wait_ld();
             const float* bff = bf + (f0 + f) * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) p[i] = (i < 3 * KB - 1) ? p[i] + bff[i] : 0.f;
+            for (int i = 0; i < 32; ++i) q[i] = (i < 3 * KB - 1) ? q[i] + bff[i] : 0.f;
             const int j = __ldg(v.trf + f0 + f);
             const float x = zs[j * kRows + row];
             float y, ld;
-            rqs_forward_fast<KB>(p, rc, x, y, ld);
+            rqs_forward_fast<KB>(q, rc, x, y, ld);
             zs[j * kRows + row] = y;
             ldacc += ld;
+          }
+          if (p + 2 < np) {
+            // region p&1 has been read by everyone: pass p+2 may overwrite it
+            hand_over();
+            if (warp == 0) {
+              uint32_t acc = 0u;
+              iss.begin(__ldg(tab + 5 + 4 * (stage + p + 2)));
+              iss.block(cD + 64 * (p & 1), 0, NCH, 0, __ldg(tab + 6 + 4 * (stage + p + 2)), acc);
+              iss.end(p & 1);
+            }
           }
         }
       }
@@ -683,7 +742,6 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
     }
     group_sync();   // rows of the next tile are written cooperatively
   }
-#undef SBI_TC_ROUND
 
   fence_before();
   group_sync();
@@ -713,7 +771,7 @@ static int tc_num_sms() {
   return n;
 }
 
-// the two-slot weight ring has to fit next to a second CTA on the SM
+// the weight ring has to fit next to a second CTA on the SM
 static int tc_plan_slots(const sbi_nsf_model* m, const sbi_nsf_tc* tc) {
   const tc::TcSmem L = tc::tc_smem_layout(*m, tc->stage_cap, tc::kSlots);
   return L.total_bytes <= 112 * 1024 ? tc::kSlots : 0;

@@ -270,12 +270,13 @@ class NsfLayout(_LayoutOps):
             for b in range(NB):
                 t = L.L_BLK0 + 6 * b
                 w1, w2, wc = int(lt[t + 0]), int(lt[t + 2]), int(lt[t + 4])
-                stages.append((np.concatenate([hidden_block(w1, 64, ident), ctx_block(wc, Cp)]), 64, 0))
+                stages.append((ctx_block(wc, Cp), 64, 0))
+                stages.append((hidden_block(w1, 64, ident), 64, 0))
                 stages.append((hidden_block(w2, 64, ident), 64, 0))
             wf = int(lt[L.L_WF])
             f0 = 0
             while f0 < n_tr:
-                nf = min(3, n_tr - f0)
+                nf = min(2, n_tr - f0)
 
                 def rowmap(n, f0=f0, nf=nf):
                     f, i = n // 32, n % 32
