@@ -123,10 +123,11 @@ __device__ __forceinline__ void ld_cols(uint32_t taddr, float* v) {
   for (int c = 0; c < NCHUNK; ++c) ld8(taddr + 8 * c, v + 8 * c);
 }
 
+// hi = x rounded to tf32 (10 explicit mantissa bits, round half away in the integer domain),
+// lo = x - hi (exact in fp32).  cvt.rna.tf32.f32 computes the same hi but expands to a longer
+// sequence on sm_100a.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
   lo = x - hi;
 }
 // split 8 values and put them into A_hi / A_lo columns [col, col+8) of the thread's lane
@@ -187,17 +188,20 @@ __global__ void nsf_tc_pack_kernel(const float* __restrict__ params, const int32
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-// Warp 0 of the CTA drives the tensor core and the weight stream: the whole warp runs this code
+// The warps of the CTA take turns driving the tensor core and the weight stream (stage k is
+// issued by warp k % 8, so the issue work is spread evenly): the whole warp runs this code
 // converged (so the descriptor arithmetic stays in the uniform datapath and the MMAs go out at
 // the tensor pipe's own cadence; a single divergent thread issues 2x slower, see
 // profiles/micro/umma_probe.cu), one elected lane executes the tcgen05 / TMA instructions.
 // Stage k lives in ring slot
 // k % kSlots.  A stage is fetched (TMA bulk copy, completion on full[slot]) as soon as the stage
-// that used its slot kSlots stages earlier is known to be complete, which warp 0 learns each
+// that used its slot kSlots stages earlier is known to be complete, which every warp learns each
 // time it passes an accumulator barrier (a tcgen05.commit covers every MMA issued before it).
 struct Issuer {
   uint32_t tbase;       // TMEM base (lane 0, column 0)
-  bool leader;          // the elected lane
+  bool leader;          // the elected lane of this warp
+  int warp;             // this warp; stage k is issued by warp k % 8, fetched by warp (k+4) % 8
+  bool mine;            // this warp issues the current stage
   float* ring;
   uint64_t *full, *bars;
   const float* tcw;
@@ -216,7 +220,7 @@ struct Issuer {
       const int32_t* t = tab + f_l * SBI_NSF_TC_STRIDE;
       const int off = __ldg(t + 4 + 4 * f_s), nfl = __ldg(t + 5 + 4 * f_s);
       const uint32_t slot = fetched % kSlots;
-      if (leader) {
+      if (leader && (int)((fetched + 4u) & 7u) == warp) {
         mbar_arrive_expect_tx(&full[slot], (uint32_t)nfl * 4u);
         bulk_g2s(ring + (size_t)slot * cap, tcw + off, (uint32_t)nfl * 4u, &full[slot]);
       }
@@ -228,6 +232,8 @@ struct Issuer {
     }
   }
   __device__ __forceinline__ void begin(int stage_floats) {
+    mine = (int)(it & 7u) == warp;
+    if (!mine) return;
     const uint32_t s = it % kSlots;
     mbar_wait(&full[s], (it / kSlots) & 1u);
     // (the shuffles only tell the compiler that these values are warp-uniform)
@@ -237,6 +243,7 @@ struct Issuer {
   }
   // one operand block of N rows starting `blk_floats` into the half: nk K-steps, A columns from a0
   __device__ __forceinline__ void block(int dcol, int a0, int nk, int blk_floats, int N, uint32_t& acc) {
+    if (!mine) return;
     N = __shfl_sync(0xffffffffu, N, 0);
     nk = __shfl_sync(0xffffffffu, nk, 0);
     blk_floats = __shfl_sync(0xffffffffu, blk_floats, 0);
@@ -261,11 +268,11 @@ struct Issuer {
   }
   // close the stage: its accumulators are signalled on accumulator barrier `b`
   __device__ __forceinline__ void end(int b) {
-    if (leader) commit(&bars[b]);
+    if (mine && leader) commit(&bars[b]);
     ++it;
     if (b == 0) cov0 = it; else cov1 = it;
   }
-  // warp 0 has just passed accumulator barrier b
+  // the warp has just passed accumulator barrier b
   __device__ __forceinline__ void passed(int b) {
     const uint32_t c = (b == 0) ? cov0 : cov1;
     if (c > done) done = c;
@@ -411,11 +418,11 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
   iss.f_tile = blockIdx.x; iss.ntiles = ntiles; iss.tile_step = gridDim.x; iss.f_l = 0; iss.f_s = 0;
   {
     uint32_t el = 0;
-    if (warp == 0)
-      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
     iss.leader = el != 0;
   }
-  if (warp == 0) iss.pump();     // first kSlots stages
+  iss.warp = warp; iss.mine = false;
+  iss.pump();     // first kSlots stages
   uint32_t bpar = 0u;          // phase parity of the two accumulator barriers (bit b)
 
   // all biases of the conditioners, once per CTA (zero beyond the real widths):
@@ -465,7 +472,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
     bpar ^= 1u << b;
     __syncwarp();
     fence_after();
-    if (warp == 0) iss.passed(b);
+    iss.passed(b);
   };
   // A-operand column j of a hidden layer: activation (j < H), context (H <= j < H+C), zero
   auto acol = [&](int j, float act) -> float {
@@ -564,7 +571,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
         }
       }
       hand_over();
-      if (warp == 0) {
+      {
         iss.begin(__ldg(tab + 5 + 4 * stage));
         uint32_t acc = 0u;
         iss.block(cD, 0, kid8 / 8, 0, 64, acc);
@@ -617,7 +624,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           write_a(a);
         }
         hand_over();
-        if (warp == 0) {
+        {
           uint32_t accg = 0u;
           iss.begin(__ldg(tab + 5 + 4 * stage));
           iss.block(cG, 8 * KC0, nkc, 0, 64, accg);
@@ -646,7 +653,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           write_a(d);
         }
         hand_over();
-        if (warp == 0) {
+        {
           uint32_t acc = 0u;
           iss.begin(__ldg(tab + 5 + 4 * stage));
           iss.block(cD, 0, NCH, 0, 64, acc);
@@ -670,7 +677,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
         const int ns = __ldg(tab);
         const int np = ns - stage;            // passes
         hand_over();
-        if (warp == 0) {
+        {
           for (int p = 0; p < 2 && p < np; ++p) {
             uint32_t acc = 0u;
             iss.begin(__ldg(tab + 5 + 4 * (stage + p)));
@@ -700,7 +707,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           if (p + 2 < np) {
             // region p&1 has been read by everyone: pass p+2 may overwrite it
             hand_over();
-            if (warp == 0) {
+            {
               uint32_t acc = 0u;
               iss.begin(__ldg(tab + 5 + 4 * (stage + p + 2)));
               iss.block(cD + 64 * (p & 1), 0, NCH, 0, __ldg(tab + 6 + 4 * (stage + p + 2)), acc);
