@@ -37,6 +37,7 @@ namespace tc {
 constexpr int kRows = 128;        // rows per tile
 constexpr int kRowThreads = 256;  // two threads per row (column halves)
 constexpr int kThreads = 256;     // 8 row warps; thread 0 also issues the MMAs and the TMA copies
+constexpr int kLuMax = 16;        // LULinear runs on register-resident rows of <= 16 features
 constexpr int kSlots = 3;         // weight ring: up to two stages in use + one prefetched
 constexpr int kCols = 256;        // TMEM columns per CTA
 constexpr int cAhi = 0, cAlo = 64, cD = 128, cG = 192;
@@ -158,7 +159,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(const sbi_nsf_model& m, int sta
   L.zs = fl;  fl += m.Dp * kRows;
   L.ctx = fl; fl += m.Cp * kRows;
   L.lds = fl; fl += kRows;
-  L.lum = fl; fl += round4(2 * m.D * m.D + 2 * m.D);
+  L.lum = fl; fl += 2 * kLuMax * kLuMax + 2 * kLuMax;   // [U 16x16 | L 16x16 | bias 16 | diag 16]
   L.bias_stride = 64 + m.NB * 192 + m.TRmax * 32;
   L.bias = fl; fl += m.T * L.bias_stride;
   fl = (fl + 31) & ~31;
@@ -286,7 +287,20 @@ struct Issuer {
 // after the 3xTF32 linears the log-density already carries ~1e-5 of rounding, and these
 // functions are 40% of the instructions of this kernel.  tests/test_nsf_tc_gpu.py holds the
 // result to the SIMT kernel within 5e-4 and to the fp64 oracle within the common 2e-3.
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 1 / (1 + 2^(-x log2 e)); x -> -inf gives rcp(inf) = 0, x -> +inf gives 1
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x));
+}
 __device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
 
 // Monotone rational-quadratic spline, forward direction, parameters in registers
@@ -579,27 +593,26 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
         iss.end(0);
       }
       ++stage;
-      // dense LU factors of this layer: [U D*D | L D*D | bias D | diag D] (used after the spline;
-      // the previous layer's were last read before the barrier above)
+      // dense LU factors of this layer, zero-padded to 16x16: [U | L | bias 16] (used after the
+      // spline; the previous layer's were last read before the barrier above)
       if (__ldg(v.LT + SBI_L_HAS_LU)) {
         const float* lo = P + __ldg(v.LT + SBI_L_LU_LOWER);
         const float* up = P + __ldg(v.LT + SBI_L_LU_UPPER);
         const float* dg = P + __ldg(v.LT + SBI_L_LU_DIAG);
         const float* bi = P + __ldg(v.LT + SBI_L_LU_BIAS);
         float* U = sm + L.lum;
-        float* Lw = U + D * D;
-        for (int t = tid; t < D * D; t += kRowThreads) {
-          const int i = t / D, j = t % D;
+        float* Lw = U + kLuMax * kLuMax;
+        for (int t = tid; t < kLuMax * kLuMax; t += kRowThreads) {
+          const int i = t / kLuMax, j = t % kLuMax;
           float u = 0.f, lv = 0.f;
-          if (j > i) u = __ldg(up + i * D - i * (i + 1) / 2 + (j - i - 1));
-          else if (j < i) lv = __ldg(lo + i * (i - 1) / 2 + j);
-          else u = softplus_f(__ldg(dg + i)) + 1e-3f;
+          if (i < D && j < D) {
+            if (j > i) u = __ldg(up + i * D - i * (i + 1) / 2 + (j - i - 1));
+            else if (j < i) lv = __ldg(lo + i * (i - 1) / 2 + j);
+            else u = softplus_f(__ldg(dg + i)) + 1e-3f;
+          }
           U[t] = u;
           Lw[t] = lv;
-          if (j == i) {
-            Lw[D * D + i] = __ldg(bi + i);
-            Lw[D * D + D + i] = u;
-          }
+          if (j == 0) Lw[kLuMax * kLuMax + i] = (i < D) ? __ldg(bi + i) : 0.f;
         }
       }
       wait_acc(0);
@@ -721,18 +734,45 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
       //      next layer's identity columns):  z <- L (U z) + b, in place ----
       group_sync();      // both halves' spline outputs are in zs
       if (half == 1 && __ldg(v.LT + SBI_L_HAS_LU)) {
-        const float* U = sm + L.lum;
-        const float* Lw = U + D * D;
-        const float* bias = Lw + D * D;
-        for (int i = 0; i < D; ++i) {
-          float a = 0.f;
-          for (int j = i; j < D; ++j) a = fmaf(U[i * D + j], zs[j * kRows + row], a);
-          zs[i * kRows + row] = a;
+        const float4* U4 = reinterpret_cast<const float4*>(sm + L.lum);
+        const float4* L4 = U4 + kLuMax * kLuMax / 4;
+        const float* bias = sm + L.lum + 2 * kLuMax * kLuMax;
+        float zr[kLuMax];
+#pragma unroll
+        for (int j = 0; j < kLuMax; ++j) zr[j] = (j < D) ? zs[j * kRows + row] : 0.f;
+        // y = U z (upper triangular incl. diagonal; padded entries are zero), same j order as
+        // lu_forward (nsf.cuh)
+#pragma unroll
+        for (int i = 0; i < kLuMax; ++i) {
+          if (i < D) {
+            float a = 0.f;
+#pragma unroll
+            for (int j4 = i / 4; j4 < kLuMax / 4; ++j4) {
+              const float4 w = U4[i * (kLuMax / 4) + j4];
+              if (4 * j4 + 0 >= i) a = fmaf(w.x, zr[4 * j4 + 0], a);
+              if (4 * j4 + 1 >= i) a = fmaf(w.y, zr[4 * j4 + 1], a);
+              if (4 * j4 + 2 >= i) a = fmaf(w.z, zr[4 * j4 + 2], a);
+              if (4 * j4 + 3 >= i) a = fmaf(w.w, zr[4 * j4 + 3], a);
+            }
+            zr[i] = a;
+          }
         }
-        for (int i = D - 1; i >= 0; --i) {
-          float a = zs[i * kRows + row];
-          for (int j = 0; j < i; ++j) a = fmaf(Lw[i * D + j], zs[j * kRows + row], a);
-          zs[i * kRows + row] = a + bias[i];
+        // z = L y + b (strictly lower), rows from the bottom so that y_j (j < i) is still intact
+#pragma unroll
+        for (int i = kLuMax - 1; i >= 0; --i) {
+          if (i < D) {
+            float a = zr[i];
+#pragma unroll
+            for (int j4 = 0; j4 <= (i - 1) / 4 && i > 0; ++j4) {
+              const float4 w = L4[i * (kLuMax / 4) + j4];
+              if (4 * j4 + 0 < i) a = fmaf(w.x, zr[4 * j4 + 0], a);
+              if (4 * j4 + 1 < i) a = fmaf(w.y, zr[4 * j4 + 1], a);
+              if (4 * j4 + 2 < i) a = fmaf(w.z, zr[4 * j4 + 2], a);
+              if (4 * j4 + 3 < i) a = fmaf(w.w, zr[4 * j4 + 3], a);
+            }
+            zr[i] = a + bias[i];
+            zs[i * kRows + row] = zr[i];
+          }
         }
       }
     }
@@ -788,7 +828,7 @@ extern "C" int sbi_b200_nsf_tc_supported(const sbi_nsf_model* m, const sbi_nsf_t
   if (!m || !tc) return 0;
   if (m->H != 50 || m->KB != 10) return 0;        // instantiated hidden width / bin count
   if (m->H + m->C > 64) return 0;                 // context rides in the hidden operand's K range
-  if (m->IDp > 48 || m->PR > 32 || m->KB > sbi::kRqsMaxBins) return 0;
+  if (m->IDp > 48 || m->PR > 32 || m->D > tc::kLuMax) return 0;
   if (m->NB < 1 || m->NB > SBI_NSF_MAX_BLOCKS) return 0;
   if (tc->stage_cap <= 0 || (tc->stage_cap & 31) || tc->n_words <= 0) return 0;
   return tc_plan_slots(m, tc) >= 2 ? 1 : 0;

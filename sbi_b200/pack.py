@@ -219,7 +219,7 @@ class NsfLayout(_LayoutOps):
         Returns dict(src=int32 (n_words,), tab=int32 (T*STRIDE,), stage_cap=int, n_words=int).
         """
         D, C, H, NB, T = self.D, self.C, self.H, self.NB, self.T
-        if H != 50 or self.KB != 10 or H + C > 64 or self.IDp > 48 or self.PR > 32:
+        if H != 50 or self.KB != 10 or H + C > 64 or self.IDp > 48 or self.PR > 32 or D > 16:
             return None
         Hp, Cp, K0p, PR, NPAR = self.Hp, self.Cp, self.K0p, self.PR, self.NPAR
         HP8 = (H + 7) & ~7
