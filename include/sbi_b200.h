@@ -163,6 +163,10 @@ int sbi_b200_nsf_tc_supported(const sbi_nsf_model* m, const sbi_nsf_tc* tc);
 int sbi_b200_nsf_tc_pack(const sbi_nsf_model* m, const sbi_nsf_tc* tc, void* stream);
 int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc, const sbi_rows* rows,
                             float* d_logp, float* d_noise, void* stream);
+/* sampling direction on the same machinery: as sbi_b200_nsf_inverse (NFlowsFlow.sample,
+ * sbi/neural_nets/estimators/nflows_flow.py:111-128) */
+int sbi_b200_nsf_inverse_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc, const sbi_rows* rows,
+                            float* d_out, float* d_logabsdet, void* stream);
 
 /* ---- masked autoregressive flow (sbi `posterior_nn("maf")`, reference builder
  * sbi/neural_nets/net_builders/flow.py:115-209: T x [MaskedAffineAutoregressiveTransform(MADE,

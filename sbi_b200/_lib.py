@@ -139,6 +139,8 @@ _EXPORTS = {
     "sbi_b200_nsf_tc_pack": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc), C.c_void_p]),
     "sbi_b200_nsf_logprob_tc": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc), C.POINTER(Rows),
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sbi_b200_nsf_inverse_tc": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc), C.POINTER(Rows),
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_maf_logprob": (C.c_int, [C.POINTER(MafModel), C.POINTER(Rows), C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "sbi_b200_maf_vjp_parts": (C.c_int, [C.c_int64]),

@@ -215,10 +215,11 @@ struct Issuer {
   uint32_t sbase, lo_off;   // current stage: shared address of the hi half, byte offset of lo half
   int64_t f_tile, ntiles, tile_step;   // next stage to fetch
   int f_l, f_s;
+  bool reverse;         // layers are walked T-1 .. 0 (sampling direction)
 
   __device__ __forceinline__ void pump() {
     while (fetched < done + kSlots && f_tile < ntiles) {
-      const int32_t* t = tab + f_l * SBI_NSF_TC_STRIDE;
+      const int32_t* t = tab + (reverse ? T - 1 - f_l : f_l) * SBI_NSF_TC_STRIDE;
       const int off = __ldg(t + 4 + 4 * f_s), nfl = __ldg(t + 5 + 4 * f_s);
       const uint32_t slot = fetched % kSlots;
       if (leader && (int)((fetched + 4u) & 7u) == warp) {
@@ -360,6 +361,66 @@ __device__ __forceinline__ void rqs_forward_fast(const float (&p)[32], const Rqs
   ld = __logf(dnum) - 2.f * __logf(den);
 }
 
+// Inverse direction (sampling): x = spline^{-1}(y), ld = log dx/dy; restates rqs_inverse of rqs.cuh
+// (bin search on the heights axis, root of the quadratic in the numerically stable form).
+template <int K>
+__device__ __forceinline__ void rqs_inverse_fast(const float (&p)[32], const RqsConst& c, float yin,
+                                                 float& x, float& ld) {
+  const float B = c.B;
+  if (!(yin >= -B && yin <= B)) { x = yin; ld = 0.f; return; }
+  float ew[K], eh[K];
+  float mw = -INFINITY, mh = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    ew[i] = p[i] * c.isq;
+    eh[i] = p[K + i] * c.isq;
+    mw = fmaxf(mw, ew[i]);
+    mh = fmaxf(mh, eh[i]);
+  }
+  float sw = 0.f, sh = 0.f;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    ew[i] = __expf(ew[i] - mw);
+    eh[i] = __expf(eh[i] - mh);
+    sw += ew[i];
+    sh += eh[i];
+  }
+  const float rw = __fdividef(1.f - c.min_w * (float)K, sw);
+  const float rh = __fdividef(1.f - c.min_h * (float)K, sh);
+  float cw = 0.f, ch = 0.f, lo_w = -B, lo_h = -B;
+  float xk = -B, xk1 = B, yk = -B, yk1 = B, r0 = c.edge_raw, r1 = c.edge_raw;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    cw += fmaf(rw, ew[i], c.min_w);
+    ch += fmaf(rh, eh[i], c.min_h);
+    const float hi_w = (i == K - 1) ? B : fmaf(2.f * B, cw, -B);
+    const float hi_h = (i == K - 1) ? B : fmaf(2.f * B, ch, -B);
+    if (yin >= lo_h) {
+      xk = lo_w; xk1 = hi_w; yk = lo_h; yk1 = hi_h;
+      r0 = (i == 0) ? c.edge_raw : p[2 * K + (i > 0 ? i - 1 : 0)];
+      r1 = (i == K - 1) ? c.edge_raw : p[2 * K + (i < K - 1 ? i : 0)];
+    }
+    lo_w = hi_w;
+    lo_h = hi_h;
+  }
+  const float wb = xk1 - xk, hb = yk1 - yk;
+  const float d0 = c.min_d + softplus_fast(r0), d1 = c.min_d + softplus_fast(r1);
+  const float delta = __fdividef(hb, wb);
+  const float dy = yin - yk;
+  const float s2 = d0 + d1 - 2.f * delta;
+  const float a = dy * s2 + hb * (delta - d0);
+  const float b = hb * d0 - dy * s2;
+  const float cc = -delta * dy;
+  const float disc = b * b - 4.f * a * cc;
+  const float root = __fdividef(2.f * cc, -b - sqrtf(disc));
+  x = fmaf(root, wb, xk);
+  const float omr = 1.f - root;
+  const float tomt = root * omr;
+  const float den = delta + s2 * tomt;
+  const float dnum = delta * delta * (d1 * root * root + 2.f * delta * tomt + d0 * omr * omr);
+  ld = -(__logf(dnum) - 2.f * __logf(den));
+}
+
 // Two threads share a row: `half` 0 owns hidden columns [0, HP8/2), `half` 1 owns [HP8/2, HP8)
 // (which end in the first context columns).  All epilogues are column-wise, so the
 // halves never exchange activations; the spline features of a layer alternate between them.
@@ -370,7 +431,12 @@ __device__ __forceinline__ void rqs_forward_fast(const float (&p)[32], const Rqs
 //               evaluated while W_1 runs),  W_2 relu(.) -> D [0]
 //   final layer in passes of <= 2 spline features, pass p -> P_(p&1) [p&1]; two passes are in
 //               flight, so the spline of pass p runs while pass p+1 is computed.
-template <int H, int KB>
+//
+// INV = false: log_prob (logp (R,), optional base-space point `noise` (R,D)).
+// INV = true : sampling direction x = T^{-1}(noise | cond): rows.d_input holds the noise, the
+//              layers run T-1 .. 0 with LU^{-1} first and the inverse spline; `noise` receives x
+//              (R,D) and `logp` (optional) log|det dx/dnoise|  (sbi_b200_nsf_inverse).
+template <int H, int KB, bool INV>
 __global__ void __launch_bounds__(kThreads, 2)
 nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ sbi_nsf_tc tc,
                       const __grid_constant__ sbi_rows rows, float* __restrict__ logp,
@@ -430,6 +496,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
   iss.it = 0; iss.done = 0; iss.fetched = 0; iss.cov0 = iss.cov1 = 0;
   iss.sbase = 0; iss.lo_off = 0;
   iss.f_tile = blockIdx.x; iss.ntiles = ntiles; iss.tile_step = gridDim.x; iss.f_l = 0; iss.f_s = 0;
+  iss.reverse = INV;
   {
     uint32_t el = 0;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
@@ -471,7 +538,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           sacc += logf(softplus_f(__ldg(P + __ldg(LT + SBI_L_LU_DIAG) + i)) + 1e-3f);
       tot += sacc;
     }
-    ld_const = tot + m.ld_zscore - 0.5f * (float)D * 1.8378770664093453f;
+    ld_const = INV ? (-tot - m.ld_zscore) : (tot + m.ld_zscore - 0.5f * (float)D * 1.8378770664093453f);
   }
 
   // operands written / accumulators read: hand TMEM over to the issuing thread
@@ -494,6 +561,30 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
     return j < H ? act : ((c < C) ? ctx_s[c * kRows + row] : 0.f);
   };
 
+  // dense LU factors of layer l, zero-padded to 16x16: [U | L | bias 16 | diag 16]
+  auto prep_lu = [&](int l) {
+    const int* LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
+    if (!__ldg(LT + SBI_L_HAS_LU)) return;
+    const float* lo = P + __ldg(LT + SBI_L_LU_LOWER);
+    const float* up = P + __ldg(LT + SBI_L_LU_UPPER);
+    const float* dg = P + __ldg(LT + SBI_L_LU_DIAG);
+    const float* bi = P + __ldg(LT + SBI_L_LU_BIAS);
+    float* U = sm + L.lum;
+    float* Lw = U + kLuMax * kLuMax;
+    for (int t = tid; t < kLuMax * kLuMax; t += kRowThreads) {
+      const int i = t / kLuMax, j = t % kLuMax;
+      float u = 0.f, lv = 0.f;
+      if (i < D && j < D) {
+        if (j > i) u = __ldg(up + i * D - i * (i + 1) / 2 + (j - i - 1));
+        else if (j < i) lv = __ldg(lo + i * (i - 1) / 2 + j);
+        else u = softplus_f(__ldg(dg + i)) + 1e-3f;
+      }
+      U[t] = u;
+      Lw[t] = lv;
+      if (j == 0) Lw[kLuMax * kLuMax + i] = (i < D) ? __ldg(bi + i) : 0.f;
+      if (j == i) Lw[kLuMax * kLuMax + kLuMax + i] = (i < D) ? u : 1.f;
+    }
+  };
   // this thread's NC columns of a hidden-layer A operand; half 1's last columns are context
   auto write_a = [&](const float (&act)[NC]) {
 #pragma unroll
@@ -527,7 +618,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
         if (d < D && gr < rows.R) {
           const int64_t src = rows.d_index ? __ldg(rows.d_index + gr) : gr;
           const float x = __ldg(rows.d_input + src * D + d);
-          val = __fadd_rn(__fmul_rn(x, __ldg(st + Dp + d)), __ldg(st + d));
+          val = INV ? x : __fadd_rn(__fmul_rn(x, __ldg(st + Dp + d)), __ldg(st + d));
         }
         zs[d * kRows + r] = val;
       }
@@ -541,6 +632,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
         }
         ctx_s[c * kRows + r] = val;
       }
+      if (INV) prep_lu(m.T - 1);
       group_sync();
     }
     // context tail columns [HP8, 64) never change within a tile
@@ -555,7 +647,8 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
     }
     float ldacc = 0.f;
 
-    for (int l = 0; l < m.T; ++l) {
+    for (int li = 0; li < m.T; ++li) {
+      const int l = INV ? m.T - 1 - li : li;
       const NsfLayerView v = layer_view(m, l);
       const int32_t* tab = tc.d_tab + l * SBI_NSF_TC_STRIDE;
       const float* bl = bias_s + l * L.bias_stride;
@@ -563,8 +656,49 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
       int stage = 0;
       float h[NC];
 
+      // ---- sampling: z <- U^{-1} L^{-1} (z - b) on the thread's row (order of lu_inverse, nsf.cuh)
+      if (INV && half == 1 && __ldg(v.LT + SBI_L_HAS_LU)) {
+        const float4* U4 = reinterpret_cast<const float4*>(sm + L.lum);
+        const float4* L4 = U4 + kLuMax * kLuMax / 4;
+        const float* bias = sm + L.lum + 2 * kLuMax * kLuMax;
+        const float* diag = bias + kLuMax;
+        float zr[kLuMax];
+#pragma unroll
+        for (int j = 0; j < kLuMax; ++j) zr[j] = (j < D) ? zs[j * kRows + row] : 0.f;
+#pragma unroll
+        for (int i = 0; i < kLuMax; ++i) {
+          if (i < D) {
+            float a = zr[i] - bias[i];
+#pragma unroll
+            for (int j4 = 0; j4 <= (i - 1) / 4 && i > 0; ++j4) {
+              const float4 w = L4[i * (kLuMax / 4) + j4];
+              if (4 * j4 + 0 < i) a -= w.x * zr[4 * j4 + 0];
+              if (4 * j4 + 1 < i) a -= w.y * zr[4 * j4 + 1];
+              if (4 * j4 + 2 < i) a -= w.z * zr[4 * j4 + 2];
+              if (4 * j4 + 3 < i) a -= w.w * zr[4 * j4 + 3];
+            }
+            zr[i] = a;
+          }
+        }
+#pragma unroll
+        for (int i = kLuMax - 1; i >= 0; --i) {
+          if (i < D) {
+            float a = zr[i];
+#pragma unroll
+            for (int j4 = (i + 1) / 4; j4 < kLuMax / 4; ++j4) {
+              const float4 w = U4[i * (kLuMax / 4) + j4];      // padded entries are zero
+              if (4 * j4 + 0 > i) a -= w.x * zr[4 * j4 + 0];
+              if (4 * j4 + 1 > i) a -= w.y * zr[4 * j4 + 1];
+              if (4 * j4 + 2 > i) a -= w.z * zr[4 * j4 + 2];
+              if (4 * j4 + 3 > i) a -= w.w * zr[4 * j4 + 3];
+            }
+            zr[i] = a / diag[i];
+            zs[i * kRows + row] = zr[i];
+          }
+        }
+      }
       // ---- initial layer: A = [identity features | 0 ... | context] ----
-      // (half 1 ran the previous layer's LU on this row, so it also writes the identity columns)
+      // (half 1 ran the LU on this row, so it also writes the identity columns)
       if (half == 1) {
         for (int kk = 0; kk < kid8 / 8; ++kk) {
           float a[8];
@@ -593,28 +727,11 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
         iss.end(0);
       }
       ++stage;
-      // dense LU factors of this layer, zero-padded to 16x16: [U | L | bias 16] (used after the
-      // spline; the previous layer's were last read before the barrier above)
-      if (__ldg(v.LT + SBI_L_HAS_LU)) {
-        const float* lo = P + __ldg(v.LT + SBI_L_LU_LOWER);
-        const float* up = P + __ldg(v.LT + SBI_L_LU_UPPER);
-        const float* dg = P + __ldg(v.LT + SBI_L_LU_DIAG);
-        const float* bi = P + __ldg(v.LT + SBI_L_LU_BIAS);
-        float* U = sm + L.lum;
-        float* Lw = U + kLuMax * kLuMax;
-        for (int t = tid; t < kLuMax * kLuMax; t += kRowThreads) {
-          const int i = t / kLuMax, j = t % kLuMax;
-          float u = 0.f, lv = 0.f;
-          if (i < D && j < D) {
-            if (j > i) u = __ldg(up + i * D - i * (i + 1) / 2 + (j - i - 1));
-            else if (j < i) lv = __ldg(lo + i * (i - 1) / 2 + j);
-            else u = softplus_f(__ldg(dg + i)) + 1e-3f;
-          }
-          U[t] = u;
-          Lw[t] = lv;
-          if (j == 0) Lw[kLuMax * kLuMax + i] = (i < D) ? __ldg(bi + i) : 0.f;
-        }
-      }
+      // dense LU factors: forward needs this layer's after the spline, sampling needs the next
+      // processed layer's before its conditioner; either way the previous contents were last
+      // read before the barrier above
+      if (!INV) prep_lu(l);
+      else if (l > 0) prep_lu(l - 1);
       wait_acc(0);
       const float* blh = bl + cbase;
       {
@@ -713,7 +830,8 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
             const int j = __ldg(v.trf + f0 + f);
             const float x = zs[j * kRows + row];
             float y, ld;
-            rqs_forward_fast<KB>(q, rc, x, y, ld);
+            if (INV) rqs_inverse_fast<KB>(q, rc, x, y, ld);
+            else rqs_forward_fast<KB>(q, rc, x, y, ld);
             zs[j * kRows + row] = y;
             ldacc += ld;
           }
@@ -733,7 +851,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
       // ---- LULinear on the row (half 1: it has one spline feature less, and it also writes the
       //      next layer's identity columns):  z <- L (U z) + b, in place ----
       group_sync();      // both halves' spline outputs are in zs
-      if (half == 1 && __ldg(v.LT + SBI_L_HAS_LU)) {
+      if (!INV && half == 1 && __ldg(v.LT + SBI_L_HAS_LU)) {
         const float4* U4 = reinterpret_cast<const float4*>(sm + L.lum);
         const float4* L4 = U4 + kLuMax * kLuMax / 4;
         const float* bias = sm + L.lum + 2 * kLuMax * kLuMax;
@@ -781,11 +899,18 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
     if (half == 0) lds[row] = ldacc;
     group_sync();
     if (half == 1 && row0 + row < rows.R) {
-      float ss = 0.f;
-      for (int d = 0; d < D; ++d) ss = fmaf(zs[d * kRows + row], zs[d * kRows + row], ss);
-      logp[row0 + row] = -0.5f * ss + (lds[row] + ldacc) + ld_const;
-      if (noise != nullptr)
-        for (int d = 0; d < D; ++d) noise[(row0 + row) * D + d] = zs[d * kRows + row];
+      if (!INV) {
+        float ss = 0.f;
+        for (int d = 0; d < D; ++d) ss = fmaf(zs[d * kRows + row], zs[d * kRows + row], ss);
+        logp[row0 + row] = -0.5f * ss + (lds[row] + ldacc) + ld_const;
+        if (noise != nullptr)
+          for (int d = 0; d < D; ++d) noise[(row0 + row) * D + d] = zs[d * kRows + row];
+      } else {
+        const float* st = m.d_stats;
+        for (int d = 0; d < D; ++d)
+          noise[(row0 + row) * D + d] = (zs[d * kRows + row] - __ldg(st + d)) / __ldg(st + m.Dp + d);
+        if (logp != nullptr) logp[row0 + row] = (lds[row] + ldacc) + ld_const;
+      }
     }
     group_sync();   // rows of the next tile are written cooperatively
   }
@@ -852,7 +977,7 @@ extern "C" int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc*
   if (rows->R == 0) return 0;
   const int nslot = tc_plan_slots(m, tc);
   const tc::TcSmem L = tc::tc_smem_layout(*m, tc->stage_cap, nslot);
-  auto k = tc::nsf_logprob_tc_kernel<50, 10>;
+  auto k = tc::nsf_logprob_tc_kernel<50, 10, false>;
   static int smem_set = 0;
   if (smem_set < L.total_bytes) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
@@ -862,5 +987,28 @@ extern "C" int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc*
   const int64_t ntiles = (rows->R + tc::kRows - 1) / tc::kRows;
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)tc_num_sms() * 2);
   k<<<grid, tc::kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *tc, *rows, d_logp, d_noise);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int sbi_b200_nsf_inverse_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc,
+                                       const sbi_rows* rows, float* d_out, float* d_logabsdet,
+                                       void* stream) {
+  if (!m || !tc || !rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_out)
+    return SBI_EINVAL;
+  if (!tc->d_tab || !tc->d_tcw) return SBI_EINVAL;
+  if (!sbi_b200_nsf_tc_supported(m, tc)) return SBI_ESMEM;
+  if (rows->R == 0) return 0;
+  const int nslot = tc_plan_slots(m, tc);
+  const tc::TcSmem L = tc::tc_smem_layout(*m, tc->stage_cap, nslot);
+  auto k = tc::nsf_logprob_tc_kernel<50, 10, true>;
+  static int smem_set = 0;
+  if (smem_set < L.total_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
+    if (e != cudaSuccess) return SBI_ESMEM;
+    smem_set = L.total_bytes;
+  }
+  const int64_t ntiles = (rows->R + tc::kRows - 1) / tc::kRows;
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)tc_num_sms() * 2);
+  k<<<grid, tc::kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *tc, *rows, d_logabsdet, d_out);
   return (int)cudaGetLastError();
 }

@@ -361,6 +361,13 @@ class FlowEstimator(nn.Module):
         lad = torch.empty(R, dtype=torch.float32, device=noise.device)
         m = self._model(nbuf=2)
         rows = L.Rows(noise.data_ptr(), ctx.data_ptr(), None, R, 1 if shared else 0)
+        force = os.environ.get("SBI_B200_TC", "") == "1"
+        if self.fam.name == "nsf" and (R >= self.TC_MIN_ROWS or force):
+            tc = self._tc_state(m)
+            if tc is not None:
+                L.check(L.load().sbi_b200_nsf_inverse_tc(C.byref(m), C.byref(tc), C.byref(rows), L.ptr(out),
+                                                         L.ptr(lad), L.stream_ptr()), "nsf_inverse_tc")
+                return out, lad
         L.check(self.fam.fn("inverse")(C.byref(m), C.byref(rows), L.ptr(out), L.ptr(lad),
                                        L.stream_ptr()), f"{self.fam.name}_inverse")
         return out, lad

@@ -116,3 +116,36 @@ def test_tc_unsupported_model_uses_simt(cuda_lib, monkeypatch):
         ref = flow.double().log_prob(theta[:200].double(), x[:200].double())[0]
         got = est.log_prob(theta[:200].cuda(), x[:200].cuda())[0].cpu()
     assert (got.double() - ref).abs().max() <= LOGP_TOL
+
+
+@pytest.mark.parametrize("D,C,R,shared", [(10, 10, 1000, True), (10, 10, 4097, False), (3, 2, 300, False),
+                                          (2, 2, 129, True)])
+def test_tc_sampling_matches_simt_and_oracle(cuda_lib, monkeypatch, D, C, R, shared):
+    """x = T^{-1}(noise | cond) through the tensor-core kernel: same samples as the SIMT kernel
+    (|dx| <= 5e-4) and as the fp64 oracle (|dx| <= 2e-3, the bar of test_nsf_gpu), and
+    log_prob(sample) consistent with the returned log|det|."""
+    flow, theta, x = oracle_nsf(D, C, n=max(R, 500))
+    est = b200_from_oracle(flow, theta, x)
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(R, D, generator=g)
+    cond = x[:1] if shared else x[:R]
+    monkeypatch.setenv("SBI_B200_TC", "0")
+    xs, ls = est.inverse_flow(noise.cuda(), cond.cuda())
+    monkeypatch.setenv("SBI_B200_TC", "1")
+    xt, lt = est.inverse_flow(noise.cuda(), cond.cuda())
+    assert torch.isfinite(xt).all()
+    assert (xs - xt).abs().max() <= VS_SIMT_TOL
+    assert (ls - lt).abs().max() <= VS_SIMT_TOL
+    with torch.no_grad():
+        flow.double()
+        emb = flow.net._embedding_net(cond.double())
+        ctx = emb.expand(R, -1) if shared else emb
+        ref, _ = flow.net._transform.inverse(noise.double(), context=ctx)
+    assert (xt.cpu().double() - ref).abs().max() <= 2e-3
+    # density of the samples through the tensor-core log_prob kernel:
+    #   log q(x) = log N(noise) - log|det dx/dnoise|
+    import math
+    with torch.no_grad():
+        lp = est.log_prob(xt.unsqueeze(1), cond.cuda())[:, 0] if shared else est.log_prob(xt, cond.cuda())[0]
+    base = -0.5 * (noise ** 2).sum(1) - 0.5 * D * math.log(2 * math.pi)
+    assert (lp.cpu() - (base - lt.cpu())).abs().max() <= 5e-3
