@@ -330,6 +330,7 @@ def run_b200(args):
     lp_eps = world * R / (lp_ms * 1e-3)
     lp_bytes = R * (4 * DIM + 4)
     lp_flops = 2.0 * R * _nsf_macs(lay)
+    tc_used = est._tc_state(est._model(nbuf=2)) is not None and R >= est.TC_MIN_ROWS
 
     # ---- end to end: host buffers through the C ABI ----------------------------------------------
     ws = L.TrainWs()
@@ -404,14 +405,23 @@ def run_b200(args):
     h_xo = x_o.cpu().pin_memory()
     h_out = torch.empty(Rh).pin_memory()
     mm = est._model(nbuf=2)
+    tcs = est._tc_state(mm)
+
+    def lp_host():
+        if tcs is not None:
+            L.check(lib.sbi_b200_nsf_logprob_host_tc(C.byref(mm), C.byref(tcs), C.byref(ws), h_eval.data_ptr(),
+                                                     h_xo.data_ptr(), Rh, 1, h_out.data_ptr(), L.stream_ptr()),
+                    "logprob_host_tc")
+        else:
+            L.check(lib.sbi_b200_nsf_logprob_host(C.byref(mm), C.byref(ws), h_eval.data_ptr(), h_xo.data_ptr(),
+                                                  Rh, 1, h_out.data_ptr(), L.stream_ptr()), "logprob_host")
+
     for _ in range(2):
-        L.check(lib.sbi_b200_nsf_logprob_host(C.byref(mm), C.byref(ws), h_eval.data_ptr(), h_xo.data_ptr(),
-                                              Rh, 1, h_out.data_ptr(), L.stream_ptr()), "logprob_host")
+        lp_host()
     barrier()
     t0 = time.perf_counter()
     for _ in range(5):
-        L.check(lib.sbi_b200_nsf_logprob_host(C.byref(mm), C.byref(ws), h_eval.data_ptr(), h_xo.data_ptr(),
-                                              Rh, 1, h_out.data_ptr(), L.stream_ptr()), "logprob_host")
+        lp_host()
     barrier()
     lp_e2e_s = (time.perf_counter() - t0) / 5
     t = torch.tensor([lp_e2e_s], device=dev)
@@ -424,6 +434,7 @@ def run_b200(args):
                   "result of step i read while step i+1 runs)" if world == 1 else
                   "host batch -> H2D -> vjp -> reduce -> NCCL all-reduce -> clip+Adam -> D2H loss, per rank",
            "log_prob": {"value": world * Rh / lp_e2e_s, "unit": "evals/s", "rows": world * Rh,
+                        "api": "sbi_b200_nsf_logprob_host_tc" if tcs is not None else "sbi_b200_nsf_logprob_host",
                         "h2d_bytes_per_step": world * (Rh * DIM * 4 + DIM * 4), "d2h_bytes_per_step": world * Rh * 4}}
     clk = clocks.stop()
 
@@ -457,16 +468,31 @@ def run_b200(args):
             "secondary": {"metric": "posterior log_prob evals/sec", "value": lp_eps, "unit": "evals/s",
                           "rows_per_step_per_gpu": R, "ms_per_step": lp_ms,
                           "l2": "inputs (168 MB) larger than L2",
-                          "roofline": {"bound": "hbm", "kernel": "nsf_logprob_kernel<64,4>",
-                                       "achieved": lp_bytes / (lp_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                                       "unit": "GB/s", "frac": lp_bytes / (lp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                       "fp32_fma_tflops": lp_flops / (lp_ms * 1e-3) / 1e12}},
+                          "roofline": _lp_roofline(tc_used, lp_bytes, lp_flops, lp_ms, peaks)},
             "cpu_baseline": cpu, "clocks": clk, "e2e": e2e, "gpu_launches": n_launch,
             "step_ms_minmax": [min(ms_steps), max(ms_steps)],
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _lp_roofline(tc_used, lp_bytes, lp_flops, lp_ms, peaks):
+    """Roofline entry of the log_prob kernel.  Tensor-core path: algorithmic fp32-equivalent flops
+    (2 x MACs of the linears, no padding, counted once although 3xTF32 issues three MMAs per
+    product) against the tf32 tensor peak, taken as half the measured dense bf16 peak."""
+    sec = lp_ms * 1e-3
+    if not tc_used:
+        return {"bound": "hbm", "kernel": "nsf_logprob_kernel<64,4>", "achieved": lp_bytes / sec / 1e9,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": lp_bytes / sec / 1e9 / peaks["hbm_gbs"],
+                "fp32_fma_tflops": lp_flops / sec / 1e12}
+    peak = peaks["bf16_tflops"] / 2.0
+    ach = lp_flops / sec / 1e12
+    return {"bound": "tensor", "kernel": "nsf_logprob_tc_kernel<50,10,false>", "achieved": ach, "peak": peak,
+            "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_source": peaks["source"] + "; tf32 = bf16/2",
+            "note": "3xTF32: the tensor pipe executes 3x the algorithmic flops (plus K/N padding 50->56/64)",
+            "hbm_gbs": lp_bytes / sec / 1e9}
 
 
 def _nsf_macs(lay):
@@ -491,8 +517,9 @@ def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "source": "MEASURED_PEAKS.json (measured)"}
-    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "source": "MEASURED_PEAKS.json (measured)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 def main():

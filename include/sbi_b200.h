@@ -354,6 +354,12 @@ int sbi_b200_nsf_logprob_host(const sbi_nsf_model* m, const sbi_train_ws* ws,
                               const float* h_input, const float* h_cond, int64_t R,
                               int cond_shared, float* h_logp, void* stream);
 
+/* same through the tensor-core kernel (sbi_b200_nsf_logprob_tc), in chunks whose host<->device
+ * copies overlap the kernels of their neighbours; re-packs tc->d_tcw first. */
+int sbi_b200_nsf_logprob_host_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc, const sbi_train_ws* ws,
+                                 const float* h_input, const float* h_cond, int64_t R,
+                                 int cond_shared, float* h_logp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -185,6 +185,9 @@ _EXPORTS = {
     "sbi_b200_nsf_logprob_host": (C.c_int, [C.POINTER(NsfModel), C.POINTER(TrainWs), C.c_void_p,
                                             C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                             C.c_void_p]),
+    "sbi_b200_nsf_logprob_host_tc": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc), C.POINTER(TrainWs),
+                                               C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                               C.c_void_p]),
 }
 
 _lib = None
