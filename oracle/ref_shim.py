@@ -118,7 +118,7 @@ def install():
     _alias_nflows()
     sys.meta_path.append(_StubFinder())
     if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.append(REFERENCE_ROOT)   # at the END: the reference tree has its own `tests` package
     _installed = True
     return True
 

@@ -373,9 +373,11 @@ class FlowEstimator(nn.Module):
         return out, lad
 
     # ---- tensor-core bulk path (nsf only) --------------------------------------------------------
-    #: rows from which log_prob goes through the tcgen05 kernel (csrc/nsf_tc.cu).  Below it the
-    #: SIMT kernel's smaller tiles fill the GPU better.  SBI_B200_TC=0 disables, =1 forces.
-    TC_MIN_ROWS = int(os.environ.get("SBI_B200_TC_MIN_ROWS", 32768))
+    #: rows from which log_prob / sampling go through the tcgen05 kernel (csrc/nsf_tc.cu).
+    #: Measured crossover (profiles/tc_cross.py): one 128-row tile takes ~90 us end to end
+    #: including the operand re-pack, the SIMT kernel 116 us at 2048 rows and 250 us at 10 000.
+    #: SBI_B200_TC=0 disables, =1 forces.
+    TC_MIN_ROWS = int(os.environ.get("SBI_B200_TC_MIN_ROWS", 1024))
 
     def _tc_state(self, m):
         """NsfTc struct for the current parameters, or None if the model is outside what the

@@ -208,8 +208,15 @@ class _FlowTrainer:
                 m_ev = net._model(nbuf=2)
                 rows = L.Rows(inp_all.data_ptr(), cond_all.data_ptr(), vperm_buf.data_ptr(),
                               vsteps * Bv, 0)
-                L.check(net.fam.fn("logprob")(C.byref(m_ev), C.byref(rows), L.ptr(val_lp), None,
-                                              L.stream_ptr()), "flow_logprob")
+                # validation rows go through the tensor-core kernel when the model fits it (its
+                # operands are re-packed from the just-updated parameters inside _tc_state)
+                tc_ev = net._tc_state(m_ev) if vsteps * Bv >= net.TC_MIN_ROWS else None
+                if tc_ev is not None:
+                    L.check(lib.sbi_b200_nsf_logprob_tc(C.byref(m_ev), C.byref(tc_ev), C.byref(rows),
+                                                        L.ptr(val_lp), None, L.stream_ptr()), "nsf_logprob_tc")
+                else:
+                    L.check(net.fam.fn("logprob")(C.byref(m_ev), C.byref(rows), L.ptr(val_lp), None,
+                                                  L.stream_ptr()), "flow_logprob")
                 finite = torch.isfinite(val_lp)
                 stats[2] = -(torch.where(finite, val_lp, torch.zeros_like(val_lp))).sum()
                 stats[3] = (~finite).sum().float()

@@ -76,9 +76,9 @@ def test_world2_gloo_protocol():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=180) for _ in range(2))
+    res = dict(q.get(timeout=240) for _ in range(2))
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
         assert p.exitcode == 0
     grad1, acc1, idx1 = _single()
     for r in (0, 1):
