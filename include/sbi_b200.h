@@ -245,6 +245,15 @@ int sbi_b200_ratio_vjp_parts(int64_t R);
 int sbi_b200_ratio_vjp(const sbi_ratio_model* m, const sbi_pairs* pairs, const float* d_gout,
                        float* d_logits, float* d_gpart, float* d_gtheta, void* stream);
 
+/* tensor-core bulk evaluation of the classifier (same operand format and `sbi_nsf_tc` descriptor as
+ * the NSF path: d_tab holds ONE stage list: initial layer, per block (W1, W2), final layer as an
+ * N = 16 block whose row 0 is the weight vector; [1] = round8(Dt + Dx)).  Supported when H == 50 and
+ * Dt + Dx <= 56.  Gather map: sbi_b200/pack.py RatioLayout.tc_plan. */
+int sbi_b200_ratio_tc_supported(const sbi_ratio_model* m, const sbi_nsf_tc* tc);
+int sbi_b200_ratio_tc_pack(const sbi_ratio_model* m, const sbi_nsf_tc* tc, void* stream);
+int sbi_b200_ratio_forward_tc(const sbi_ratio_model* m, const sbi_nsf_tc* tc, const sbi_pairs* pairs,
+                              float* d_logits, void* stream);
+
 /* ---- lock-step vectorized slice sampler (state machine of
  * sbi/samplers/mcmc/slice_numpy.py:412-587 `SliceSamplerVectorized.run`): one thread per chain,
  * chain state resident in HBM, one launch per lock-step between two potential evaluations.

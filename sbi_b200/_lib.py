@@ -150,6 +150,10 @@ _EXPORTS = {
     "sbi_b200_maf_inverse": (C.c_int, [C.POINTER(MafModel), C.POINTER(Rows), C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "sbi_b200_ratio_forward": (C.c_int, [C.POINTER(RatioModel), C.POINTER(Pairs), C.c_void_p, C.c_void_p]),
+    "sbi_b200_ratio_tc_supported": (C.c_int, [C.POINTER(RatioModel), C.POINTER(NsfTc)]),
+    "sbi_b200_ratio_tc_pack": (C.c_int, [C.POINTER(RatioModel), C.POINTER(NsfTc), C.c_void_p]),
+    "sbi_b200_ratio_forward_tc": (C.c_int, [C.POINTER(RatioModel), C.POINTER(NsfTc), C.POINTER(Pairs),
+                                            C.c_void_p, C.c_void_p]),
     "sbi_b200_ratio_vjp_parts": (C.c_int, [C.c_int64]),
     "sbi_b200_ratio_vjp": (C.c_int, [C.POINTER(RatioModel), C.POINTER(Pairs), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),

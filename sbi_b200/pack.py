@@ -517,6 +517,54 @@ class RatioLayout(_LayoutOps):
         self.tab = tab
         self.buffers = {}
 
+    def tc_plan(self):
+        """Gather map + stage table for the tcgen05 evaluation path (csrc/ratio_tc.cu), or None."""
+        Dt, Dx, H, NB = self.Dt, self.Dx, self.H, self.NB
+        if H != 50 or Dt + Dx > 56:
+            return None
+        Hp, K0p, Dtp = self.Hp, self.Dtp + self.Dxp, self.Dtp
+        HP8 = (H + 7) & ~7
+        K0 = Dt + Dx
+        k0p8 = (K0 + 7) & ~7
+        tab = np.zeros(L.SBI_NSF_TC_STRIDE, np.int32)
+
+        def block(N, K, fill):
+            blk = np.full((K // 4, N, 4), -1, np.int64)
+            n = np.arange(N)[:, None] + 0 * np.arange(K)[None, :]
+            k = np.arange(K)[None, :] + 0 * np.arange(N)[:, None]
+            blk[k // 4, n, k % 4] = fill(n, k)
+            return blk.reshape(-1)
+
+        t = self.tab
+        w0 = int(t[L.R_W0])
+
+        def fill0(n, k):
+            col = np.where(k < Dt, k, Dtp + (k - Dt))       # packed columns [theta | pad | x | pad]
+            ok = (n < H) & (k < K0)
+            return np.where(ok, w0 + n * K0p + np.clip(col, 0, K0p - 1), -1)
+
+        def hidden(woff, N, rows_valid):
+            def fill(n, k):
+                ok = (n < rows_valid) & (k < H)
+                return np.where(ok, woff + np.minimum(n, rows_valid - 1) * Hp + np.minimum(k, H - 1), -1)
+            return block(N, HP8, fill)
+
+        stages = [(block(64, k0p8, fill0), 64)]
+        for b in range(NB):
+            stages.append((hidden(int(t[L.R_BLK0 + 4 * b + 0]), 64, H), 64))
+            stages.append((hidden(int(t[L.R_BLK0 + 4 * b + 2]), 64, H), 64))
+        stages.append((hidden(int(t[L.R_WF]), 16, 1), 16))
+        chunks, off, cap = [], 0, 0
+        tab[0], tab[1] = len(stages), k0p8
+        for s_, (hi, N) in enumerate(stages):
+            nfl = 2 * hi.size
+            tab[4 + 4 * s_: 8 + 4 * s_] = (off, nfl, N, 0)
+            chunks += [hi, np.where(hi >= 0, -2 - hi, -1)]
+            off += nfl
+            cap = max(cap, nfl)
+        return dict(src=np.concatenate(chunks).astype(np.int32), tab=tab.astype(np.int32),
+                    stage_cap=int((cap + 31) & ~31), n_words=int(off))
+
     def fill_struct(self, s: "L.RatioModel", nbuf: int):
         s.Dt, s.Dx, s.H, s.NB = self.Dt, self.Dx, self.H, self.NB
         s.Dtp, s.Dxp, s.Hp = self.Dtp, self.Dxp, self.Hp

@@ -9,6 +9,7 @@ reference's keys.  `classifier_nn` / `build_resnet_classifier` mirror factory.py
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Callable, Optional
 
 import torch
@@ -173,8 +174,42 @@ class RatioEstimator(nn.Module):
         m = self._model(nbuf=2)
         pr = L.Pairs(theta.data_ptr(), x.data_ptr(), None if ti is None else ti.data_ptr(),
                      None if xi is None else xi.data_ptr(), R, 1 if x_shared else 0)
+        tc = self._tc_state(m) if (R >= self.TC_MIN_ROWS or os.environ.get("SBI_B200_TC", "") == "1") else None
+        if tc is not None:
+            L.check(lib.sbi_b200_ratio_forward_tc(C.byref(m), C.byref(tc), C.byref(pr), L.ptr(out),
+                                                  L.stream_ptr()), "ratio_forward_tc")
+            return out
         L.check(lib.sbi_b200_ratio_forward(C.byref(m), C.byref(pr), L.ptr(out), L.stream_ptr()), "ratio_forward")
         return out
+
+    #: pairs from which the logits go through the tcgen05 kernel (csrc/ratio_tc.cu); measured
+    #: (profiles/tc_ratio_time.py): 10 k pairs 29 us SIMT vs 35 us, 131 k pairs 140 vs 58 us
+    TC_MIN_ROWS = int(os.environ.get("SBI_B200_RATIO_TC_MIN_ROWS", 32768))
+
+    def _tc_state(self, m):
+        """`NsfTc` descriptor with freshly packed operands, or None if the model is outside what
+        the tensor-core kernel instantiates (see FlowEstimator._tc_state)."""
+        if os.environ.get("SBI_B200_TC", "") == "0":
+            return None
+        flat = self.net.flat
+        st = self._cache.get("tc")
+        if st is None or st["dev"] != flat.device:
+            plan = self.layout.tc_plan()
+            st = {"dev": flat.device, "plan": plan}
+            if plan is not None:
+                st.update(src=torch.as_tensor(plan["src"], device=flat.device),
+                          tab=torch.as_tensor(plan["tab"], device=flat.device),
+                          tcw=torch.empty(plan["n_words"], dtype=torch.float32, device=flat.device))
+            self._cache["tc"] = st
+        if st["plan"] is None:
+            return None
+        tc = L.NsfTc(st["plan"]["n_words"], st["plan"]["stage_cap"], st["src"].data_ptr(),
+                     st["tab"].data_ptr(), st["tcw"].data_ptr())
+        lib = L.load()
+        if not lib.sbi_b200_ratio_tc_supported(C.byref(m), C.byref(tc)):
+            return None
+        L.check(lib.sbi_b200_ratio_tc_pack(C.byref(m), C.byref(tc), L.stream_ptr()), "ratio_tc_pack")
+        return tc
 
 
 class _RatioFn(torch.autograd.Function):

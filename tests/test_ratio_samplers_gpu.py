@@ -118,3 +118,33 @@ def test_nle_mcmc_and_nre_rejection_linear_gaussian(cuda_lib):
     s = post.sample((2000,), x=x_o).cpu()
     assert (s.mean(0) - x_o[0] / 2).abs().max() < 0.06
     assert (s.std(0) / math.sqrt(0.05) - 1).abs().max() < 0.25
+
+
+@pytest.mark.parametrize("Dt,Dx,R,shared", [(10, 10, 5000, False), (10, 10, 129, True), (4, 6, 2048, False),
+                                            (1, 1, 33, False), (2, 3, 20000, True)])
+def test_ratio_tensor_core_matches_simt_and_oracle(cuda_lib, monkeypatch, Dt, Dx, R, shared):
+    """Logits through the tcgen05 kernel (csrc/ratio_tc.cu, 3xTF32) vs the SIMT kernel (<= 2e-4) and
+    the fp64 oracle (<= 1e-3, the bar of the SIMT test); pairs given directly, by index, or with a
+    shared x."""
+    ref, est, theta, x = _ratio_pair(Dt, Dx)
+    g0 = torch.Generator().manual_seed(2)
+    th = torch.randn(R, Dt, generator=g0)
+    xx = torch.randn(1 if shared else R, Dx, generator=g0)
+    with torch.no_grad():
+        o64 = ref.double()(th.double(), xx.double().expand(R, -1) if shared else xx.double()).double()
+    thc, xc = th.cuda(), xx.cuda()
+    monkeypatch.setenv("SBI_B200_TC", "0")
+    simt = est.logits_raw(thc, xc, x_shared=shared)
+    monkeypatch.setenv("SBI_B200_TC", "1")
+    tc = est.logits_raw(thc, xc, x_shared=shared)
+    assert est._tc_state(est._model(nbuf=2)) is not None
+    assert torch.isfinite(tc).all()
+    assert (tc - simt).abs().max() <= 2e-4
+    assert (tc.cpu().double() - o64.reshape(-1)).abs().max() <= 1e-3
+    if not shared:
+        ti = torch.randperm(R, device="cuda")[: R // 2]
+        xi = torch.randperm(R, device="cuda")[: R // 2]
+        a = est.logits_raw(thc, xc, ti, xi)
+        monkeypatch.setenv("SBI_B200_TC", "0")
+        b = est.logits_raw(thc, xc, ti, xi)
+        assert (a - b).abs().max() <= 2e-4
