@@ -181,6 +181,33 @@ class FlowMatchingEstimator(nn.Module):
         """flowmatching_estimator.py:349-372: the flow's ODE right-hand side is the velocity itself."""
         return self.forward(input, condition, times)
 
+    # ---- SDE view of the flow (flowmatching_estimator.py:374-469) ----------------------------
+    mean_base = property(lambda self: self._mean_base)
+    std_base = property(lambda self: self._std_base)
+
+    def score(self, input: Tensor, condition: Tensor, t: Tensor) -> Tensor:
+        """grad_theta log p_t(theta | x) = (-(1 - t) v - theta) / (t + sigma_min)   (:374-399)."""
+        t = torch.as_tensor(t, dtype=torch.float32, device=input.device)
+        v = self.forward(input, condition, t)
+        return (-(1 - t) * v - input) / (t + self.noise_scale)
+
+    def drift_fn(self, input: Tensor, times: Tensor, effective_t_max: float = 0.99) -> Tensor:
+        """f(t) = -theta / (1 - t), with 1 - t floored at 1 - effective_t_max   (:401-434)."""
+        times = torch.as_tensor(times, dtype=input.dtype, device=input.device)
+        return -input / torch.maximum(1 - times, torch.tensor(1 - effective_t_max).to(input))
+
+    def diffusion_fn(self, input: Tensor, times: Tensor, effective_t_max: float = 0.99) -> Tensor:
+        """g(t) = sqrt(2 (t + sigma_min) / (1 - t))   (:436-469)."""
+        times = torch.as_tensor(times, dtype=input.dtype, device=input.device)
+        return torch.sqrt(2 * (times + self.noise_scale)
+                          / torch.maximum(1 - times, torch.tensor(1 - effective_t_max).to(times)))
+
+    def solve_schedule(self, num_steps: int, t_min: Optional[float] = None, t_max: Optional[float] = None) -> Tensor:
+        """Uniform grid from t_max down to t_min (estimators/base.py:605-624)."""
+        t_min = self.t_min if t_min is None else t_min
+        t_max = self.t_max if t_max is None else t_max
+        return torch.linspace(t_max, t_min, num_steps, device=self._mean_base.device)
+
     def loss(self, input: Tensor, condition: Tensor, times: Optional[Tensor] = None, **kwargs) -> Tensor:
         """(batch,) flow-matching losses; flowmatching_estimator.py:270-347.  t ~ U(0,1) and
         theta_1 ~ N(0, I) are drawn with torch on the device in the reference's order."""
@@ -354,3 +381,28 @@ def sample_ode(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, 
     y, nfe = odeint_dopri5(lambda y, t: est.forward(y, cond, torch.tensor(t, device=dev)), y0, est.t_max, est.t_min,
                            atol=atol, rtol=rtol)
     return (y, nfe) if return_nfe else y
+
+
+@torch.no_grad()
+def sample_sde(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, steps: int = 500,
+               ts: Optional[Tensor] = None, eta: float = 1.0) -> Tensor:
+    """Draw theta ~ q(theta | x) with the reverse SDE, Euler-Maruyama predictor, no corrector
+    (Diffuser.run, samplers/score/diffuser.py:124-180; EulerMaruyama.predict,
+    samplers/score/predictors.py:112-120; driver VectorFieldPosterior._sample_via_diffusion,
+    vector_field_posterior.py:331-433).  One `fm_forward` kernel per step, the step arithmetic in
+    the reference's order."""
+    assert eta > 0, "eta must be positive."
+    dev = est.net.flat.device
+    cond = condition.reshape(1, *est.condition_shape).to(dev).float()
+    ts = est.solve_schedule(steps) if ts is None else ts
+    ts = ts.to(dev)
+    theta = est._mean_base.to(dev) + est._std_base.to(dev) * torch.randn(num_samples, est.layout.D, device=dev)
+    for i in range(1, ts.numel()):
+        t1, t0 = ts[i - 1], ts[i]
+        dt = t1 - t0
+        f = est.drift_fn(theta, t1)
+        g = est.diffusion_fn(theta, t1)
+        score = est.score(theta, cond, t1)
+        f_backward = f - (1 + eta ** 2) / 2 * g ** 2 * score
+        theta = theta - f_backward * dt + (eta * g) * torch.randn_like(theta) * torch.sqrt(dt)
+    return theta

@@ -633,7 +633,8 @@ class FMPE(_FlowTrainer):
 
     def build_posterior(self, density_estimator=None, prior=None, sample_with: str = "ode", **kwargs):
         from .posteriors import VectorFieldPosterior
-        if sample_with != "ode":
-            raise NotImplementedError("FMPE.build_posterior implements sample_with='ode'")
+        if sample_with not in ("ode", "sde"):
+            raise ValueError(f"sample_with must be 'ode' or 'sde', but is {sample_with}.")
         est = deepcopy(density_estimator if density_estimator is not None else self._neural_net)
-        return VectorFieldPosterior(est, prior if prior is not None else self._prior, device=self._device)
+        return VectorFieldPosterior(est, prior if prior is not None else self._prior, device=self._device,
+                                    sample_with=sample_with)

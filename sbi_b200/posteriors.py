@@ -367,12 +367,14 @@ class RejectionPosterior:
 
 
 class VectorFieldPosterior:
-    """Posterior of a flow-matching estimator sampled by integrating its ODE (reference:
-    /root/reference/sbi/inference/posteriors/vector_field_posterior.py: sample :155-329,
-    sample_via_ode :436-465); draws outside the prior support are rejected like the reference
-    (`reject_outside_prior=True`)."""
+    """Posterior of a flow-matching estimator sampled by integrating its ODE or its reverse SDE
+    (reference: /root/reference/sbi/inference/posteriors/vector_field_posterior.py: sample :155-329,
+    sample_via_ode :436-465, _sample_via_diffusion :331-433 with the Euler-Maruyama predictor);
+    draws outside the prior support are rejected like the reference (`reject_outside_prior=True`)."""
 
-    def __init__(self, vector_field_estimator, prior, device: Optional[str] = None, max_sampling_batch_size: int = 10_000):
+    def __init__(self, vector_field_estimator, prior, device: Optional[str] = None, max_sampling_batch_size: int = 10_000,
+                 sample_with: str = "ode"):
+        self.sample_with = sample_with
         self.vector_field_estimator = vector_field_estimator
         self._device = device or str(vector_field_estimator.flat.device)
         self.prior = prior_to_device(prior, self._device)
@@ -385,12 +387,14 @@ class VectorFieldPosterior:
         return self
 
     @torch.no_grad()
-    def sample(self, sample_shape=torch.Size(), x: Optional[Tensor] = None, sample_with: str = "ode",
+    def sample(self, sample_shape=torch.Size(), x: Optional[Tensor] = None, sample_with: Optional[str] = None,
                reject_outside_prior: bool = True, max_sampling_batch_size: Optional[int] = None,
                show_progress_bars: bool = False, **kwargs) -> Tensor:
-        from .flowmatching import sample_ode
-        if sample_with != "ode":
-            raise NotImplementedError("sample_with='ode' only")
+        from .flowmatching import sample_ode, sample_sde
+        sample_with = sample_with or self.sample_with
+        if sample_with not in ("ode", "sde"):
+            raise ValueError(f"Expected sample_with to be 'ode' or 'sde', but got {sample_with}.")
+        steps, ts, eta = kwargs.get("steps", 500), kwargs.get("ts"), (kwargs.get("predictor_params") or {}).get("eta", 1.0)
         x = x if x is not None else self.default_x
         if x is None:
             raise ValueError("Context `x` needed when a default has not been set.")
@@ -399,8 +403,13 @@ class VectorFieldPosterior:
         est = self.vector_field_estimator
 
         def proposal(shape, **kw):
-            s, nfe = sample_ode(est, torch.Size(shape).numel(), x, return_nfe=True)
-            self.num_function_evaluations += nfe
+            n = torch.Size(shape).numel()
+            if sample_with == "sde":
+                s = sample_sde(est, n, x, steps=steps, ts=ts, eta=eta)
+                self.num_function_evaluations += (steps if ts is None else ts.numel()) - 1
+            else:
+                s, nfe = sample_ode(est, n, x, return_nfe=True)
+                self.num_function_evaluations += nfe
             return s.unsqueeze(1)
 
         if reject_outside_prior and self.prior is not None:

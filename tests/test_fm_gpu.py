@@ -97,3 +97,32 @@ def test_fmpe_fit_linear_gaussian(cuda_lib):
     s = post.sample((3000,), x=x_o).cpu()
     assert (s.mean(0) - x_o[0] / 2).abs().max() < 0.05
     assert (s.std(0) / math.sqrt(0.05) - 1).abs().max() < 0.25
+    # reverse-SDE sampling (Euler-Maruyama, 500 steps) of the same estimator:
+    # linearGaussian_vector_field_test.py samples fmpe with both "ode" and "sde"
+    post_sde = inf.build_posterior(sample_with="sde")
+    s2 = post_sde.sample((3000,), x=x_o).cpu()
+    assert torch.isfinite(s2).all()
+    assert (s2.mean(0) - x_o[0] / 2).abs().max() < 0.06
+    assert (s2.std(0) / math.sqrt(0.05) - 1).abs().max() < 0.3
+
+
+def test_fm_score_drift_diffusion_formulas(cuda_lib):
+    """score / drift / diffusion / schedule of the estimator (flowmatching_estimator.py:374-469,
+    estimators/base.py:605-624) against the oracle port's velocity on the same weights."""
+    ref, est, theta, x = _pair(4, 3)
+    g = torch.Generator().manual_seed(3)
+    th = torch.randn(64, 4, generator=g)
+    for tv in (0.05, 0.5, 0.93):          # the predictor passes a 0-dim time (ts[i])
+        t = torch.tensor(tv)
+        with torch.no_grad():
+            v = ref.double()(th.double(), x[:64].double(), t.double())
+            score_ref = (-(1 - tv) * v - th.double()) / (tv + 1e-3)
+        score_k = est.score(th.cuda(), x[:64].cuda(), t.cuda())
+        assert score_k.shape == (64, 4)
+        assert (score_k.cpu().double() - score_ref).abs().max() <= 5e-3 * score_ref.abs().max()
+    f = est.drift_fn(th.cuda(), torch.tensor(0.995, device="cuda"))
+    assert torch.allclose(f.cpu(), -th / 0.01, rtol=1e-4)
+    gdiff = est.diffusion_fn(th.cuda(), torch.tensor(0.5, device="cuda"))
+    assert abs(float(gdiff) - math.sqrt(2 * (0.5 + 1e-3) / 0.5)) < 1e-5
+    ts = est.solve_schedule(11)
+    assert float(ts[0]) == 1.0 and float(ts[-1]) == 0.0 and ts.numel() == 11
