@@ -99,6 +99,47 @@ class SliceSamplerVectorized:
         return samples[:, -num_samples:, :] if group_by_chain else samples[-num_samples:, :]
 
 
+class SliceSampler:
+    """Single-chain coordinate-wise slice sampler with the reference's interface
+    (/root/reference/sbi/samplers/mcmc/slice_numpy.py:57-216: `SliceSampler(x, lp_f, max_width,
+    init_width, thin, tuning)`, `.gen(n_samples)` -> (n_samples, dim) array, `.set_state(x)`).
+    `lp_f` maps one parameter vector (1-D numpy array) to its log-probability, as in the
+    reference.  The chain's state machine is the same device kernel as the vectorized sampler
+    (one chain, lock-step with the host callback)."""
+
+    def __init__(self, x, lp_f: Callable, max_width: float = float("inf"), init_width: Union[float, np.ndarray] = 0.01,
+                 thin: Optional[int] = None, tuning: int = 50, verbose: bool = False, device: str = "cuda",
+                 seed: Optional[int] = None):
+        self.x = np.array(x, dtype=float).reshape(-1)
+        self.n_dims = self.x.size
+        self.lp_f = lp_f
+        self.L = lp_f(self.x)
+        self.thin = 1 if thin is None else thin
+        self.max_width, self.init_width, self.tuning, self.verbose = max_width, init_width, tuning, verbose
+        self._device, self._seed = device, seed
+        self._tuned = False
+
+    def set_state(self, x):
+        self.x = np.array(x, dtype=float).reshape(-1)
+        self.L = self.lp_f(self.x)
+
+    def gen(self, n_samples: int, logger=None, show_info: bool = False, rng=None) -> np.ndarray:
+        assert n_samples >= 0, "number of samples can't be negative"
+
+        def batch_lp(params: Tensor) -> Tensor:
+            return torch.tensor([float(self.lp_f(params[0].double().cpu().numpy()))], dtype=torch.float32)
+
+        vec = SliceSamplerVectorized(batch_lp, self.x[None, :], num_chains=1, thin=self.thin,
+                                     tuning=0 if self._tuned else self.tuning, init_width=self.init_width,
+                                     max_width=self.max_width, device=self._device, seed=self._seed, check_every=1)
+        out = vec.run(int(n_samples) * self.thin)[0]
+        self._tuned = True
+        if out.shape[0] > 0:
+            self.x = out[-1].copy()
+            self.L = self.lp_f(self.x)
+        return out
+
+
 # ------------------------------------------------------------------------------------------------
 def gradient_ascent(potential_fn: Callable, inits: Tensor, theta_transform: Optional[torch_tf.Transform] = None,
                     num_iter: int = 1_000, num_to_optimize: int = 100, learning_rate: float = 0.01,

@@ -148,3 +148,24 @@ def test_ratio_tensor_core_matches_simt_and_oracle(cuda_lib, monkeypatch, Dt, Dx
         monkeypatch.setenv("SBI_B200_TC", "0")
         b = est.logits_raw(thc, xc, ti, xi)
         assert (a - b).abs().max() <= 2e-4
+
+
+def test_single_chain_slice_sampler_interface(cuda_lib):
+    """`SliceSampler(x, lp_f).gen(n)` (slice_numpy.py:57-216): numpy in / numpy out, one chain;
+    1-D standard-normal-ish target N(1, 0.5^2) x N(-2, 2^2)."""
+    from sbi_b200.samplers import SliceSampler
+    mu, sd = np.array([1.0, -2.0]), np.array([0.5, 2.0])
+    calls = []
+
+    def lp_f(p):
+        assert isinstance(p, np.ndarray) and p.shape == (2,)
+        calls.append(1)
+        return float(-0.5 * (((p - mu) / sd) ** 2).sum())
+
+    smp = SliceSampler(np.zeros(2), lp_f, tuning=50, thin=2, seed=7)
+    out = smp.gen(1500)
+    assert out.shape == (1500, 2) and np.isfinite(out).all()
+    assert np.abs(out[200:].mean(0) - mu).max() < 0.35
+    assert np.abs(out[200:].std(0) / sd - 1).max() < 0.3
+    assert np.allclose(smp.x, out[-1])
+    assert len(calls) > 1500
