@@ -326,6 +326,86 @@ __global__ void __launch_bounds__(128) cadence(long long* __restrict__ cyc, int 
                  : "memory");
 }
 
+
+// ---- operands for the weight-gradient GEMM dW = dY^T X (K = rows): both operands from shared
+// memory, MN-major (the row index is K).  Canonical no-swizzle MN-major layout tried here
+// (cute/atom/mma_traits_sm100.hpp, Major-MN INTERLEAVE: ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)), T = 4):
+//   core matrix = 8 K-rows x 4 MN-elements, 128 B contiguous (K-row j0 at +16*j0 B);
+//   SBO = byte distance between consecutive groups of 4 along MN, LBO = between groups of 8 along K.
+// X is (Krows x NF) "row-major by 4-feature groups": addr(k, f) = (k/8)*LBO + (f/4)*SBO + (k%8)*16 + (f%4)*4.
+// The kernel computes D[m][n] = sum_k A[k][m] * B[k][n] for M in {64, 128}, N = 64, K = 128 rows and
+// dumps ALL 128 lanes x N columns so that the host can find where (m, n) lands for M = 64.
+__device__ __forceinline__ uint32_t make_idesc_mn(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__global__ void __launch_bounds__(128) probe_mn(const float* __restrict__ A, const float* __restrict__ B,
+                                                float* __restrict__ out, int M, int N, int KR, int swap) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  float* as = reinterpret_cast<float*>(smem);
+  float* bs = as + KR * M;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tbase_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t sboA = 128u, lboA = (uint32_t)(M / 4) * 128u;
+  const uint32_t sboB = 128u, lboB = (uint32_t)(N / 4) * 128u;
+  for (int i = tid; i < KR * M; i += 128) {
+    const int k = i / M, f = i % M;
+    as[((k / 8) * lboA + (f / 4) * sboA + (k % 8) * 16 + (f % 4) * 4) / 4] = A[i];
+  }
+  for (int i = tid; i < KR * N; i += 128) {
+    const int k = i / N, f = i % N;
+    bs[((k / 8) * lboB + (f / 4) * sboB + (k % 8) * 16 + (f % 4) * 4) / 4] = B[i];
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tbase_s)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tbase_s;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  {   // clear the accumulator columns so that untouched lanes read back as a sentinel
+    float v[8];
+    for (int i = 0; i < 8; ++i) v[i] = -777.f;
+    for (int c = 0; c < N; c += 8) tc_st8(tbase + lane_base + c, v);
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_mn(M, N, 1, 1);
+    for (int kg = 0; kg < KR / 8; ++kg) {
+      const uint64_t ad = swap ? make_bdesc(smem_u32(as) + kg * lboA, sboA, lboA)
+                               : make_bdesc(smem_u32(as) + kg * lboA, lboA, sboA);
+      const uint64_t bd = swap ? make_bdesc(smem_u32(bs) + kg * lboB, sboB, lboB)
+                               : make_bdesc(smem_u32(bs) + kg * lboB, lboB, sboB);
+      tc_mma_tf32_ss(tbase, ad, bd, idesc, kg > 0);
+    }
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c = 0; c < N; c += 8) {
+    float r[8];
+    tc_ld8(tbase + lane_base + c, r);
+    for (int i = 0; i < 8; ++i) out[tid * N + c + i] = r[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256)
+                 : "memory");
+}
+
 static float tf32_trunc(float x) {
   uint32_t u;
   memcpy(&u, &x, 4);
@@ -387,6 +467,52 @@ int main() {
                  "max|ref|=%.2f  cycles/layer=%lld\n",
                  mode, N, K, swap, rterr, err, err1, ref_max, cyc);
         }
+  // ---- MN-major operands / M = 64 accumulator placement ----
+  CK(cudaFuncSetAttribute(probe_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  for (int M : {128, 64})
+    for (int swap = 0; swap < 2; ++swap) {
+      const int N = 64, KR = 128;
+      std::vector<float> A(KR * M), B(KR * N), O(128 * N);
+      srand(99);
+      for (auto& a : A) a = (float)((rand() % 9) - 4) / 4.f;
+      for (auto& b : B) b = (float)((rand() % 9) - 4) / 2.f;
+      float *dA2, *dB2;
+      CK(cudaMalloc(&dA2, A.size() * 4));
+      CK(cudaMalloc(&dB2, B.size() * 4));
+      CK(cudaMemcpy(dA2, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dB2, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+      probe_mn<<<1, 128, (KR * M + KR * N) * 4>>>(dA2, dB2, dO, M, N, KR, swap);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mn M=%d swap=%d: CUDA error %s\n", M, swap, cudaGetErrorString(e)); return 1; }
+      CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
+      // reference
+      std::vector<double> R(M * N);
+      for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+          double sacc = 0;
+          for (int k = 0; k < KR; ++k) sacc += (double)A[k * M + m] * B[k * N + n];
+          R[m * N + n] = sacc;
+        }
+      // hypothesis 1: row m in lane m
+      double e1 = 0;
+      for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) e1 = fmax(e1, fabs(O[m * N + n] - R[m * N + n]));
+      // hypothesis 2 (M = 64): row m in lane (m % 16) + 32 * (m / 16)
+      double e2 = 0;
+      for (int m = 0; m < M && M == 64; ++m)
+        for (int n = 0; n < N; ++n)
+          e2 = fmax(e2, fabs(O[((m % 16) + 32 * (m / 16)) * N + n] - R[m * N + n]));
+      int touched = 0;
+      for (int l = 0; l < 128; ++l) touched += (O[l * N] != -777.f);
+      printf("mn-major M=%3d swap=%d: lanes written %d; err(lane=m) %.3e; err(lane=m%%16+32*(m/16)) %.3e\n", M, swap,
+             touched, e1, e2);
+      if (M == 64) {
+        printf("   lanes holding data:");
+        for (int l = 0; l < 128; ++l) if (O[l * N] != -777.f) printf(" %d", l);
+        printf("\n");
+      }
+      cudaFree(dA2); cudaFree(dB2);
+    }
   CK(cudaFuncSetAttribute(cadence, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   for (int var : {0, 4, 5})
     for (int N : {64, 128, 256}) {
