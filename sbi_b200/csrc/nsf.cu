@@ -202,13 +202,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ sbi_rows rows,
                const float* __restrict__ gout, float g_const, float* __restrict__ logp,
                float* __restrict__ gpart, float* __restrict__ ginput, float* __restrict__ gcond,
-               float* __restrict__ loss_acc) {
+               float* __restrict__ loss_acc, float* __restrict__ scratch) {
   constexpr int LD = Tile<TM>::LD;
   extern __shared__ __align__(128) float sm[];
   const NsfSmem L = nsf_smem_layout(m, TM, true);
   WPipe pipe = make_pipe(m, sm, L);
   const int64_t ntiles = (rows.R + TM - 1) / TM;
   const bool need_dctx = (gcond != nullptr);
+  // Activation spill: with a scratch buffer (one slab per CTA and layer, L2-resident) the forward
+  // sweep keeps every conditioner intermediate and the spline parameters of each layer, and the
+  // backward sweep reads them back instead of recomputing the conditioner (a quarter of the GEMM
+  // work of this kernel).  Without it (scratch == nullptr) the layer is recomputed.
+  const bool spill = (scratch != nullptr);
+  const int sv_rows = (4 * m.NB + 1) * m.Hp;           // HS | A1S | T2S | SS, contiguous
+  const int prm_rows = m.TRmax * m.PR;
+  const int slab = (sv_rows + prm_rows) * LD;          // floats per (CTA, layer)
   const float* __restrict__ P = m.d_params;
   const int Hp = m.Hp, Cp = m.Cp, K0p = m.Cp + m.IDp;
 
@@ -218,13 +226,15 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int l = 0; l < m.T; ++l) {
           const NsfLayerView v = layer_view(m, l);
-          float* hf = cond_forward<kProducer, TM, RN, SBI_VJP_SINGLE_COND != 0>(m, v, pipe, sm, L);
+          float* hf = cond_forward<kProducer, TM, RN, true>(m, v, pipe, sm, L);
           spline_forward<kProducer, TM, RN, false>(m, v, pipe, sm, L, hf);
         }
         for (int l = m.T - 1; l >= 0; --l) {
           const NsfLayerView v = layer_view(m, l);
-          float* hf = cond_forward<kProducer, TM, RN, true>(m, v, pipe, sm, L);
-          final_layer<kProducer, TM, RN>(m, v, pipe, sm, L, hf);
+          if (!spill) {
+            float* hf = cond_forward<kProducer, TM, RN, true>(m, v, pipe, sm, L);
+            final_layer<kProducer, TM, RN>(m, v, pipe, sm, L, hf);
+          }
           auto noop2 = [](int, int, float(&)[RK][4], bool) {};
           dx_stage<kProducer, TM, RK>(pipe, P + __ldg(v.LT + SBI_L_WF), v.n_tr * m.PR, Hp,
                                       m.nf_chunk * m.PR, nullptr, Hp, noop2);
@@ -277,8 +287,18 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
         sm[L.ZS + l * m.Dp * LD + e] = Z[e];
       lu_prepare(m, v, sm, L);
       gather_identity<TM>(m, v, Z, U);
-      float* hf = cond_forward<kConsumer, TM, RN, SBI_VJP_SINGLE_COND != 0>(m, v, pipe, sm, L);
+      float* hf = cond_forward<kConsumer, TM, RN, true>(m, v, pipe, sm, L);
       spline_forward<kConsumer, TM, RN, false>(m, v, pipe, sm, L, hf);
+      if (spill) {
+        // (spline_forward ended with a barrier; nothing below touches these regions before the
+        // barriers inside lu_forward, so every thread's part is out before they are rewritten)
+        float4* dst = reinterpret_cast<float4*>(scratch + ((size_t)blockIdx.x * m.T + l) * slab);
+        const float4* s0 = reinterpret_cast<const float4*>(sm + L.HS);
+        const float4* s1 = reinterpret_cast<const float4*>(sm + L.PRM);
+        const int n0 = sv_rows * LD / 4, n1 = prm_rows * LD / 4;
+        for (int e = threadIdx.x; e < n0; e += kConsumerThreads) __stcg(dst + e, s0[e]);
+        for (int e = threadIdx.x; e < n1; e += kConsumerThreads) __stcg(dst + n0 + e, s1[e]);
+      }
       fold_ldf<TM>(v, sm, L);
       for (int e = threadIdx.x; e < m.Dp * LD; e += kConsumerThreads)
         sm[L.VS + l * m.Dp * LD + e] = Z[e];
@@ -327,14 +347,27 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
       lu_prepare(m, v, sm, L);
       consumer_sync();
       lu_backward<TM>(m, v, sm, L, VSl, gp, accum);
-      // recompute the conditioner from the saved layer input
+      // the conditioner's intermediates of this layer: read back, or recomputed from the saved
+      // layer input
       gather_identity<TM>(m, v, ZSl, U);
-      float* hf = cond_forward<kConsumer, TM, RN, true>(m, v, pipe, sm, L);
+      float* hf;
+      if (spill) {
+        const float4* src = reinterpret_cast<const float4*>(scratch + ((size_t)blockIdx.x * m.T + l) * slab);
+        float4* d0 = reinterpret_cast<float4*>(sm + L.HS);
+        float4* d1 = reinterpret_cast<float4*>(sm + L.PRM);
+        const int n0 = sv_rows * LD / 4, n1 = prm_rows * LD / 4;
+        for (int e = threadIdx.x; e < n0; e += kConsumerThreads) d0[e] = __ldcg(src + e);
+        for (int e = threadIdx.x; e < n1; e += kConsumerThreads) d1[e] = __ldcg(src + n0 + e);
+        hf = sm + L.HS + m.NB * Hp * LD;
+        consumer_sync();
+      } else {
+        hf = cond_forward<kConsumer, TM, RN, true>(m, v, pipe, sm, L);
+      }
       // final layer (all features) -> spline backward -> dW, dH
       {
         const int oWF = __ldg(v.LT + SBI_L_WF), oBF = __ldg(v.LT + SBI_L_BF);
         const int N = v.n_tr * m.PR;
-        final_layer<kConsumer, TM, RN>(m, v, pipe, sm, L, hf);
+        if (!spill) final_layer<kConsumer, TM, RN>(m, v, pipe, sm, L, hf);
         for (int t = threadIdx.x; t < v.n_tr * TM; t += kConsumerThreads) {
           const int f = t / TM, r = t % TM;
           const int j = __ldg(v.trf + f);
@@ -601,6 +634,37 @@ extern "C" int sbi_b200_nsf_vjp_parts(int64_t R) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, num_sms()));
 }
 
+// Scratch for the activation spill of the VJP kernel: one slab per (CTA, layer), owned by the
+// library and grown on demand.  It cannot be (re)allocated while the stream is being captured into
+// a CUDA graph; then -- or with SBI_B200_VJP_SPILL=0 -- the kernel recomputes instead.
+static float* g_vjp_scratch = nullptr;
+static size_t g_vjp_scratch_bytes = 0;
+static int g_vjp_scratch_dev = -1;
+static float* vjp_scratch(size_t bytes, cudaStream_t s) {
+  static const bool off = [] {
+    const char* e = getenv("SBI_B200_VJP_SPILL");
+    return e && e[0] == '0';
+  }();
+  if (off) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (g_vjp_scratch && dev == g_vjp_scratch_dev && bytes <= g_vjp_scratch_bytes) return g_vjp_scratch;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+  if (g_vjp_scratch && dev == g_vjp_scratch_dev) cudaFree(g_vjp_scratch);
+  g_vjp_scratch = nullptr;
+  g_vjp_scratch_bytes = 0;
+  float* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_vjp_scratch = p;
+  g_vjp_scratch_bytes = bytes;
+  g_vjp_scratch_dev = dev;
+  return p;
+}
+
 extern "C" int sbi_b200_nsf_vjp(const sbi_nsf_model* m, const sbi_rows* rows, const float* d_gout,
                                 float g_const, float* d_logp, float* d_gpart, float* d_ginput,
                                 float* d_gcond, float* d_loss_acc, void* stream) {
@@ -613,7 +677,9 @@ extern "C" int sbi_b200_nsf_vjp(const sbi_nsf_model* m, const sbi_rows* rows, co
   auto k = nsf_vjp_kernel<TM, 2, 2>;
   if ((rc = set_smem<4>(k, L.total_bytes))) return rc;
   const int grid = sbi_b200_nsf_vjp_parts(rows->R);
+  const size_t slab = (size_t)((4 * m->NB + 1) * m->Hp + m->TRmax * m->PR) * (TM + 4);
+  float* scratch = vjp_scratch(sizeof(float) * slab * m->T * (size_t)num_sms(), s);
   k<<<grid, kThreads, L.total_bytes, s>>>(*m, *rows, d_gout, g_const, d_logp, d_gpart, d_ginput,
-                                          d_gcond, d_loss_acc);
+                                          d_gcond, d_loss_acc, scratch);
   return (int)cudaGetLastError();
 }

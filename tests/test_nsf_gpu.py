@@ -121,3 +121,35 @@ def test_sample_shapes_and_roundtrip(cuda_lib):
     assert (lp - lp2).abs().max() <= 5e-3
     # samples of sample() belong to their condition: log_prob under the right condition is finite
     assert torch.isfinite(est.log_prob(s.reshape(14, 3, 10), cond)).all()
+
+
+def test_vjp_activation_spill_equals_recompute(cuda_lib, tmp_path):
+    """The VJP kernel's activation spill (conditioner intermediates written to an L2-resident
+    scratch in the forward sweep, read back in the backward sweep) must give bit-identical
+    gradients to the recompute path (SBI_B200_VJP_SPILL=0, read once per process -> subprocess)."""
+    import os
+    import subprocess
+    import sys
+    script = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from tests.helpers import b200_from_oracle, oracle_nsf
+flow, theta, x = oracle_nsf(10, 10, n=5000)
+est = b200_from_oracle(flow, theta, x)
+inp = theta[:4096].cuda().requires_grad_(True)
+cond = x[:4096].cuda().requires_grad_(True)
+g = torch.Generator().manual_seed(9)
+w = torch.randn(4096, generator=g).cuda()
+lp = est.log_prob(inp, cond)[0]
+(lp * w).sum().backward()
+torch.save({"flat": est.flat.grad.cpu(), "inp": inp.grad.cpu(), "cond": cond.grad.cpu()}, sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for mode in ("1", "0"):
+        env = dict(os.environ, SBI_B200_VJP_SPILL=mode)
+        f = tmp_path / f"g{mode}.pt"
+        subprocess.run([sys.executable, "-c", script, str(f)], check=True, env=env, timeout=300)
+        outs[mode] = torch.load(f)
+    for k in ("flat", "inp", "cond"):
+        assert torch.equal(outs["1"][k], outs["0"][k]), k
+    assert outs["1"]["flat"].abs().max() > 0
