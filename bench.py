@@ -456,7 +456,7 @@ def run_b200(args):
                        "global_batch": B * world, "per_gpu_batch": B, "params": real_params,
                        "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB memset, untimed)",
                        "launch": "cuda-graph per step" if graphs is not None else "eager"},
-            "roofline": {"bound": "hbm", "kernel": "nsf_vjp_kernel<32,2,2>", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "nsf_vjp_kernel<32,2,2,true>", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": traffic.get("nsf_vjp_kernel", {}).get("dram_bytes_per_launch"),
                          "traffic_source": "profiles/r01_traffic.json (ncu --set full, B=4096)",

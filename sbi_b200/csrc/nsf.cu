@@ -197,7 +197,7 @@ __device__ __forceinline__ void lu_backward(const sbi_nsf_model& m, const NsfLay
   consumer_sync();
 }
 
-template <int TM, int RN, int RK>
+template <int TM, int RN, int RK, bool SPILL>
 __global__ void __launch_bounds__(kThreads, 1)
 nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ sbi_rows rows,
                const float* __restrict__ gout, float g_const, float* __restrict__ logp,
@@ -213,7 +213,7 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
   // sweep keeps every conditioner intermediate and the spline parameters of each layer, and the
   // backward sweep reads them back instead of recomputing the conditioner (a quarter of the GEMM
   // work of this kernel).  Without it (scratch == nullptr) the layer is recomputed.
-  const bool spill = (scratch != nullptr);
+  constexpr bool spill = SPILL;      // compile-time: the unused path costs instruction cache
   const int sv_rows = (4 * m.NB + 1) * m.Hp;           // HS | A1S | T2S | SS, contiguous
   const int prm_rows = m.TRmax * m.PR;
   const int slab = (sv_rows + prm_rows) * LD;          // floats per (CTA, layer)
@@ -674,12 +674,19 @@ extern "C" int sbi_b200_nsf_vjp(const sbi_nsf_model* m, const sbi_rows* rows, co
   cudaStream_t s = (cudaStream_t)stream;
   constexpr int TM = 32;
   const NsfSmem L = nsf_smem_layout(*m, TM, true);
-  auto k = nsf_vjp_kernel<TM, 2, 2>;
-  if ((rc = set_smem<4>(k, L.total_bytes))) return rc;
   const int grid = sbi_b200_nsf_vjp_parts(rows->R);
   const size_t slab = (size_t)((4 * m->NB + 1) * m->Hp + m->TRmax * m->PR) * (TM + 4);
   float* scratch = vjp_scratch(sizeof(float) * slab * m->T * (size_t)num_sms(), s);
-  k<<<grid, kThreads, L.total_bytes, s>>>(*m, *rows, d_gout, g_const, d_logp, d_gpart, d_ginput,
-                                          d_gcond, d_loss_acc, scratch);
+  if (scratch != nullptr) {
+    auto k = nsf_vjp_kernel<TM, 2, 2, true>;
+    if ((rc = set_smem<4>(k, L.total_bytes))) return rc;
+    k<<<grid, kThreads, L.total_bytes, s>>>(*m, *rows, d_gout, g_const, d_logp, d_gpart, d_ginput,
+                                            d_gcond, d_loss_acc, scratch);
+  } else {
+    auto k = nsf_vjp_kernel<TM, 2, 2, false>;
+    if ((rc = set_smem<6>(k, L.total_bytes))) return rc;
+    k<<<grid, kThreads, L.total_bytes, s>>>(*m, *rows, d_gout, g_const, d_logp, d_gpart, d_ginput,
+                                            d_gcond, d_loss_acc, scratch);
+  }
   return (int)cudaGetLastError();
 }
