@@ -317,6 +317,26 @@ int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows, const floa
                          const float* d_eps, const float* d_gout, float g_const, float* d_loss,
                          float* d_gpart, float* d_loss_acc, void* stream);
 
+/* ---- multi-GPU: gradient sum over NVLink peer memory (csrc/peer.cu), replacing the NCCL all-reduce +
+ * norm pass of the data-parallel step (reference semantics: clip_grad_norm_ + Adam on the summed
+ * gradient, sbi/inference/trainers/base.py:1181-1187).  Each rank allocates a symmetric buffer
+ * (`peer_alloc`), exports its IPC handle (64 bytes) to the other ranks of the node, imports theirs, and
+ * then calls `peer_sum` once per step with the table of all ranks' buffers (own buffer at [rank]):
+ * d_grad_out = sum over ranks (fixed rank order) of d_grad_local, plus sbi_b200_peer_blocks(n) partials
+ * of sum(g^2) for sbi_b200_adam_clip_step_norm.  The step number is read from d_step[0] (the optimizer's
+ * device counter), so the launch can sit in a CUDA graph. */
+int64_t sbi_b200_peer_bytes(int64_t n_params);
+int sbi_b200_peer_blocks(int64_t n_params);
+void* sbi_b200_peer_alloc(int64_t n_params);
+int sbi_b200_peer_free(void* p);
+int sbi_b200_peer_export(void* p, void* handle64);
+void* sbi_b200_peer_import(const void* handle64);
+int sbi_b200_peer_close(void* p);
+int sbi_b200_peer_sum(const float* d_grad_local, void* const* h_peer_ptrs, int world, int rank,
+                      int64_t n_params, float* d_grad_out, const uint8_t* d_mask, float* d_sumsq_part,
+                      const int32_t* d_step, void* stream);
+int sbi_b200_peer_error(const void* p, int64_t n_params);
+
 /* ---- host-buffer entry points (the end-to-end path a CPU caller binds) ------------------
  * Device staging / optimizer buffers are owned by the caller and passed in a workspace;
  * h_* buffers should be pinned for full PCIe bandwidth.  These calls copy host->device,

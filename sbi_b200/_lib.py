@@ -189,6 +189,16 @@ _EXPORTS = {
     "sbi_b200_nsf_logprob_host": (C.c_int, [C.POINTER(NsfModel), C.POINTER(TrainWs), C.c_void_p,
                                             C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                             C.c_void_p]),
+    "sbi_b200_peer_bytes": (C.c_int64, [C.c_int64]),
+    "sbi_b200_peer_blocks": (C.c_int, [C.c_int64]),
+    "sbi_b200_peer_alloc": (C.c_void_p, [C.c_int64]),
+    "sbi_b200_peer_free": (C.c_int, [C.c_void_p]),
+    "sbi_b200_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sbi_b200_peer_import": (C.c_void_p, [C.c_void_p]),
+    "sbi_b200_peer_close": (C.c_int, [C.c_void_p]),
+    "sbi_b200_peer_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sbi_b200_peer_error": (C.c_int, [C.c_void_p, C.c_int64]),
     "sbi_b200_nsf_logprob_host_tc": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc), C.POINTER(TrainWs),
                                                C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                                C.c_void_p]),

@@ -88,3 +88,65 @@ def rejection_fixed_budget(potential_fn: Callable[[Tensor], Tensor], proposal_sa
     keep = ratio > u[lo:hi].to(device)
     idx = torch.nonzero(keep).reshape(-1) + lo
     return gather_accepted(mine[keep], idx)
+
+
+class PeerGradientSum:
+    """Sum of the per-rank flat gradients over NVLink peer memory, fused with the Σg² partials the
+    clip norm needs (kernel `peer_sum_kernel`, csrc/peer.cu) — the single-node replacement of
+    `allreduce_flat_gradient` + norm pass.  All ranks must be processes on one node with P2P access
+    between their GPUs; construction is collective (handles are exchanged with all_gather_object).
+
+        ex = PeerGradientSum(n_params)                       # once, on every rank
+        ex.sum(grad_local, grad_out, mask, sumsq, opt_step)  # every step, graph-capturable
+    """
+
+    def __init__(self, n_params: int):
+        import ctypes as C
+        from . import _lib as L
+        self._L, self._C = L, C
+        self.lib = L.load()
+        self.rank, self.world = world()
+        self.n = int(n_params)
+        self.own = self.lib.sbi_b200_peer_alloc(self.n)
+        if not self.own:
+            raise RuntimeError("peer buffer allocation failed")
+        h = C.create_string_buffer(64)
+        L.check(self.lib.sbi_b200_peer_export(C.c_void_p(self.own), h), "peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(h.raw))
+        self._imported = []
+        ptrs = (C.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = self.own
+            else:
+                p = self.lib.sbi_b200_peer_import(C.create_string_buffer(handles[r], 64))
+                if not p:
+                    raise RuntimeError(f"rank {self.rank}: cannot map the peer buffer of rank {r} "
+                                       "(no P2P access between the GPUs?)")
+                self._imported.append(p)
+                ptrs[r] = p
+        self._ptrs = ptrs
+        self.n_sumsq = self.lib.sbi_b200_peer_blocks(self.n)
+        dist.barrier()
+
+    def sum(self, grad_local: Tensor, grad_out: Tensor, mask: Optional[Tensor], sumsq: Optional[Tensor],
+            opt_step: Tensor) -> None:
+        L, C = self._L, self._C
+        L.check(self.lib.sbi_b200_peer_sum(L.ptr(grad_local), self._ptrs, self.world, self.rank, self.n,
+                                           L.ptr(grad_out), L.ptr(mask), L.ptr(sumsq), L.ptr(opt_step),
+                                           L.stream_ptr()), "peer_sum")
+
+    def error(self) -> bool:
+        return self.lib.sbi_b200_peer_error(self._C.c_void_p(self.own), self.n) != 0
+
+    def close(self) -> None:
+        if self.own is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier()
+        for p in self._imported:
+            self.lib.sbi_b200_peer_close(self._C.c_void_p(p))
+        dist.barrier()
+        self.lib.sbi_b200_peer_free(self._C.c_void_p(self.own))
+        self.own = None

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_header_symbols_exported(lib):
     from sbi_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "sbi_b200.h")).read()
-    declared = set(re.findall(r"\b(?:int|void\*|void)\s+(sbi_b200_\w+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(?:int64_t|int|void\*|void)\s+(sbi_b200_\w+)\s*\(", hdr))
     assert declared, "no declarations parsed"
     assert declared == set(_lib.exported_symbols())
     for name in declared:
