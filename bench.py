@@ -223,6 +223,14 @@ def run_b200(args):
     mask = est.net._mask
     idx_pool = torch.stack([torch.randperm(n_train, device=dev)[:B] for _ in range(16)])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    # N > 1: the flat gradients are summed over NVLink peer memory by our own kernel (csrc/peer.cu);
+    # SBI_B200_NCCL=1 keeps the NCCL all-reduce instead (no CUDA graph then)
+    peer = None
+    grad_local = grad
+    if world > 1 and os.environ.get("SBI_B200_NCCL", "") != "1":
+        from sbi_b200.parallel import PeerGradientSum
+        peer = PeerGradientSum(P)
+        grad_local = torch.zeros(P, device=dev)
     launches = {"n": 0}
 
     def train_step(i):
@@ -231,7 +239,13 @@ def run_b200(args):
         rows = L.Rows(theta_d.data_ptr(), x_d.data_ptr(), idx.data_ptr(), B, 0)
         L.check(lib.sbi_b200_nsf_vjp(C.byref(m), C.byref(rows), None, -1.0 / B, None, L.ptr(gpart),
                                      None, None, L.ptr(loss_acc), L.stream_ptr()), "vjp")
-        if world > 1:
+        if peer is not None:
+            L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad_local), L.stream_ptr()), "reduce")
+            peer.sum(grad_local, grad, mask, sumsq, step_ctr)
+            L.check(lib.sbi_b200_adam_clip_step_norm(L.ptr(est.flat.data), L.ptr(grad), L.ptr(state),
+                                                     L.ptr(step_ctr), L.ptr(mask), P, 5e-4, 0.9, 0.999, 1e-8,
+                                                     5.0, 1.0 / world, L.ptr(sumsq), peer.n_sumsq, L.stream_ptr()), "adam")
+        elif world > 1:
             L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad), L.stream_ptr()), "reduce")
             dist.all_reduce(grad)
             L.check(lib.sbi_b200_adam_clip_step(L.ptr(est.flat.data), L.ptr(grad), L.ptr(state),
@@ -243,7 +257,7 @@ def run_b200(args):
             L.check(lib.sbi_b200_adam_clip_step_norm(L.ptr(est.flat.data), L.ptr(grad), L.ptr(state),
                                                      L.ptr(step_ctr), L.ptr(mask), P, 5e-4, 0.9, 0.999, 1e-8,
                                                      5.0, 1.0, L.ptr(sumsq), sumsq.shape[0], L.stream_ptr()), "adam")
-        launches["n"] += 3
+        launches["n"] += 4 if peer is not None else 3
 
     def barrier():
         if world > 1:
@@ -258,7 +272,9 @@ def run_b200(args):
     for i in range(W):
         train_step(i)
     torch.cuda.synchronize()
-    if world == 1:
+    if world == 1 or peer is not None:
+        if world > 1:
+            dist.barrier()
         # one CUDA graph per index slot so that replays carry no host launch gaps
         graphs = []
         for i in range(idx_pool.shape[0]):
@@ -274,7 +290,7 @@ def run_b200(args):
         ev[i][0].record()
         if graphs is not None:
             graphs[i % len(graphs)].replay()
-            launches["n"] += 3
+            launches["n"] += 4 if peer is not None else 3
         else:
             train_step(i)
         ev[i][1].record()
@@ -374,11 +390,18 @@ def run_b200(args):
         rows = L.Rows(st_in.data_ptr(), st_c.data_ptr(), None, B, 0)
         L.check(lib.sbi_b200_nsf_vjp(C.byref(mm), C.byref(rows), None, -1.0 / B, None, L.ptr(gpart), None, None,
                                      L.ptr(loss_acc), L.stream_ptr()), "vjp")
-        L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad), L.stream_ptr()), "reduce")
-        dist.all_reduce(grad)
-        L.check(lib.sbi_b200_adam_clip_step(L.ptr(est.flat.data), L.ptr(grad), L.ptr(state), L.ptr(step_ctr),
-                                            L.ptr(mask), P, 5e-4, 0.9, 0.999, 1e-8, 5.0, 1.0 / world,
-                                            L.stream_ptr()), "adam")
+        if peer is not None:
+            L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad_local), L.stream_ptr()), "reduce")
+            peer.sum(grad_local, grad, mask, sumsq, step_ctr)
+            L.check(lib.sbi_b200_adam_clip_step_norm(L.ptr(est.flat.data), L.ptr(grad), L.ptr(state), L.ptr(step_ctr),
+                                                     L.ptr(mask), P, 5e-4, 0.9, 0.999, 1e-8, 5.0, 1.0 / world,
+                                                     L.ptr(sumsq), peer.n_sumsq, L.stream_ptr()), "adam")
+        else:
+            L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad), L.stream_ptr()), "reduce")
+            dist.all_reduce(grad)
+            L.check(lib.sbi_b200_adam_clip_step(L.ptr(est.flat.data), L.ptr(grad), L.ptr(state), L.ptr(step_ctr),
+                                                L.ptr(mask), P, 5e-4, 0.9, 0.999, 1e-8, 5.0, 1.0 / world,
+                                                L.stream_ptr()), "adam")
         h_loss.copy_(loss_acc, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -432,7 +455,9 @@ def run_b200(args):
            "h2d_bytes_per_step": world * B * 2 * DIM * 4, "d2h_bytes_per_step": world * 8,
            "api": "sbi_b200_nsf_train_step_host_async (C ABI, pinned host batch; each step's H2D/D2H inside, "
                   "result of step i read while step i+1 runs)" if world == 1 else
-                  "host batch -> H2D -> vjp -> reduce -> NCCL all-reduce -> clip+Adam -> D2H loss, per rank",
+                  ("host batch -> H2D -> vjp -> reduce -> peer-memory gradient sum (csrc/peer.cu) -> clip+Adam -> D2H "
+                   "loss, per rank" if peer is not None else
+                   "host batch -> H2D -> vjp -> reduce -> NCCL all-reduce -> clip+Adam -> D2H loss, per rank"),
            "log_prob": {"value": world * Rh / lp_e2e_s, "unit": "evals/s", "rows": world * Rh,
                         "api": "sbi_b200_nsf_logprob_host_tc" if tcs is not None else "sbi_b200_nsf_logprob_host",
                         "h2d_bytes_per_step": world * (Rh * DIM * 4 + DIM * 4), "d2h_bytes_per_step": world * Rh * 4}}
@@ -455,7 +480,10 @@ def run_b200(args):
                                    "(BASELINE configs[1]); step = fwd+bwd+clip+Adam on one batch",
                        "global_batch": B * world, "per_gpu_batch": B, "params": real_params,
                        "parallelism": f"dp{world}", "l2": "flushed between timed steps (256 MiB memset, untimed)",
-                       "launch": "cuda-graph per step" if graphs is not None else "eager"},
+                       "launch": "cuda-graph per step" if graphs is not None else "eager",
+                       "gradient_exchange": ("none" if world == 1 else
+                                             "peer-memory sum kernel over NVLink (csrc/peer.cu)" if peer is not None
+                                             else "NCCL all-reduce")},
             "roofline": {"bound": "hbm", "kernel": "nsf_vjp_kernel<32,2,2,true>", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": traffic.get("nsf_vjp_kernel", {}).get("dram_bytes_per_launch"),
@@ -473,6 +501,10 @@ def run_b200(args):
             "step_ms_minmax": [min(ms_steps), max(ms_steps)],
         }
         print(json.dumps(line))
+    if peer is not None:
+        if peer.error():
+            raise RuntimeError("peer gradient exchange timed out")
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 

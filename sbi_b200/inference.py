@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import time
 import warnings
 from copy import deepcopy
@@ -75,6 +76,16 @@ class _FlowTrainer:
         self._dist = None   # (rank, world) when data-parallel
 
     # ------------------------------------------------------------------ data
+    def data_parallel(self):
+        """Train data-parallel over the initialised `torch.distributed` group (one process per
+        GPU): every rank appends ITS OWN simulations, rank 0's initial network is
+        broadcast when `train()` starts, each step's flat gradients are summed over the ranks
+        (NVLink peer-memory kernel on one node, NCCL otherwise) and every rank applies the same
+        deterministic clip + Adam, so the replicas stay bit-identical."""
+        from . import parallel
+        self._dist = parallel.world()
+        return self
+
     def append_simulations(self, theta: Tensor, x: Tensor, proposal=None,
                            exclude_invalid_x: Optional[bool] = None, data_device: Optional[str] = None):
         """Store simulations (npe_base.py:188-299): float32 only, rows with NaN/Inf in x are
@@ -139,6 +150,11 @@ class _FlowTrainer:
             del th_cpu, x_cpu
         net = self._neural_net.to(dev)
         self._neural_net = net
+        if self._dist is not None and self._dist[1] > 1 and not resume_training:
+            # replicas start identical: parameters AND standardisation statistics of rank 0
+            for t in list(net.parameters()) + list(net.buffers()):
+                torch.distributed.broadcast(t.data, 0)
+            net._cache.clear()
         if not isinstance(net, FlowEstimator):
             raise TypeError(f"{type(self).__name__} needs an sbi_b200 flow estimator, "
                             f"got {type(net).__name__}")
@@ -177,6 +193,13 @@ class _FlowTrainer:
         stats = torch.zeros(4, dtype=torch.float32, device=dev)   # train nll sum, bad, val nll sum, val bad
         mask = net.net._mask
         max_norm = float(clip_max_norm) if clip_max_norm is not None else 0.0
+        # data-parallel on one node: sum the gradients with our peer-memory kernel (graph-capturable);
+        # SBI_B200_NCCL=1 keeps the NCCL all-reduce (eager launches)
+        peer, grad_local = None, grad
+        if world > 1 and os.environ.get("SBI_B200_NCCL", "") != "1" and net.fam.name == "nsf":
+            from .parallel import PeerGradientSum
+            peer = PeerGradientSum(P)
+            grad_local = torch.zeros(P, dtype=torch.float32, device=dev)
 
         def run_epoch():
             """All kernels of one epoch on the current stream (graph-capturable)."""
@@ -188,7 +211,15 @@ class _FlowTrainer:
                 L.check(net.fam.fn("vjp")(C.byref(m_tr), C.byref(rows), None, -1.0 / (B * world),
                                           None, L.ptr(gpart), None, None, L.ptr(loss_acc),
                                           L.stream_ptr()), "flow_vjp")
-                if world > 1:   # the clip norm must be taken on the all-reduced gradient
+                if peer is not None:   # gradients summed over NVLink peer memory (csrc/peer.cu)
+                    L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad_local),
+                                                         L.stream_ptr()), "reduce_partials")
+                    peer.sum(grad_local, grad, mask, sumsq, self._opt_step)
+                    L.check(lib.sbi_b200_adam_clip_step_norm(
+                        L.ptr(net.flat.data), L.ptr(grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
+                        L.ptr(mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.ptr(sumsq),
+                        peer.n_sumsq, L.stream_ptr()), "adam_clip_step")
+                elif world > 1:   # the clip norm must be taken on the all-reduced gradient
                     L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad),
                                                          L.stream_ptr()), "reduce_partials")
                     torch.distributed.all_reduce(grad)
@@ -228,7 +259,7 @@ class _FlowTrainer:
 
         # warm-up (also sets kernel attributes) on a throw-away copy of the state, then capture
         graph = None
-        if world == 1:
+        if world == 1 or peer is not None:
             snap = (net.flat.data.clone(), self._opt_state.clone(), self._opt_step.clone())
             fill_perms()
             side = torch.cuda.Stream()
@@ -287,6 +318,11 @@ class _FlowTrainer:
         self._summary["epochs_trained"].append(self.epoch)
         self._summary["best_validation_loss"].append(self._best_val_loss)
         net.zero_grad(set_to_none=True)
+        if peer is not None:
+            timed_out = peer.error()
+            peer.close()
+            if timed_out:
+                raise RuntimeError("peer-memory gradient exchange timed out (a rank fell behind or died)")
         return deepcopy(net)
 
     @property
