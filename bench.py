@@ -227,10 +227,11 @@ def run_b200(args):
     # SBI_B200_NCCL=1 keeps the NCCL all-reduce instead (no CUDA graph then)
     peer = None
     grad_local = grad
-    if world > 1 and os.environ.get("SBI_B200_NCCL", "") != "1":
-        from sbi_b200.parallel import PeerGradientSum
-        peer = PeerGradientSum(P)
-        grad_local = torch.zeros(P, device=dev)
+    if world > 1:
+        from sbi_b200.parallel import make_gradient_exchange
+        peer = make_gradient_exchange(P)          # None -> NCCL all-reduce
+        if peer is not None:
+            grad_local = torch.zeros(P, device=dev)
     launches = {"n": 0}
 
     def train_step(i):

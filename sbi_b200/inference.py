@@ -196,10 +196,11 @@ class _FlowTrainer:
         # data-parallel on one node: sum the gradients with our peer-memory kernel (graph-capturable);
         # SBI_B200_NCCL=1 keeps the NCCL all-reduce (eager launches)
         peer, grad_local = None, grad
-        if world > 1 and os.environ.get("SBI_B200_NCCL", "") != "1" and net.fam.name == "nsf":
-            from .parallel import PeerGradientSum
-            peer = PeerGradientSum(P)
-            grad_local = torch.zeros(P, dtype=torch.float32, device=dev)
+        if world > 1:
+            from .parallel import make_gradient_exchange
+            peer = make_gradient_exchange(P)      # None -> NCCL all-reduce, eager launches
+            if peer is not None:
+                grad_local = torch.zeros(P, dtype=torch.float32, device=dev)
 
         def run_epoch():
             """All kernels of one epoch on the current stream (graph-capturable)."""

@@ -107,11 +107,14 @@ class PeerGradientSum:
         self.lib = L.load()
         self.rank, self.world = world()
         self.n = int(n_params)
+        # Every collective below runs on every rank whatever happened locally; failures are
+        # collected and agreed on at the end, so that either all ranks get a working exchange or
+        # all ranks raise (and can fall back to NCCL together).
+        ok = 1
         self.own = self.lib.sbi_b200_peer_alloc(self.n)
-        if not self.own:
-            raise RuntimeError("peer buffer allocation failed")
         h = C.create_string_buffer(64)
-        L.check(self.lib.sbi_b200_peer_export(C.c_void_p(self.own), h), "peer_export")
+        if not self.own or self.lib.sbi_b200_peer_export(C.c_void_p(self.own), h) != 0:
+            ok = 0
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(h.raw))
         self._imported = []
@@ -119,16 +122,21 @@ class PeerGradientSum:
         for r in range(self.world):
             if r == self.rank:
                 ptrs[r] = self.own
-            else:
+            elif ok:
                 p = self.lib.sbi_b200_peer_import(C.create_string_buffer(handles[r], 64))
                 if not p:
-                    raise RuntimeError(f"rank {self.rank}: cannot map the peer buffer of rank {r} "
-                                       "(no P2P access between the GPUs?)")
-                self._imported.append(p)
-                ptrs[r] = p
+                    ok = 0
+                else:
+                    self._imported.append(p)
+                    ptrs[r] = p
         self._ptrs = ptrs
         self.n_sumsq = self.lib.sbi_b200_peer_blocks(self.n)
-        dist.barrier()
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError("peer-memory gradient exchange unavailable (allocation, IPC export or P2P "
+                               "mapping failed on at least one rank)")
 
     def sum(self, grad_local: Tensor, grad_out: Tensor, mask: Optional[Tensor], sumsq: Optional[Tensor],
             opt_step: Tensor) -> None:
@@ -141,12 +149,27 @@ class PeerGradientSum:
         return self.lib.sbi_b200_peer_error(self._C.c_void_p(self.own), self.n) != 0
 
     def close(self) -> None:
-        if self.own is None:
+        if getattr(self, "_closed", False):
             return
+        self._closed = True
         torch.cuda.synchronize()
         dist.barrier()
         for p in self._imported:
             self.lib.sbi_b200_peer_close(self._C.c_void_p(p))
+        self._imported = []
         dist.barrier()
-        self.lib.sbi_b200_peer_free(self._C.c_void_p(self.own))
+        if self.own:
+            self.lib.sbi_b200_peer_free(self._C.c_void_p(self.own))
         self.own = None
+
+
+def make_gradient_exchange(n_params: int) -> Optional[PeerGradientSum]:
+    """PeerGradientSum if the group has more than one rank, the ranks can map each other's memory and
+    SBI_B200_NCCL != 1; otherwise None (callers then use `allreduce_flat_gradient`).  Collective."""
+    import os
+    if world()[1] <= 1 or os.environ.get("SBI_B200_NCCL", "") == "1":
+        return None
+    try:
+        return PeerGradientSum(n_params)
+    except RuntimeError:
+        return None
