@@ -13,6 +13,9 @@ Fixtures (small, committed):
   maf_d3c2.pt     reference `posterior_nn("maf")` (theta-dim 3, x-dim 2; BASELINE configs[0]): state_dict,
                   permutations, log_prob and inverse outputs.
   searchsorted.pt the reference's bin-search known-answer test vectors (tests/torchutils_test.py:135-157).
+  ratio_d4x6.pt   reference `classifier_nn("resnet")` (theta-dim 4, x-dim 6): state_dict, pairs, logits.
+  fm_d5c3.pt      reference `posterior_flow_nn("mlp")` (theta-dim 5, x-dim 3): state_dict, inputs, times,
+                  velocity field, and the flow-matching loss for given (t, theta_1).
 """
 import os
 import sys
@@ -85,6 +88,45 @@ def train_fixture():
                 train_indices=inf.train_indices, val_indices=inf.val_indices)
 
 
+def ratio_fixture(Dt, Dx, seed, n=400):
+    from sbi.neural_nets import classifier_nn
+    g = torch.Generator().manual_seed(seed)
+    theta = 0.7 * torch.randn(n, Dt, generator=g) + 0.3
+    x = 1.3 * torch.randn(n, Dx, generator=g) - 0.2
+    torch.manual_seed(seed)
+    est = classifier_nn("resnet")(theta, x)
+    with torch.no_grad():
+        for name, p in est.named_parameters():
+            p.add_(0.1 * torch.randn(p.shape, generator=g))
+        th, xx = theta[:96] * 1.2, x[:96]
+        logits = est(th, xx)
+        logits_shared = est(th, xx[:1].expand(96, -1))
+    return dict(state_dict=est.state_dict(), theta=theta, x=x, th=th, xx=xx, logits=logits,
+                logits_shared=logits_shared, Dt=Dt, Dx=Dx, seed=seed)
+
+
+def fm_fixture(D, C, seed, n=500):
+    from sbi.neural_nets import posterior_flow_nn
+    g = torch.Generator().manual_seed(seed)
+    theta = 0.7 * torch.randn(n, D, generator=g) + 0.3
+    x = 1.3 * torch.randn(n, C, generator=g) - 0.2
+    torch.manual_seed(seed)
+    est = posterior_flow_nn("mlp")(theta, x)
+    with torch.no_grad():
+        for name, p in est.named_parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=g))
+        inp, cond = theta[:64] * 1.1, x[:64]
+        t = torch.rand(64, generator=g)
+        v = est(inp, cond, t)
+        v_shared = est(inp, cond[:1], torch.tensor(0.37))
+        torch.manual_seed(seed + 1)
+        theta_1 = torch.randn_like(inp)          # the draw est.loss makes right after `times`
+        torch.manual_seed(seed + 1)
+        loss = est.loss(inp, cond, times=t)
+    return dict(state_dict=est.state_dict(), theta=theta, x=x, inp=inp, cond=cond, t=t, v=v,
+                v_shared=v_shared, theta_1=theta_1, loss=loss, D=D, C=C, seed=seed)
+
+
 def searchsorted_fixture():
     """Exactly the cases of /root/reference/tests/torchutils_test.py:135-157, evaluated by the
     reference's own `sbi.utils.torchutils.searchsorted` (expected there: arange(0, 9))."""
@@ -106,5 +148,7 @@ if __name__ == "__main__":
     torch.save(train_fixture(), os.path.join(HERE, "npe_train.pt"))
     torch.save(maf_fixture(3, 2, 9), os.path.join(HERE, "maf_d3c2.pt"))
     torch.save(searchsorted_fixture(), os.path.join(HERE, "searchsorted.pt"))
+    torch.save(ratio_fixture(4, 6, 12), os.path.join(HERE, "ratio_d4x6.pt"))
+    torch.save(fm_fixture(5, 3, 13), os.path.join(HERE, "fm_d5c3.pt"))
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -143,3 +143,26 @@ def test_spline_is_monotone_and_identity_outside():
     # central difference of y against exp(logabsdet): O(h) only at the C1 knots
     err = (num.log() - ld[1:-1])[inside].abs()
     assert torch.quantile(err, 0.995) < 5e-3   # minimum-width bins (1e-3) are under-resolved by the grid
+
+
+def test_port_reproduces_reference_ratio_fixture():
+    """oracle port of the NRE `resnet` classifier == the reference's own logits (fixture generated by
+    tests/golden/make_golden.py from the unmodified reference)."""
+    g = torch.load(os.path.join(GOLD, "ratio_d4x6.pt"))
+    est = sbi_port.build_resnet_classifier(g["theta"], g["x"])
+    est.load_state_dict(g["state_dict"])
+    with torch.no_grad():
+        assert torch.equal(est(g["th"], g["xx"]), g["logits"])
+        assert torch.equal(est(g["th"], g["xx"][:1].expand(96, -1)), g["logits_shared"])
+
+
+def test_port_reproduces_reference_flow_matching_fixture():
+    """oracle port of the flow-matching estimator == the reference's velocity field and loss."""
+    g = torch.load(os.path.join(GOLD, "fm_d5c3.pt"))
+    est = sbi_port.build_flow_matching_estimator(g["theta"], g["x"])
+    est.load_state_dict(g["state_dict"])
+    with torch.no_grad():
+        assert torch.allclose(est(g["inp"], g["cond"], g["t"]), g["v"], atol=1e-6, rtol=1e-5)
+        assert torch.allclose(est(g["inp"], g["cond"][:1], torch.tensor(0.37)), g["v_shared"], atol=1e-6, rtol=1e-5)
+        assert torch.allclose(est.loss(g["inp"], g["cond"], times=g["t"], theta_1=g["theta_1"]), g["loss"],
+                              atol=1e-6, rtol=1e-5)
