@@ -478,24 +478,71 @@ class NRE_B(_FlowTrainer):
                 return True
             return False
 
+        # One CUDA graph per optimisation step and one per validation step: a step is ~15 small
+        # launches (contrastive draws, index gathers, logits kernel, logsumexp, VJP kernel, reduce,
+        # clip+Adam) that the host cannot issue as fast as the GPU runs them at the default batch
+        # of 200.  The batch indices come from a static buffer filled before each replay; random
+        # draws inside the graph use torch's graph-safe Philox offsets.
+        idx_buf = torch.zeros(B, dtype=torch.int64, device=dev)
+        vidx_buf = torch.zeros(max(Bv, 1), dtype=torch.int64, device=dev)
+        train_sum = torch.zeros((), device=dev)
+        val_sum = torch.zeros((), device=dev)
+
+        def train_step():
+            net.net.flat.grad = None
+            loss = self._loss_on(net, idx_buf, num_atoms)
+            loss.backward()
+            train_sum.add_(loss.detach())
+            L.check(lib.sbi_b200_adam_clip_step(
+                L.ptr(net.flat.data), L.ptr(net.flat.grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
+                L.ptr(net.net._mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.stream_ptr()),
+                "adam_clip_step")
+
+        def val_step():
+            with torch.no_grad():
+                val_sum.add_(self._loss_on(net, vidx_buf, num_atoms))
+
+        g_train = g_val = None
+        if os.environ.get("SBI_B200_NRE_GRAPH", "1") != "0" and B - 1 <= 4096 and steps > 0:
+            snap = (net.flat.data.clone(), self._opt_state.clone(), self._opt_step.clone())
+            idx_buf.copy_(train_idx[:B])
+            if vsteps > 0:
+                vidx_buf.copy_(val_idx[:Bv])
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up outside capture (allocations, kernel attributes)
+                for _ in range(3):
+                    train_step()
+                if vsteps > 0:
+                    val_step()
+            torch.cuda.current_stream().wait_stream(side)
+            g_train = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_train):
+                train_step()
+            if vsteps > 0:
+                g_val = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_val):
+                    val_step()
+            net.flat.data.copy_(snap[0]); self._opt_state.copy_(snap[1]); self._opt_step.copy_(snap[2])
+
         while self.epoch <= max_num_epochs and not converged():
             t0 = time.time()
             perm = train_idx[torch.randperm(n_train, device=dev)]
-            train_sum = torch.zeros((), device=dev)
+            train_sum.zero_()
             for s in range(steps):
-                net.net.flat.grad = None
-                loss = self._loss_on(net, perm[s * B:(s + 1) * B], num_atoms)
-                loss.backward()
-                train_sum += loss.detach()
-                L.check(lib.sbi_b200_adam_clip_step(
-                    L.ptr(net.flat.data), L.ptr(net.flat.grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
-                    L.ptr(net.net._mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.stream_ptr()),
-                    "adam_clip_step")
-            val_sum = torch.zeros((), device=dev)
-            with torch.no_grad():
-                vperm = val_idx[torch.randperm(n_val, device=dev)]
-                for s in range(vsteps):
-                    val_sum += self._loss_on(net, vperm[s * Bv:(s + 1) * Bv], num_atoms)
+                idx_buf.copy_(perm[s * B:(s + 1) * B])
+                if g_train is not None:
+                    g_train.replay()
+                else:
+                    train_step()
+            val_sum.zero_()
+            vperm = val_idx[torch.randperm(n_val, device=dev)] if vsteps > 0 else None
+            for s in range(vsteps):
+                vidx_buf.copy_(vperm[s * Bv:(s + 1) * Bv])
+                if g_val is not None:
+                    g_val.replay()
+                else:
+                    val_step()
             tl, vl = float(train_sum.item()), float(val_sum.item())
             if not (math.isfinite(tl) and math.isfinite(vl)):
                 raise AssertionError("NaN/Inf present in NRE-B loss.")
