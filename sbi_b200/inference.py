@@ -663,12 +663,16 @@ class FMPE(_FlowTrainer):
                 return True
             return False
 
-        while self.epoch <= max_num_epochs and not converged():
-            t0 = time.time()
-            perm = train_idx[torch.randperm(n_train, device=dev)]
+        # One CUDA graph per epoch (single GPU): every step is [t ~ U, theta_1 ~ N draws, fused loss
+        # fwd+bwd kernel, reduce, clip+Adam]; the epoch's row permutations live in static buffers.
+        perm_buf = torch.zeros(max(steps * B, 1), dtype=torch.int64, device=dev)
+        vperm_buf = torch.zeros(max(vsteps * Bv, 1), dtype=torch.int64, device=dev)
+        stats = torch.zeros(4, dtype=torch.float32, device=dev)     # train loss sum, bad, val loss sum, bad
+
+        def run_epoch():
             loss_acc.zero_()
             for s in range(steps):
-                idx = perm[s * B:(s + 1) * B].contiguous()
+                idx = perm_buf[s * B:(s + 1) * B]
                 tms = torch.rand(B, device=dev)
                 eps = torch.randn(B, D, device=dev)
                 _, gpart, n_part = net.loss_raw(self._theta, x2d, tms, eps, index=idx, g_const=1.0 / (B * world),
@@ -679,19 +683,46 @@ class FMPE(_FlowTrainer):
                 L.check(lib.sbi_b200_adam_clip_step(L.ptr(net.flat.data), L.ptr(grad), L.ptr(self._opt_state),
                                                     L.ptr(self._opt_step), L.ptr(net.net._mask), P, learning_rate,
                                                     0.9, 0.999, 1e-8, max_norm, 1.0, L.stream_ptr()), "adam")
-            train_stats = loss_acc.clone()
+            stats[0:2].copy_(loss_acc)
             # validation: every batch evaluated at all validation times (:524-543); g = 0 -> loss only
             loss_acc.zero_()
             if vsteps > 0:
-                vperm = val_idx[torch.randperm(n_val, device=dev)]
                 nt = vt.shape[0]
                 for s in range(vsteps):
-                    idx = vperm[s * Bv:(s + 1) * Bv].repeat(nt).contiguous()
+                    idx = vperm_buf[s * Bv:(s + 1) * Bv].repeat(nt).contiguous()
                     tms = vt.repeat_interleave(Bv).contiguous()
                     eps = torch.randn(Bv * nt, D, device=dev)
                     net.loss_raw(self._theta, x2d, tms, eps, index=idx, g_const=0.0, loss_acc=loss_acc, want_loss=False)
-            tl, tb = train_stats.tolist()
-            vl, vb = loss_acc.tolist()
+            stats[2:4].copy_(loss_acc)
+
+        def fill_perms():
+            perm_buf[:steps * B].copy_(train_idx[torch.randperm(n_train, device=dev)[:steps * B]])
+            if vsteps > 0:
+                vperm_buf[:vsteps * Bv].copy_(val_idx[torch.randperm(n_val, device=dev)[:vsteps * Bv]])
+
+        graph = None
+        if world == 1 and os.environ.get("SBI_B200_FMPE_GRAPH", "1") != "0" and steps > 0:
+            snap = (net.flat.data.clone(), self._opt_state.clone(), self._opt_step.clone())
+            fill_perms()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run_epoch()
+            torch.cuda.current_stream().wait_stream(side)
+            net.flat.data.copy_(snap[0]); self._opt_state.copy_(snap[1]); self._opt_step.copy_(snap[2])
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run_epoch()
+            net.flat.data.copy_(snap[0]); self._opt_state.copy_(snap[1]); self._opt_step.copy_(snap[2])
+
+        while self.epoch <= max_num_epochs and not converged():
+            t0 = time.time()
+            fill_perms()
+            if graph is not None:
+                graph.replay()
+            else:
+                run_epoch()
+            tl, tb, vl, vb = stats.tolist()      # the one host sync of the epoch
             if tb > 0 or vb > 0:
                 raise AssertionError("NaN/Inf present in FMPE loss.")
             train_loss = tl / (steps * B)
