@@ -1,5 +1,6 @@
-// Tensor-core bulk evaluation of the neural spline flow: NFlowsFlow.log_prob
-// (/root/reference/sbi/neural_nets/estimators/nflows_flow.py:77-97) for large row counts.
+// Tensor-core bulk evaluation and sampling of the neural spline flow: NFlowsFlow.log_prob /
+// inverse_transform / sample (/root/reference/sbi/neural_nets/estimators/nflows_flow.py:42-128)
+// from 1024 rows.
 //
 // Same function, same parameter buffer and same evaluation order outside the linears as
 // nsf_logprob_kernel (nsf.cu); the ResidualNet linears (nflows ResidualNet, restated in
@@ -7,9 +8,10 @@
 // tensor cores:
 //
 //   * one CTA = 8 warps (128 rows = 128 TMEM lanes, two threads per row splitting the columns
-//     of every epilogue), two CTAs per SM (256 TMEM columns each); thread 0 issues the MMAs
-//     and, right behind them, the TMA copy of the next stage's weights;
-//   * tcgen05.mma kind::tf32, M = 128, issued by one thread; A (activations) is read from TMEM,
+//     of every epilogue), two CTAs per SM (256 TMEM columns each); the warps take turns issuing
+//     the MMAs of a stage (whole warp converged, one elected lane) and the TMA copies of the
+//     weight stages (tc_common.cuh);
+//   * tcgen05.mma kind::tf32, M = 128; A (activations) is read from TMEM,
 //     where the row threads put it with tcgen05.st after splitting every fp32 value into
 //     hi = tf32(x) and lo = x - hi; B (weights, pre-split hi/lo and pre-arranged in the K-major
 //     no-swizzle UMMA layout by tc_pack_kernel) is streamed by TMA bulk copies into a
@@ -18,8 +20,10 @@
 //   * the context is a K-extension of the hidden operand: A columns are
 //     [ hidden (H) | context (C) | 0 ], so the GLU gate W_c ctx is one more small MMA on the
 //     same operand and the context never has to be re-staged;
-//   * spline, LU and base density are per-thread code on the thread's own row, using the very
-//     same rqs.cuh routines as the SIMT kernels.
+//   * spline, LU (register-resident row against zero-padded 16x16 factors) and base density are
+//     per-thread code on the thread's own row; the gate's sigmoid is evaluated while W_1 relu(h)
+//     is on the tensor core and the spline of final-layer pass p while pass p+1 is computed;
+//   * the same kernel template runs the sampling direction (layers T-1..0, LU^-1, inverse spline).
 //
 // TMEM columns of a CTA:  [0,64) A_hi | [64,128) A_lo | [128,192) D | [192,256) G (GLU gate);
 // the final layer's spline parameters P (32 columns per feature, 2 features per pass)

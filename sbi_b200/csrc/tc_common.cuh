@@ -13,7 +13,7 @@ namespace tc {
 
 constexpr int kRows = 128;        // rows per tile
 constexpr int kRowThreads = 256;  // two threads per row (column halves)
-constexpr int kThreads = 256;     // 8 row warps; thread 0 also issues the MMAs and the TMA copies
+constexpr int kThreads = 256;     // 8 row warps, which also take turns issuing MMAs and TMA copies
 constexpr int kLuMax = 16;        // LULinear runs on register-resident rows of <= 16 features
 constexpr int kSlots = 3;         // weight ring: up to two stages in use + one prefetched
 constexpr int kCols = 256;        // TMEM columns per CTA
