@@ -96,3 +96,10 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_gradient_exchange_is_off_without_a_process_group():
+    """Single process: no peer exchange object, callers keep the plain path (no GPU touched)."""
+    assert parallel.world() == (0, 1)
+    assert parallel.make_gradient_exchange(1000) is None
+    assert parallel.shard_range(10, 0, 1) == (0, 10)
