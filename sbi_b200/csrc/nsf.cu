@@ -635,7 +635,7 @@ extern "C" int sbi_b200_nsf_vjp_parts(int64_t R) {
 }
 
 // Scratch for the activation spill of the VJP kernel: one slab per (CTA, layer), owned by the
-// library and grown on demand.  It cannot be (re)allocated while the stream is being captured into
+// library and grown on demand (old, smaller buffers stay allocated).  It cannot be (re)allocated while the stream is being captured into
 // a CUDA graph; then -- or with SBI_B200_VJP_SPILL=0 -- the kernel recomputes instead.
 static float* g_vjp_scratch = nullptr;
 static size_t g_vjp_scratch_bytes = 0;
@@ -651,7 +651,8 @@ static float* vjp_scratch(size_t bytes, cudaStream_t s) {
   if (g_vjp_scratch && dev == g_vjp_scratch_dev && bytes <= g_vjp_scratch_bytes) return g_vjp_scratch;
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
-  if (g_vjp_scratch && dev == g_vjp_scratch_dev) cudaFree(g_vjp_scratch);
+  // a smaller buffer handed out earlier is NOT freed: a CUDA graph captured with it may still be
+  // replayed (growth happens at most a few times per process, with model size)
   g_vjp_scratch = nullptr;
   g_vjp_scratch_bytes = 0;
   float* p = nullptr;
