@@ -113,6 +113,11 @@ int sbi_b200_sumsq_blocks(int64_t n_params);
 int sbi_b200_reduce_partials_norm(const float* d_gpart, int n_part, int64_t n_params, float* d_grad,
                                   const uint8_t* d_mask, float* d_sumsq_part, void* stream);
 
+/* Epoch statistics of a validation pass (sbi/inference/trainers/base.py:1195-1225 followed by
+ * assert_all_finite): d_out2[0] = -sum of the finite entries of d_logp (n), d_out2[1] = number of
+ * non-finite entries.  One launch, fixed summation order. */
+int sbi_b200_nll_stats(const float* d_logp, int64_t n, float* d_out2, void* stream);
+
 /* clip_grad_norm_(max_norm) + Adam (torch defaults, no weight decay), in place.
  *   d_state: [m (n) | v (n)] ; d_step: int32 device counter (incremented here);
  *   grad_scale multiplies the gradient first (e.g. 1/world_size after an all-reduce);
@@ -323,8 +328,10 @@ int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows, const floa
  * (`peer_alloc`), exports its IPC handle (64 bytes) to the other ranks of the node, imports theirs, and
  * then calls `peer_sum` once per step with the table of all ranks' buffers (own buffer at [rank]):
  * d_grad_out = sum over ranks (fixed rank order) of d_grad_local, plus sbi_b200_peer_blocks(n) partials
- * of sum(g^2) for sbi_b200_adam_clip_step_norm.  The step number is read from d_step[0] (the optimizer's
- * device counter), so the launch can sit in a CUDA graph. */
+ * of sum(g^2) for sbi_b200_adam_clip_step_norm.  The step number that tags the flags is read from the
+ * exchange's own device counter inside the symmetric buffer (d_step == NULL; advanced by the kernel, never
+ * rewound) or from d_step[0] (a caller-owned counter, e.g. the optimizer's), so the launch can sit in a
+ * CUDA graph. */
 int64_t sbi_b200_peer_bytes(int64_t n_params);
 int sbi_b200_peer_blocks(int64_t n_params);
 void* sbi_b200_peer_alloc(int64_t n_params);

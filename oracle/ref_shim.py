@@ -9,8 +9,9 @@ library ``nflows==0.14`` is absent and not installable offline, so this module
   access on a stub returns another stub / a dummy class, so ``from x import Y`` works;
 * puts /root/reference on ``sys.path``.
 
-Used only by ``tests/golden/make_golden.py`` (fixture generation) and by CPU tests that
-are skipped when /root/reference does not exist (e.g. on the GPU box).
+Used by ``tests/golden/make_golden.py`` (fixture generation), by tests that are skipped when
+no copy of the reference exists, and by ``bench.py --impl reference``.  On the GPU box the
+reference is the pip-installed copy under ``baseline/_ref`` (same files, unmodified).
 """
 import importlib
 import importlib.abc
@@ -19,7 +20,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SBI_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    """/root/reference in the build container; on the GPU box the unmodified reference package
+    installed by `pip install --no-deps --target baseline/_ref /root/reference` (git-ignored,
+    travels with the gpurun snapshot)."""
+    for c in (os.environ.get("SBI_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if c and os.path.isdir(os.path.join(c, "sbi")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 _STUB_ROOTS = ("zuko", "pyro", "matplotlib", "skorch", "pymc", "arviz", "tabpfn",
                "pytest_harvest", "torchtestcase")

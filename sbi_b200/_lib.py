@@ -166,6 +166,7 @@ _EXPORTS = {
     "sbi_b200_slice_step": (C.c_int, [C.POINTER(SliceChains), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_reduce_partials": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                            C.c_void_p]),
+    "sbi_b200_nll_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "sbi_b200_sumsq_blocks": (C.c_int, [C.c_int64]),
     "sbi_b200_reduce_partials_norm": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),
@@ -245,15 +246,26 @@ def check(rc: int, what: str):
     raise SbiB200Error(f"{what}: CUDA error {rc}")
 
 
+_active_device = None    # device of the tensors the next kernel launch works on
+
+
 def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """torch's current stream ON THE DEVICE OF THE TENSORS last passed to `require_cuda` (every
+    launch path validates its parameters / inputs with it first), not on whatever device happens
+    to be current: an estimator on cuda:1 launches on cuda:1's stream while cuda:0 is current.
+    The C entry points make that device current themselves (csrc/device.cuh)."""
+    if _active_device is None:
+        return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(_active_device).cuda_stream
 
 
 def require_cuda(t: torch.Tensor, name: str):
+    global _active_device
     if not t.is_cuda:
         raise RuntimeError(
             f"sbi_b200: `{name}` lives on {t.device}; the kernels only run on a CUDA (sm_100a) "
             "device and there is no CPU fallback")
+    _active_device = t.device
     return t
 
 

@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "stages.cuh"
+#include "device.cuh"
 
 namespace sbi {
 
@@ -480,16 +481,7 @@ fm_vjp_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sb
 
 using namespace sbi;
 
-static int fm_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaDeviceProp p;
-    n = (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess)
-            ? p.multiProcessorCount : 148;
-  }
-  return n;
-}
+static int fm_num_sms() { return sbi::dev_num_sms(); }
 
 static int fm_check(const sbi_fm_model* m) {
   if (!m || !m->d_params || !m->d_tab || !m->d_stats) return SBI_EINVAL;
@@ -505,7 +497,8 @@ static int fm_check(const sbi_fm_model* m) {
 
 template <int ID, class K>
 static int fm_set_smem(K kernel, int bytes) {
-  static int granted = 0;
+  static int granted_[sbi::kMaxDev] = {0};
+  int& granted = granted_[sbi::cur_dev()];
   if (bytes > 227 * 1024) return SBI_ESMEM;
   if (bytes <= granted) return 0;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -516,6 +509,7 @@ static int fm_set_smem(K kernel, int bytes) {
 
 extern "C" int sbi_b200_fm_forward(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
                                    int32_t time_shared, float* d_v, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   int rc = fm_check(m);
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_time || !d_v) return SBI_EINVAL;
@@ -538,6 +532,7 @@ extern "C" int sbi_b200_fm_vjp_parts(int64_t R) {
 extern "C" int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
                                     const float* d_eps, const float* d_gout, float g_const, float* d_loss,
                                     float* d_gpart, float* d_loss_acc, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   int rc = fm_check(m);
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 1 || !d_time || !d_eps || !d_gpart) return SBI_EINVAL;

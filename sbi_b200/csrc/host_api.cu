@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/sbi_b200.h"
+#include "device.cuh"
 
 #define CK(x)                            \
   do {                                   \
@@ -31,6 +32,7 @@ extern "C" int sbi_b200_nsf_train_step_host(const sbi_nsf_model* m, const sbi_tr
                                             const float* h_input, const float* h_cond, int64_t B,
                                             float lr, float beta1, float beta2, float eps,
                                             float max_norm, float* h_loss_out, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !ws || !h_input || !h_cond || !h_loss_out || B < 1 || B > ws->cap_rows)
     return SBI_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
@@ -56,6 +58,7 @@ extern "C" int sbi_b200_nsf_train_step_host(const sbi_nsf_model* m, const sbi_tr
 extern "C" int sbi_b200_nsf_logprob_host(const sbi_nsf_model* m, const sbi_train_ws* ws,
                                          const float* h_input, const float* h_cond, int64_t R,
                                          int cond_shared, float* h_logp, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !ws || !h_input || !h_cond || !h_logp || R < 1 || R > ws->cap_rows) return SBI_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaMemcpyAsync(ws->d_input, h_input, sizeof(float) * R * m->D, cudaMemcpyHostToDevice, s));
@@ -82,6 +85,7 @@ extern "C" int sbi_b200_nsf_logprob_host_tc(const sbi_nsf_model* m, const sbi_ns
                                             const sbi_train_ws* ws, const float* h_input,
                                             const float* h_cond, int64_t R, int cond_shared,
                                             float* h_logp, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !tc || !ws || !h_input || !h_cond || !h_logp || R < 1 || R > ws->cap_rows) return SBI_EINVAL;
   if (!sbi_b200_nsf_tc_supported(m, tc)) return SBI_ESMEM;
   static cudaStream_t ss[2] = {nullptr, nullptr};
@@ -146,6 +150,7 @@ extern "C" void* sbi_b200_pipe_create(void) {
 }
 
 extern "C" void sbi_b200_pipe_destroy(void* pipe) {
+  sbi::DeviceGuard dev_guard_(pipe);
   SbiPipe* p = static_cast<SbiPipe*>(pipe);
   if (!p) return;
   for (int i = 0; i < 2; ++i) {
@@ -170,6 +175,7 @@ extern "C" int sbi_b200_nsf_train_step_host_async(const sbi_nsf_model* m, const 
                                                   const float* h_input, const float* h_cond, int64_t B,
                                                   float lr, float beta1, float beta2, float eps,
                                                   float max_norm, float* h_loss_prev, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   SbiPipe* p = static_cast<SbiPipe*>(pipe);
   if (!m || !ws || !p || !h_input || !h_cond || B < 1 || B > ws->cap_rows) return SBI_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
@@ -196,6 +202,7 @@ extern "C" int sbi_b200_nsf_train_step_host_async(const sbi_nsf_model* m, const 
 }
 
 extern "C" int sbi_b200_pipe_drain(void* pipe, float* h_loss_last) {
+  sbi::DeviceGuard dev_guard_(pipe);
   SbiPipe* p = static_cast<SbiPipe*>(pipe);
   if (!p) return SBI_EINVAL;
   return pipe_wait_prev(p, h_loss_last);

@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "stages.cuh"
+#include "device.cuh"
 
 namespace sbi {
 
@@ -490,16 +491,7 @@ maf_vjp_kernel(const __grid_constant__ sbi_maf_model m, const __grid_constant__ 
 // =================================================================================================
 using namespace sbi;
 
-static int maf_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaDeviceProp p;
-    n = (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess)
-            ? p.multiProcessorCount : 148;
-  }
-  return n;
-}
+static int maf_num_sms() { return sbi::dev_num_sms(); }
 
 static int maf_check(const sbi_maf_model* m) {
   if (!m || !m->d_params || !m->d_layer_tab || !m->d_perm_tab || !m->d_stats) return SBI_EINVAL;
@@ -516,7 +508,8 @@ static int maf_check(const sbi_maf_model* m) {
 
 template <int ID, class K>
 static int maf_set_smem(K kernel, int bytes) {
-  static int granted = 0;
+  static int granted_[sbi::kMaxDev] = {0};
+  int& granted = granted_[sbi::cur_dev()];
   if (bytes > 227 * 1024) return SBI_ESMEM;
   if (bytes <= granted) return 0;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -540,6 +533,7 @@ static int maf_launch_rows(KF kernel, const sbi_maf_model* m, const sbi_rows* ro
 
 extern "C" int sbi_b200_maf_logprob(const sbi_maf_model* m, const sbi_rows* rows, float* d_logp,
                                     float* d_noise, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   int rc = maf_check(m);
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_logp) return SBI_EINVAL;
@@ -551,6 +545,7 @@ extern "C" int sbi_b200_maf_logprob(const sbi_maf_model* m, const sbi_rows* rows
 
 extern "C" int sbi_b200_maf_inverse(const sbi_maf_model* m, const sbi_rows* rows, float* d_out,
                                     float* d_logabsdet, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   int rc = maf_check(m);
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_out) return SBI_EINVAL;
@@ -568,6 +563,7 @@ extern "C" int sbi_b200_maf_vjp_parts(int64_t R) {
 extern "C" int sbi_b200_maf_vjp(const sbi_maf_model* m, const sbi_rows* rows, const float* d_gout,
                                 float g_const, float* d_logp, float* d_gpart, float* d_ginput,
                                 float* d_gcond, float* d_loss_acc, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   int rc = maf_check(m);
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 1 || !d_gpart) return SBI_EINVAL;

@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "nsf.cuh"
+#include "device.cuh"
 
 namespace sbi {
 
@@ -503,18 +504,7 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
 // =================================================================================================
 using namespace sbi;
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaDeviceProp p;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess)
-      g_num_sms = p.multiProcessorCount;
-    else
-      g_num_sms = 148;
-  }
-  return g_num_sms;
-}
+static int num_sms() { return sbi::dev_num_sms(); }
 
 static int check_model(const sbi_nsf_model* m) {
   if (!m || !m->d_params || !m->d_layer_tab || !m->d_feat_tab || !m->d_stats) return SBI_EINVAL;
@@ -538,7 +528,8 @@ static int check_model(const sbi_nsf_model* m) {
 // launches -- and launches recorded during CUDA-graph capture -- make no attribute calls.
 template <int ID, class K>
 static int set_smem(K kernel, int bytes) {
-  static int granted = 0;   // one instance per kernel id (same-signature kernels share a type)
+  static int granted_[sbi::kMaxDev] = {0};
+  int& granted = granted_[sbi::cur_dev()];   // one instance per kernel id (same-signature kernels share a type)
   if (bytes > 227 * 1024) return SBI_ESMEM;
   if (bytes <= granted) return 0;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -561,6 +552,7 @@ static bool use_big_tile(int64_t R) { return R >= (int64_t)64 * 148 * 2; }
 
 extern "C" int sbi_b200_nsf_logprob(const sbi_nsf_model* m, const sbi_rows* rows, float* d_logp,
                                     float* d_noise, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   int rc = check_model(m);
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_logp) return SBI_EINVAL;
@@ -601,6 +593,7 @@ extern "C" int sbi_b200_nsf_logprob(const sbi_nsf_model* m, const sbi_rows* rows
 
 extern "C" int sbi_b200_nsf_inverse(const sbi_nsf_model* m, const sbi_rows* rows, float* d_out,
                                     float* d_logabsdet, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   int rc = check_model(m);
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_out) return SBI_EINVAL;
@@ -637,38 +630,34 @@ extern "C" int sbi_b200_nsf_vjp_parts(int64_t R) {
 // Scratch for the activation spill of the VJP kernel: one slab per (CTA, layer), owned by the
 // library and grown on demand (old, smaller buffers stay allocated).  It cannot be (re)allocated while the stream is being captured into
 // a CUDA graph; then -- or with SBI_B200_VJP_SPILL=0 -- the kernel recomputes instead.
-static float* g_vjp_scratch = nullptr;
-static size_t g_vjp_scratch_bytes = 0;
-static int g_vjp_scratch_dev = -1;
+static float* g_vjp_scratch[sbi::kMaxDev] = {nullptr};
+static size_t g_vjp_scratch_bytes[sbi::kMaxDev] = {0};
 static float* vjp_scratch(size_t bytes, cudaStream_t s) {
   static const bool off = [] {
     const char* e = getenv("SBI_B200_VJP_SPILL");
     return e && e[0] == '0';
   }();
   if (off) return nullptr;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  if (g_vjp_scratch && dev == g_vjp_scratch_dev && bytes <= g_vjp_scratch_bytes) return g_vjp_scratch;
+  const int dev = sbi::cur_dev();      // one scratch per device: switching devices never reallocates
+  if (g_vjp_scratch[dev] && bytes <= g_vjp_scratch_bytes[dev]) return g_vjp_scratch[dev];
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
   // a smaller buffer handed out earlier is NOT freed: a CUDA graph captured with it may still be
-  // replayed (growth happens at most a few times per process, with model size)
-  g_vjp_scratch = nullptr;
-  g_vjp_scratch_bytes = 0;
+  // replayed (growth happens at most a few times per process and device, with model size)
   float* p = nullptr;
   if (cudaMalloc(&p, bytes) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
-  g_vjp_scratch = p;
-  g_vjp_scratch_bytes = bytes;
-  g_vjp_scratch_dev = dev;
+  g_vjp_scratch[dev] = p;
+  g_vjp_scratch_bytes[dev] = bytes;
   return p;
 }
 
 extern "C" int sbi_b200_nsf_vjp(const sbi_nsf_model* m, const sbi_rows* rows, const float* d_gout,
                                 float g_const, float* d_logp, float* d_gpart, float* d_ginput,
                                 float* d_gcond, float* d_loss_acc, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   int rc = check_model(m);
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 1 || !d_gpart) return SBI_EINVAL;

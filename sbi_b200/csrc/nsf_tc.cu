@@ -36,6 +36,7 @@
 #include "nsf.cuh"
 
 #include "tc_common.cuh"
+#include "device.cuh"
 
 namespace sbi {
 namespace tc {
@@ -709,18 +710,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
 // =================================================================================================
 using namespace sbi;
 
-static int tc_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    cudaDeviceProp p;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess)
-      n = p.multiProcessorCount;
-    else
-      n = 148;
-  }
-  return n;
-}
+static int tc_num_sms() { return sbi::dev_num_sms(); }
 
 // the weight ring has to fit next to a second CTA on the SM
 static int tc_plan_slots(const sbi_nsf_model* m, const sbi_nsf_tc* tc) {
@@ -729,6 +719,7 @@ static int tc_plan_slots(const sbi_nsf_model* m, const sbi_nsf_tc* tc) {
 }
 
 extern "C" int sbi_b200_nsf_tc_supported(const sbi_nsf_model* m, const sbi_nsf_tc* tc) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !tc) return 0;
   if (m->H != 50 || m->KB != 10) return 0;        // instantiated hidden width / bin count
   if (m->H + m->C > 64) return 0;                 // context rides in the hidden operand's K range
@@ -739,6 +730,7 @@ extern "C" int sbi_b200_nsf_tc_supported(const sbi_nsf_model* m, const sbi_nsf_t
 }
 
 extern "C" int sbi_b200_nsf_tc_pack(const sbi_nsf_model* m, const sbi_nsf_tc* tc, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !tc || !m->d_params || !tc->d_src || !tc->d_tcw || tc->n_words <= 0) return SBI_EINVAL;
   const int threads = 256, blocks = (tc->n_words + threads - 1) / threads;
   tc::tc_pack_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(m->d_params, tc->d_src,
@@ -749,6 +741,7 @@ extern "C" int sbi_b200_nsf_tc_pack(const sbi_nsf_model* m, const sbi_nsf_tc* tc
 extern "C" int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc,
                                        const sbi_rows* rows, float* d_logp, float* d_noise,
                                        void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !tc || !rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_logp)
     return SBI_EINVAL;
   if (!tc->d_tab || !tc->d_tcw) return SBI_EINVAL;
@@ -757,7 +750,8 @@ extern "C" int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc*
   const int nslot = tc_plan_slots(m, tc);
   const tc::TcSmem L = tc::tc_smem_layout(*m, tc->stage_cap, nslot);
   auto k = tc::nsf_logprob_tc_kernel<50, 10, false>;
-  static int smem_set = 0;
+  static int smem_set_[sbi::kMaxDev] = {0};
+  int& smem_set = smem_set_[sbi::cur_dev()];
   if (smem_set < L.total_bytes) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
     if (e != cudaSuccess) return SBI_ESMEM;
@@ -772,6 +766,7 @@ extern "C" int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc*
 extern "C" int sbi_b200_nsf_inverse_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc,
                                        const sbi_rows* rows, float* d_out, float* d_logabsdet,
                                        void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !tc || !rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_out)
     return SBI_EINVAL;
   if (!tc->d_tab || !tc->d_tcw) return SBI_EINVAL;
@@ -780,7 +775,8 @@ extern "C" int sbi_b200_nsf_inverse_tc(const sbi_nsf_model* m, const sbi_nsf_tc*
   const int nslot = tc_plan_slots(m, tc);
   const tc::TcSmem L = tc::tc_smem_layout(*m, tc->stage_cap, nslot);
   auto k = tc::nsf_logprob_tc_kernel<50, 10, true>;
-  static int smem_set = 0;
+  static int smem_set_[sbi::kMaxDev] = {0};
+  int& smem_set = smem_set_[sbi::cur_dev()];
   if (smem_set < L.total_bytes) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
     if (e != cudaSuccess) return SBI_ESMEM;

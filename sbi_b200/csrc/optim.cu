@@ -7,6 +7,7 @@
 
 #include "../../include/sbi_b200.h"
 #include "common.cuh"
+#include "device.cuh"
 
 namespace sbi {
 
@@ -155,10 +156,43 @@ adam_clip_kernel(float* __restrict__ params, const float* __restrict__ grad,
   }
 }
 
+// -sum of the finite entries of a log-prob vector and the count of non-finite ones (the epoch
+// statistics of the validation pass, trainers/base.py:1195-1225 + assert_all_finite): one block,
+// fixed summation order (deterministic).
+__global__ void __launch_bounds__(1024)
+nll_stats_kernel(const float* __restrict__ lp, int64_t n, float* __restrict__ out) {
+  __shared__ float s_sum[32], s_bad[32];
+  float a = 0.f, b = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = lp[i];
+    if (isfinite(v)) a -= v; else b += 1.f;
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_sum[w] = a; s_bad[w] = b; }
+  __syncthreads();
+  if (w == 0) {
+    a = s_sum[l];
+    b = s_bad[l];
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (l == 0) { out[0] = a; out[1] = b; }
+  }
+}
+
 }  // namespace sbi
+
+extern "C" int sbi_b200_nll_stats(const float* d_logp, int64_t n, float* d_out2, void* stream) {
+  sbi::DeviceGuard dev_guard_(d_logp);
+  if (!d_logp || !d_out2 || n < 0) return SBI_EINVAL;
+  sbi::nll_stats_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_logp, n, d_out2);
+  return (int)cudaGetLastError();
+}
 
 extern "C" int sbi_b200_reduce_partials(const float* d_gpart, int n_part, int64_t n_params,
                                         float* d_grad, void* stream) {
+  sbi::DeviceGuard dev_guard_(d_gpart);
   return sbi_b200_reduce_partials_norm(d_gpart, n_part, n_params, d_grad, nullptr, nullptr, stream);
 }
 
@@ -167,6 +201,7 @@ extern "C" int sbi_b200_sumsq_blocks(int64_t n_params) { return (int)((n_params 
 extern "C" int sbi_b200_reduce_partials_norm(const float* d_gpart, int n_part, int64_t n_params,
                                              float* d_grad, const uint8_t* d_mask, float* d_sumsq_part,
                                              void* stream) {
+  sbi::DeviceGuard dev_guard_(d_gpart);
   if (!d_gpart || !d_grad || n_part < 1 || n_params < 4 || (n_params & 3)) return SBI_EINVAL;
   const int64_t n4 = n_params / 4;
   const int grid = (int)((n4 + 63) / 64);
@@ -179,6 +214,7 @@ extern "C" int sbi_b200_adam_clip_step(float* d_params, const float* d_grad, flo
                                        int32_t* d_step, const uint8_t* d_mask, int64_t n, float lr,
                                        float beta1, float beta2, float eps, float max_norm,
                                        float grad_scale, void* stream) {
+  sbi::DeviceGuard dev_guard_(d_params);
   return sbi_b200_adam_clip_step_norm(d_params, d_grad, d_state, d_step, d_mask, n, lr, beta1, beta2, eps,
                                       max_norm, grad_scale, nullptr, 0, stream);
 }
@@ -188,6 +224,7 @@ extern "C" int sbi_b200_adam_clip_step_norm(float* d_params, const float* d_grad
                                             float beta1, float beta2, float eps, float max_norm,
                                             float grad_scale, const float* d_sumsq_part, int n_sumsq,
                                             void* stream) {
+  sbi::DeviceGuard dev_guard_(d_params);
   if (!d_params || !d_grad || !d_state || !d_step || n < 1) return SBI_EINVAL;
   if (d_sumsq_part != nullptr && n_sumsq < 1) return SBI_EINVAL;
   int grid = (int)((n + 1023) / 1024);

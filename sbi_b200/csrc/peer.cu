@@ -15,8 +15,10 @@
 //      every rank adds the same numbers in the same order and the replicas stay bit-identical),
 //      write the reduced gradient and one partial of sum(g^2) per block for the clip norm.
 // Block b only ever waits for block b of the other ranks, so no co-residency is required.  The step
-// number comes from the optimizer's device counter: the launch is CUDA-graph capturable and carries no
-// host-side state.  Slot reuse is safe: a rank rewrites slot s two steps later, after it has seen
+// number is a device counter -- the exchange's OWN, kept in the symmetric buffer and advanced by the
+// last block to finish (d_step == nullptr; it only ever grows, so flags left by a warm-up pass whose
+// optimizer state was rewound can never match a later step), or a caller-provided one (the
+// optimizer's) -- so the launch is CUDA-graph capturable and carries no host-side state.  Slot reuse is safe: a rank rewrites slot s two steps later, after it has seen
 // every peer's flag of the step in between, which that peer set after finishing this step's reads.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,6 +26,7 @@
 
 #include "../../include/sbi_b200.h"
 #include "common.cuh"
+#include "device.cuh"
 
 namespace sbi {
 
@@ -49,10 +52,12 @@ peer_sum_kernel(const float* __restrict__ grad_local, PeerPtrs peers, int world,
                 float* __restrict__ sumsq_part, const int32_t* __restrict__ d_step) {
   __shared__ float red[32];
   __shared__ int s_bad;
-  const int step = __ldg(d_step) + 1;           // this optimisation step, 1-based
-  const int slot = step & 1;
   const int64_t i = (int64_t)blockIdx.x * kPeerBlock + threadIdx.x;
   float* own = peers.p[rank];
+  int* ctl = reinterpret_cast<int*>(own + 2 * n_pad) + 2 * nblk;     // [err | done | counter | -]
+  // this exchange, 1-based (every block reads the counter before the last block can advance it)
+  const int step = (d_step ? __ldg(d_step) : *reinterpret_cast<volatile int*>(ctl + 2)) + 1;
+  const int slot = step & 1;
   // 1. publish
   own[(int64_t)slot * n_pad + i] = (i < n) ? grad_local[i] : 0.f;
   if (threadIdx.x == 0) s_bad = 0;
@@ -90,6 +95,15 @@ peer_sum_kernel(const float* __restrict__ grad_local, PeerPtrs peers, int world,
       if (l == 0) sumsq_part[blockIdx.x] = t;
     }
   }
+  // own counter: the block that finishes last advances it (all blocks have read it by then)
+  if (d_step == nullptr && threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ctl + 1, 1) == nblk - 1) {
+      ctl[1] = 0;
+      ctl[2] = step;
+      __threadfence();
+    }
+  }
 }
 
 }  // namespace sbi
@@ -110,8 +124,10 @@ extern "C" void* sbi_b200_peer_alloc(int64_t n_params) {
   cudaDeviceSynchronize();
   return p;
 }
-extern "C" int sbi_b200_peer_free(void* p) { return (int)cudaFree(p); }
+extern "C" int sbi_b200_peer_free(void* p) {
+  sbi::DeviceGuard dev_guard_(p); return (int)cudaFree(p); }
 extern "C" int sbi_b200_peer_export(void* p, void* handle64) {
+  sbi::DeviceGuard dev_guard_(p);
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaIpcGetMemHandle(&h, p);
   if (e != cudaSuccess) return (int)e;
@@ -128,13 +144,15 @@ extern "C" void* sbi_b200_peer_import(const void* handle64) {
   }
   return p;
 }
-extern "C" int sbi_b200_peer_close(void* p) { return (int)cudaIpcCloseMemHandle(p); }
+extern "C" int sbi_b200_peer_close(void* p) {
+  sbi::DeviceGuard dev_guard_(p); return (int)cudaIpcCloseMemHandle(p); }
 
 extern "C" int sbi_b200_peer_sum(const float* d_grad_local, void* const* h_peer_ptrs, int world, int rank,
                                  int64_t n_params, float* d_grad_out, const uint8_t* d_mask,
                                  float* d_sumsq_part, const int32_t* d_step, void* stream) {
+  sbi::DeviceGuard dev_guard_(d_grad_local);
   if (!d_grad_local || !h_peer_ptrs || world < 1 || world > kMaxPeers || rank < 0 || rank >= world ||
-      n_params < 1 || !d_grad_out || !d_step)
+      n_params < 1 || !d_grad_out)
     return SBI_EINVAL;
   PeerPtrs pp;
   for (int r = 0; r < kMaxPeers; ++r) pp.p[r] = r < world ? static_cast<float*>(h_peer_ptrs[r]) : nullptr;
@@ -149,6 +167,7 @@ extern "C" int sbi_b200_peer_sum(const float* d_grad_local, void* const* h_peer_
 
 /* 1 if a bounded wait of the peer kernel expired since the buffer was allocated */
 extern "C" int sbi_b200_peer_error(const void* p, int64_t n_params) {
+  sbi::DeviceGuard dev_guard_(p);
   const int nblk = sbi_b200_peer_blocks(n_params);
   int v = 0;
   const int* f = reinterpret_cast<const int*>(static_cast<const float*>(p) + 2 * (int64_t)nblk * kPeerBlock) + 2 * nblk;

@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "stages.cuh"
+#include "device.cuh"
 
 namespace sbi {
 
@@ -295,16 +296,7 @@ ratio_vjp_kernel(const __grid_constant__ sbi_ratio_model m, const __grid_constan
 
 using namespace sbi;
 
-static int ratio_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaDeviceProp p;
-    n = (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess)
-            ? p.multiProcessorCount : 148;
-  }
-  return n;
-}
+static int ratio_num_sms() { return sbi::dev_num_sms(); }
 
 static int ratio_check(const sbi_ratio_model* m) {
   if (!m || !m->d_params || !m->d_tab || !m->d_stats) return SBI_EINVAL;
@@ -317,7 +309,8 @@ static int ratio_check(const sbi_ratio_model* m) {
 
 template <int ID, class K>
 static int ratio_set_smem(K kernel, int bytes) {
-  static int granted = 0;
+  static int granted_[sbi::kMaxDev] = {0};
+  int& granted = granted_[sbi::cur_dev()];
   if (bytes > 227 * 1024) return SBI_ESMEM;
   if (bytes <= granted) return 0;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -328,6 +321,7 @@ static int ratio_set_smem(K kernel, int bytes) {
 
 extern "C" int sbi_b200_ratio_forward(const sbi_ratio_model* m, const sbi_pairs* pairs, float* d_logits,
                                       void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   int rc = ratio_check(m);
   if (rc) return rc;
   if (!pairs || !pairs->d_theta || !pairs->d_x || pairs->R < 0 || !d_logits) return SBI_EINVAL;
@@ -360,6 +354,7 @@ extern "C" int sbi_b200_ratio_vjp_parts(int64_t R) {
 
 extern "C" int sbi_b200_ratio_vjp(const sbi_ratio_model* m, const sbi_pairs* pairs, const float* d_gout,
                                   float* d_logits, float* d_gpart, float* d_gtheta, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   int rc = ratio_check(m);
   if (rc) return rc;
   if (!pairs || !pairs->d_theta || !pairs->d_x || pairs->R < 1 || !d_gpart || !d_gout) return SBI_EINVAL;

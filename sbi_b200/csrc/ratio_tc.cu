@@ -16,6 +16,7 @@
 #include <algorithm>
 
 #include "tc_common.cuh"
+#include "device.cuh"
 
 namespace sbi {
 namespace tc {
@@ -254,20 +255,10 @@ ratio_forward_tc_kernel(const __grid_constant__ sbi_ratio_model m, const __grid_
 
 using namespace sbi;
 
-static int rtc_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    cudaDeviceProp p;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess)
-      n = p.multiProcessorCount;
-    else
-      n = 148;
-  }
-  return n;
-}
+static int rtc_num_sms() { return sbi::dev_num_sms(); }
 
 extern "C" int sbi_b200_ratio_tc_supported(const sbi_ratio_model* m, const sbi_nsf_tc* tc) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !tc) return 0;
   if (m->H != 50) return 0;
   if (m->Dt + m->Dx > 56 || m->NB < 1 || m->NB > 8) return 0;
@@ -277,6 +268,7 @@ extern "C" int sbi_b200_ratio_tc_supported(const sbi_ratio_model* m, const sbi_n
 }
 
 extern "C" int sbi_b200_ratio_tc_pack(const sbi_ratio_model* m, const sbi_nsf_tc* tc, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !tc || !m->d_params || !tc->d_src || !tc->d_tcw || tc->n_words <= 0) return SBI_EINVAL;
   const int threads = 256, blocks = (tc->n_words + threads - 1) / threads;
   tc::tc_pack_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(m->d_params, tc->d_src, tc->d_tcw,
@@ -286,13 +278,15 @@ extern "C" int sbi_b200_ratio_tc_pack(const sbi_ratio_model* m, const sbi_nsf_tc
 
 extern "C" int sbi_b200_ratio_forward_tc(const sbi_ratio_model* m, const sbi_nsf_tc* tc,
                                          const sbi_pairs* pairs, float* d_logits, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !tc || !pairs || !pairs->d_theta || !pairs->d_x || pairs->R < 0 || !d_logits) return SBI_EINVAL;
   if (!tc->d_tab || !tc->d_tcw) return SBI_EINVAL;
   if (!sbi_b200_ratio_tc_supported(m, tc)) return SBI_ESMEM;
   if (pairs->R == 0) return 0;
   const tc::RatioTcSmem L = tc::ratio_tc_smem_layout(*m, tc->stage_cap);
   auto k = tc::ratio_forward_tc_kernel<50>;
-  static int smem_set = 0;
+  static int smem_set_[sbi::kMaxDev] = {0};
+  int& smem_set = smem_set_[sbi::cur_dev()];
   if (smem_set < L.total_bytes) {
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes) != cudaSuccess)
       return SBI_ESMEM;

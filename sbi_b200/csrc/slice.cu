@@ -14,6 +14,7 @@
 #include <math.h>
 
 #include "../../include/sbi_b200.h"
+#include "device.cuh"
 
 namespace sbi {
 
@@ -150,6 +151,7 @@ static int slice_check(const sbi_slice_chains* s) {
 }
 
 extern "C" int sbi_b200_slice_init(const sbi_slice_chains* s, float* d_params, void* stream) {
+  sbi::DeviceGuard dev_guard_(s ? s->d_x : nullptr);
   int rc = slice_check(s);
   if (rc || !d_params) return SBI_EINVAL;
   sbi::slice_init_kernel<<<(s->C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*s, d_params);
@@ -158,6 +160,7 @@ extern "C" int sbi_b200_slice_init(const sbi_slice_chains* s, float* d_params, v
 
 extern "C" int sbi_b200_slice_step(const sbi_slice_chains* s, const float* d_logp, float* d_params,
                                    int32_t* d_n_done, void* stream) {
+  sbi::DeviceGuard dev_guard_(s ? s->d_x : nullptr);
   int rc = slice_check(s);
   if (rc || !d_logp || !d_params || !d_n_done) return SBI_EINVAL;
   cudaError_t e = cudaMemsetAsync(d_n_done, 0, sizeof(int32_t), (cudaStream_t)stream);

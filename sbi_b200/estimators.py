@@ -290,6 +290,11 @@ class FlowEstimator(nn.Module):
         """(sample_dim, batch_dim) log-probabilities; nflows_flow.py:77-97."""
         self._check_input_shape(input)
         self._check_condition_shape(condition)
+        if not self.net.flat.is_cuda:
+            # the reference probes a freshly built (CPU-resident) net with two CPU rows before it
+            # moves it to the training device (user_input_checks.py:767-795): device hop, no CPU math
+            from ._refabc import hop_to_device
+            return hop_to_device(self, "log_prob", input, condition)
         inp, cond, shared, S, B = self._align(input, condition)
         ctx = self._embed(cond)
         lp = _NsfLogProb.apply(self.net.flat, inp.contiguous().float(), ctx.contiguous().float(),

@@ -185,6 +185,18 @@ class FlowMatchingEstimator(nn.Module):
     mean_base = property(lambda self: self._mean_base)
     std_base = property(lambda self: self._std_base)
 
+    # boundary affine of the reference base class (estimators/base.py:460-475); composition is off
+    compose_enabled = property(lambda self: bool(self._compose_standardization))
+
+    def to_z(self, theta: Tensor) -> Tensor:
+        return (theta - self._theta_shift) / self._theta_scale
+
+    def from_z(self, z: Tensor) -> Tensor:
+        return self._theta_shift + self._theta_scale * z
+
+    def log_abs_det(self) -> Tensor:
+        return torch.log(self._theta_scale).sum()
+
     def score(self, input: Tensor, condition: Tensor, t: Tensor) -> Tensor:
         """grad_theta log p_t(theta | x) = (-(1 - t) v - theta) / (t + sigma_min)   (:374-399)."""
         t = torch.as_tensor(t, dtype=torch.float32, device=input.device)
@@ -319,6 +331,8 @@ def posterior_flow_nn(model: str = "mlp", z_score_theta: Optional[str] = "indepe
         raise NotImplementedError("only the sinusoidal time embedding (FMPE default) is implemented")
 
     def build_fn(batch_theta, batch_x):
+        from ._refabc import register_with_reference
+        register_with_reference()
         return build_vector_field_estimator(
             batch_x=batch_theta, batch_y=batch_x, z_score_x=z_score_theta, z_score_y=z_score_x,
             hidden_features=hidden_features, num_layers=num_layers, embedding_net=embedding_net,

@@ -76,15 +76,69 @@ class _FlowTrainer:
         self._dist = None   # (rank, world) when data-parallel
 
     # ------------------------------------------------------------------ data
-    def data_parallel(self):
+    def data_parallel(self, partition: str = "global"):
         """Train data-parallel over the initialised `torch.distributed` group (one process per
-        GPU): every rank appends ITS OWN simulations, rank 0's initial network is
+        GPU).  Replicas are identical: rank 0's initial network and statistics are
         broadcast when `train()` starts, each step's flat gradients are summed over the ranks
         (NVLink peer-memory kernel on one node, NCCL otherwise) and every rank applies the same
-        deterministic clip + Adam, so the replicas stay bit-identical."""
+        deterministic clip + Adam, so the replicas stay bit-identical.
+
+        partition="global" (SURVEY 8e): every rank holds the SAME simulations; the split and every
+            epoch permutation come from rank 0, and rank r differentiates rows
+            [r*B/G, (r+1)*B/G) of each global batch of `training_batch_size` rows, so batch
+            composition, loss and update equal the single-GPU run (strong scaling).
+        partition="local": every rank appends ITS OWN simulations and draws its own batches of
+            `training_batch_size` rows (global batch = G x that; weak scaling)."""
         from . import parallel
+        if partition not in ("global", "local"):
+            raise ValueError("partition must be 'global' or 'local'")
         self._dist = parallel.world()
+        self._partition = partition
         return self
+
+    # ---- data-parallel helpers (no-ops on one process) ---------------------------------------------
+    def _dp(self):
+        rank, world = self._dist if getattr(self, "_dist", None) is not None else (0, 1)
+        return rank, world, (getattr(self, "_partition", "global") if world > 1 else "local")
+
+    def _dp_agree(self, value: int, what: str):
+        """All ranks must see the same `value` (step counts, set sizes): a mismatch would leave a
+        rank waiting in a collective forever."""
+        rank, world, _ = self._dp()
+        if world == 1:
+            return
+        t = torch.tensor([value, -value], dtype=torch.int64, device=self._device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        if int(t[0]) != value or int(-t[1]) != value:
+            raise RuntimeError(f"data-parallel training needs the same {what} on every rank "
+                               f"(this rank: {value}, max {int(t[0])}, min {int(-t[1])})")
+
+    def _dp_split(self, N: int, n_train: int):
+        """90/10 split indices (base.py:525-539); with partition='global' rank 0's split is used."""
+        perm = torch.randperm(N)
+        rank, world, part = self._dp()
+        if world > 1 and part == "global":
+            p = perm.to(self._device)
+            torch.distributed.broadcast(p, 0)
+            perm = p.cpu()
+        return perm[:n_train], perm[n_train:]
+
+    def _dp_sync_net(self, net):
+        """Replicas start identical: parameters AND standardisation statistics of rank 0."""
+        _, world, _ = self._dp()
+        if world > 1:
+            for t in list(net.parameters()) + list(net.buffers()):
+                torch.distributed.broadcast(t.data, 0)
+            net._cache.clear()
+
+    def _dp_sum(self, values):
+        """Sum of per-rank epoch statistics (list of floats), identical on every rank."""
+        _, world, _ = self._dp()
+        if world == 1:
+            return values
+        t = torch.tensor(values, dtype=torch.float64, device=self._device)
+        torch.distributed.all_reduce(t)
+        return t.tolist()
 
     def append_simulations(self, theta: Tensor, x: Tensor, proposal=None,
                            exclude_invalid_x: Optional[bool] = None, data_device: Optional[str] = None):
@@ -136,12 +190,14 @@ class _FlowTrainer:
         lib = L.load()
         dev = self._device
         N = self._theta.shape[0]
+        rank, world, part = self._dp()
+        glob = world > 1 and part == "global"
+        self._dp_agree(N, "number of simulations") if glob else None
         # --- split (base.py:525-539): CPU global generator, like the reference
         n_train = int((1 - validation_fraction) * N)
         n_val = N - n_train
         if not resume_training or not hasattr(self, "train_indices"):
-            perm = torch.randperm(N)
-            self.train_indices, self.val_indices = perm[:n_train], perm[n_train:]
+            self.train_indices, self.val_indices = self._dp_split(N, n_train)
         # --- network (npe_base.py:674-708): built from the CPU training split
         if self._neural_net is None or retrain_from_scratch:
             th_cpu = self._theta[self.train_indices.to(dev)].cpu()
@@ -150,11 +206,8 @@ class _FlowTrainer:
             del th_cpu, x_cpu
         net = self._neural_net.to(dev)
         self._neural_net = net
-        if self._dist is not None and self._dist[1] > 1 and not resume_training:
-            # replicas start identical: parameters AND standardisation statistics of rank 0
-            for t in list(net.parameters()) + list(net.buffers()):
-                torch.distributed.broadcast(t.data, 0)
-            net._cache.clear()
+        if not resume_training:
+            self._dp_sync_net(net)
         if not isinstance(net, FlowEstimator):
             raise TypeError(f"{type(self).__name__} needs an sbi_b200 flow estimator, "
                             f"got {type(net).__name__}")
@@ -164,11 +217,19 @@ class _FlowTrainer:
                 "the fused trainer supports nn.Identity() embedding nets; train estimators with "
                 "torch embedding nets through estimator.loss(...).backward()")
         P = lay.n_params
-        B = min(training_batch_size, n_train)
+        B = min(training_batch_size, n_train)        # rows of one optimisation step (global batch if `glob`)
         Bv = min(training_batch_size, n_val)
         steps = n_train // B
         vsteps = n_val // Bv if Bv > 0 else 0
-        rank, world = self._dist if self._dist is not None else (0, 1)
+        if glob and B % world:
+            raise ValueError(f"partition='global' needs training_batch_size ({B}) divisible by the "
+                             f"number of ranks ({world})")
+        Bl = B // world if glob else B                 # rows this rank differentiates per step
+        Btot = B if glob else B * world                # rows behind one update
+        self._dp_agree(steps, "number of steps per epoch")
+        # validation rows: every rank evaluates its contiguous share of the epoch's validation order
+        from .parallel import shard_range
+        v_lo, v_hi = shard_range(vsteps * Bv, rank, world) if glob else (0, vsteps * Bv)
 
         if not resume_training or not hasattr(self, "_opt_state"):
             self._opt_state = torch.zeros(2 * P, dtype=torch.float32, device=dev)
@@ -186,7 +247,7 @@ class _FlowTrainer:
         vperm_buf = torch.empty(max(vsteps * Bv, 1), dtype=torch.int64, device=dev)
         grad = torch.zeros(P, dtype=torch.float32, device=dev)
         sumsq = torch.zeros(lib.sbi_b200_sumsq_blocks(P), dtype=torch.float32, device=dev)
-        n_part = net.fam.fn("vjp_parts")(B)
+        n_part = net.fam.fn("vjp_parts")(Bl)
         gpart = net._gpart(n_part)
         loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
         val_lp = torch.empty(max(vsteps * Bv, 1), dtype=torch.float32, device=dev)
@@ -207,15 +268,16 @@ class _FlowTrainer:
             m_tr = net._model(nbuf=3)
             loss_acc.zero_()
             for s in range(steps):
-                idx = perm_buf[s * B:(s + 1) * B]
-                rows = L.Rows(inp_all.data_ptr(), cond_all.data_ptr(), idx.data_ptr(), B, 0)
-                L.check(net.fam.fn("vjp")(C.byref(m_tr), C.byref(rows), None, -1.0 / (B * world),
+                o = s * B + (rank * Bl if glob else 0)
+                idx = perm_buf[o:o + Bl]
+                rows = L.Rows(inp_all.data_ptr(), cond_all.data_ptr(), idx.data_ptr(), Bl, 0)
+                L.check(net.fam.fn("vjp")(C.byref(m_tr), C.byref(rows), None, -1.0 / Btot,
                                           None, L.ptr(gpart), None, None, L.ptr(loss_acc),
                                           L.stream_ptr()), "flow_vjp")
                 if peer is not None:   # gradients summed over NVLink peer memory (csrc/peer.cu)
                     L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad_local),
                                                          L.stream_ptr()), "reduce_partials")
-                    peer.sum(grad_local, grad, mask, sumsq, self._opt_step)
+                    peer.sum(grad_local, grad, mask, sumsq)
                     L.check(lib.sbi_b200_adam_clip_step_norm(
                         L.ptr(net.flat.data), L.ptr(grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
                         L.ptr(mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.ptr(sumsq),
@@ -236,33 +298,41 @@ class _FlowTrainer:
                         L.ptr(mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.ptr(sumsq),
                         sumsq.shape[0], L.stream_ptr()), "adam_clip_step")
             stats[0:2].copy_(loss_acc)
-            if vsteps > 0:
+            stats[2:4].zero_()
+            if v_hi > v_lo:
                 m_ev = net._model(nbuf=2)
-                rows = L.Rows(inp_all.data_ptr(), cond_all.data_ptr(), vperm_buf.data_ptr(),
-                              vsteps * Bv, 0)
+                vrows = vperm_buf[v_lo:v_hi]
+                vlp = val_lp[:v_hi - v_lo]
+                rows = L.Rows(inp_all.data_ptr(), cond_all.data_ptr(), vrows.data_ptr(), v_hi - v_lo, 0)
                 # validation rows go through the tensor-core kernel when the model fits it (its
                 # operands are re-packed from the just-updated parameters inside _tc_state)
-                tc_ev = net._tc_state(m_ev) if vsteps * Bv >= net.TC_MIN_ROWS else None
+                tc_ev = net._tc_state(m_ev) if v_hi - v_lo >= net.TC_MIN_ROWS else None
                 if tc_ev is not None:
                     L.check(lib.sbi_b200_nsf_logprob_tc(C.byref(m_ev), C.byref(tc_ev), C.byref(rows),
-                                                        L.ptr(val_lp), None, L.stream_ptr()), "nsf_logprob_tc")
+                                                        L.ptr(vlp), None, L.stream_ptr()), "nsf_logprob_tc")
                 else:
-                    L.check(net.fam.fn("logprob")(C.byref(m_ev), C.byref(rows), L.ptr(val_lp), None,
+                    L.check(net.fam.fn("logprob")(C.byref(m_ev), C.byref(rows), L.ptr(vlp), None,
                                                   L.stream_ptr()), "flow_logprob")
-                finite = torch.isfinite(val_lp)
-                stats[2] = -(torch.where(finite, val_lp, torch.zeros_like(val_lp))).sum()
-                stats[3] = (~finite).sum().float()
+                # -sum of the finite log-probs and the count of non-finite ones, one fused launch
+                L.check(lib.sbi_b200_nll_stats(L.ptr(vlp), v_hi - v_lo, L.ptr(stats[2:]), L.stream_ptr()),
+                        "nll_stats")
 
         def fill_perms():
             perm_buf.copy_(train_idx[torch.randperm(n_train, device=dev)[:steps * B]])
             if vsteps > 0:
                 vperm_buf.copy_(val_idx[torch.randperm(n_val, device=dev)[:vsteps * Bv]])
+            if glob:      # one epoch order for all ranks: rank 0's
+                torch.distributed.broadcast(perm_buf, 0)
+                if vsteps > 0:
+                    torch.distributed.broadcast(vperm_buf, 0)
 
         # warm-up (also sets kernel attributes) on a throw-away copy of the state, then capture
         graph = None
         if world == 1 or peer is not None:
             snap = (net.flat.data.clone(), self._opt_state.clone(), self._opt_step.clone())
-            fill_perms()
+            rng = torch.cuda.get_rng_state(dev)      # the warm-up's permutation draw leaves no trace:
+            fill_perms()                             # a seed gives the same run with and without graphs
+            torch.cuda.set_rng_state(rng, dev)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -294,15 +364,11 @@ class _FlowTrainer:
                 graph.replay()
             else:
                 run_epoch()
-            s = stats.tolist()   # the one host sync of the epoch
-            if world > 1:
-                t = torch.tensor(s, device=dev)
-                torch.distributed.all_reduce(t)
-                s = (t / world).tolist()
+            s = self._dp_sum(stats.tolist())   # the one host sync of the epoch (+ one tiny all-reduce)
             if s[1] > 0 or s[3] > 0:
                 raise AssertionError("NaN/Inf present in NPE loss.")
-            train_loss = s[0] / (steps * B)
-            self._val_loss = s[2] / (vsteps * Bv) if vsteps > 0 else float("nan")
+            train_loss = s[0] / (steps * Btot)
+            self._val_loss = s[2] / (vsteps * Bv * (1 if glob else world)) if vsteps > 0 else float("nan")
             self._summary["training_loss"].append(train_loss)
             self._summary["validation_loss"].append(self._val_loss)
             self._summary["epoch_durations_sec"].append(time.time() - t0)
@@ -402,33 +468,41 @@ class NRE_B(_FlowTrainer):
         self._dist = None
 
     @staticmethod
-    def _contrastive_choices(B: int, k: int, device) -> Tensor:
-        """(B, k) indices j != i, distinct per row, uniform: same law as
+    def _contrastive_choices(B: int, k: int, device, rows: Optional[tuple] = None) -> Tensor:
+        """(n, k) indices j != i into a batch of B, distinct per row, uniform, for the batch rows
+        i in [rows[0], rows[1]) (default: all B): same law as
         `torch.multinomial((1 - eye) / (B - 1), k, replacement=False)` (nre_base.py:406-408) without the
         O(B^2) probability matrix: k draws without replacement from range(B-1), shifted past i."""
+        lo, hi = rows if rows is not None else (0, B)
+        n = hi - lo
         if B - 1 <= 4096:
-            draws = torch.multinomial(torch.ones(B, B - 1, device=device), k, replacement=False)
+            draws = torch.multinomial(torch.ones(n, B - 1, device=device), k, replacement=False)
         else:
-            draws = torch.randint(0, B - 1, (B, k), device=device)
+            draws = torch.randint(0, B - 1, (n, k), device=device)
             while True:
                 srt = draws.sort(dim=1).values
                 dup = (srt[:, 1:] == srt[:, :-1]).any(dim=1)
-                n = int(dup.sum().item())
-                if n == 0:
+                nd = int(dup.sum().item())
+                if nd == 0:
                     break
-                draws[dup] = torch.randint(0, B - 1, (n, k), device=device)
-        rows = torch.arange(B, device=device).unsqueeze(1)
-        return draws + (draws >= rows).long()
+                draws[dup] = torch.randint(0, B - 1, (nd, k), device=device)
+        own = torch.arange(lo, hi, device=device).unsqueeze(1)
+        return draws + (draws >= own).long()
 
-    def _loss_on(self, net, idx: Tensor, num_atoms: int, choices: Optional[Tensor] = None) -> Tensor:
+    def _loss_on(self, net, idx: Tensor, num_atoms: int, choices: Optional[Tensor] = None,
+                 rows: Optional[tuple] = None) -> Tensor:
+        """NRE-B loss (nre_b.py:157-182) of the batch rows [rows[0], rows[1]) (default: all) of the
+        batch `idx`; the contrastive thetas of a row come from the WHOLE batch (with the
+        global batch on every rank the data-parallel loss keeps the single-GPU semantics)."""
         from .ratio import _RatioFn
         B = idx.shape[0]
+        lo, hi = rows if rows is not None else (0, B)
         if choices is None:
-            choices = self._contrastive_choices(B, num_atoms - 1, idx.device)
-        local = torch.cat([torch.arange(B, device=idx.device).unsqueeze(1), choices], dim=1)   # (B, A)
+            choices = self._contrastive_choices(B, num_atoms - 1, idx.device, (lo, hi))
+        local = torch.cat([torch.arange(lo, hi, device=idx.device).unsqueeze(1), choices], dim=1)   # (n, A)
         ti = idx[local].reshape(-1).contiguous()
-        xi = idx.repeat_interleave(num_atoms).contiguous()
-        logits = _RatioFn.apply(net.net.flat, self._theta, self._x2d, net, ti, xi, False).reshape(B, num_atoms)
+        xi = idx[lo:hi].repeat_interleave(num_atoms).contiguous()
+        logits = _RatioFn.apply(net.net.flat, self._theta, self._x2d, net, ti, xi, False).reshape(hi - lo, num_atoms)
         log_prob = logits[:, 0] - torch.logsumexp(logits, dim=-1)
         return -torch.mean(log_prob)
 
@@ -443,11 +517,14 @@ class NRE_B(_FlowTrainer):
         dev = self._device
         N = self._theta.shape[0]
         self._x2d = self._x.reshape(N, -1).contiguous()
+        rank, world, part = self._dp()
+        glob = world > 1 and part == "global"
+        if glob:
+            self._dp_agree(N, "number of simulations")
         n_train = int((1 - validation_fraction) * N)
         n_val = N - n_train
         if not resume_training or not hasattr(self, "train_indices"):
-            perm = torch.randperm(N)
-            self.train_indices, self.val_indices = perm[:n_train], perm[n_train:]
+            self.train_indices, self.val_indices = self._dp_split(N, n_train)
         B = min(training_batch_size, n_train)
         Bv = min(training_batch_size, n_val)
         clipped = min(B, Bv)
@@ -457,6 +534,8 @@ class NRE_B(_FlowTrainer):
             self._neural_net = self._build_neural_net(self._theta[tr].cpu(), self._x[tr].cpu())
         net = self._neural_net.to(dev)
         self._neural_net = net
+        if not resume_training:
+            self._dp_sync_net(net)
         P = net.layout.n_params
         if not resume_training or not hasattr(self, "_opt_state"):
             self._opt_state = torch.zeros(2 * P, dtype=torch.float32, device=dev)
@@ -465,7 +544,21 @@ class NRE_B(_FlowTrainer):
             self._best_val_loss, self._best_flat, self._epochs_since_last_improvement = float("Inf"), None, 0
         train_idx, val_idx = self.train_indices.to(dev), self.val_indices.to(dev)
         steps, vsteps = n_train // B, (n_val // Bv if Bv > 0 else 0)
+        self._dp_agree(steps, "number of steps per epoch")
+        self._dp_agree(vsteps, "number of validation steps per epoch")
+        if glob and (B % world or Bv % world):
+            raise ValueError(f"partition='global' needs the batch sizes ({B}, {Bv}) divisible by the "
+                             f"number of ranks ({world})")
+        # rows of each (global) batch whose loss this rank differentiates / evaluates
+        t_rows = (rank * (B // world), (rank + 1) * (B // world)) if glob else (0, B)
+        v_rows = (rank * (Bv // world), (rank + 1) * (Bv // world)) if glob else (0, Bv)
         max_norm = float(clip_max_norm) if clip_max_norm is not None else 0.0
+        peer = None
+        if world > 1:
+            from .parallel import make_gradient_exchange
+            peer = make_gradient_exchange(P)          # None -> NCCL all-reduce, eager launches
+        grad_sum = torch.zeros(P, dtype=torch.float32, device=dev) if peer is not None else None
+        sumsq = torch.zeros(peer.n_sumsq, dtype=torch.float32, device=dev) if peer is not None else None
 
         def converged() -> bool:
             if self.epoch == 0 or self._val_loss < self._best_val_loss:
@@ -490,9 +583,19 @@ class NRE_B(_FlowTrainer):
 
         def train_step():
             net.net.flat.grad = None
-            loss = self._loss_on(net, idx_buf, num_atoms)
+            # every rank's rows weigh 1/world of the update's batch mean; gradients are summed
+            loss = self._loss_on(net, idx_buf, num_atoms, rows=t_rows) / world
             loss.backward()
             train_sum.add_(loss.detach())
+            if peer is not None:       # gradient sum over NVLink peer memory + sum(g^2) partials
+                peer.sum(net.flat.grad, grad_sum, net.net._mask, sumsq)
+                L.check(lib.sbi_b200_adam_clip_step_norm(
+                    L.ptr(net.flat.data), L.ptr(grad_sum), L.ptr(self._opt_state), L.ptr(self._opt_step),
+                    L.ptr(net.net._mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.ptr(sumsq),
+                    peer.n_sumsq, L.stream_ptr()), "adam_clip_step")
+                return
+            if world > 1:
+                torch.distributed.all_reduce(net.flat.grad)
             L.check(lib.sbi_b200_adam_clip_step(
                 L.ptr(net.flat.data), L.ptr(net.flat.grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
                 L.ptr(net.net._mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.stream_ptr()),
@@ -500,10 +603,11 @@ class NRE_B(_FlowTrainer):
 
         def val_step():
             with torch.no_grad():
-                val_sum.add_(self._loss_on(net, vidx_buf, num_atoms))
+                val_sum.add_(self._loss_on(net, vidx_buf, num_atoms, rows=v_rows) / world)
 
         g_train = g_val = None
-        if os.environ.get("SBI_B200_NRE_GRAPH", "1") != "0" and B - 1 <= 4096 and steps > 0:
+        if (os.environ.get("SBI_B200_NRE_GRAPH", "1") != "0" and B - 1 <= 4096 and steps > 0
+                and (world == 1 or peer is not None)):
             snap = (net.flat.data.clone(), self._opt_state.clone(), self._opt_step.clone())
             idx_buf.copy_(train_idx[:B])
             if vsteps > 0:
@@ -528,6 +632,11 @@ class NRE_B(_FlowTrainer):
         while self.epoch <= max_num_epochs and not converged():
             t0 = time.time()
             perm = train_idx[torch.randperm(n_train, device=dev)]
+            vperm = val_idx[torch.randperm(n_val, device=dev)] if vsteps > 0 else None
+            if glob:      # one epoch order for all ranks: rank 0's
+                torch.distributed.broadcast(perm, 0)
+                if vperm is not None:
+                    torch.distributed.broadcast(vperm, 0)
             train_sum.zero_()
             for s in range(steps):
                 idx_buf.copy_(perm[s * B:(s + 1) * B])
@@ -536,14 +645,13 @@ class NRE_B(_FlowTrainer):
                 else:
                     train_step()
             val_sum.zero_()
-            vperm = val_idx[torch.randperm(n_val, device=dev)] if vsteps > 0 else None
             for s in range(vsteps):
                 vidx_buf.copy_(vperm[s * Bv:(s + 1) * Bv])
                 if g_val is not None:
                     g_val.replay()
                 else:
                     val_step()
-            tl, vl = float(train_sum.item()), float(val_sum.item())
+            tl, vl = self._dp_sum([float(train_sum.item()), float(val_sum.item())])
             if not (math.isfinite(tl) and math.isfinite(vl)):
                 raise AssertionError("NaN/Inf present in NRE-B loss.")
             # the reference divides the sum of per-batch MEAN losses by steps * batch_size
@@ -562,6 +670,11 @@ class NRE_B(_FlowTrainer):
         self._summary["epochs_trained"].append(self.epoch)
         self._summary["best_validation_loss"].append(self._best_val_loss)
         net.zero_grad(set_to_none=True)
+        if peer is not None:
+            timed_out = peer.error()
+            peer.close()
+            if timed_out:
+                raise RuntimeError("peer-memory gradient exchange timed out (a rank fell behind or died)")
         return deepcopy(net)
 
     def build_posterior(self, density_estimator=None, prior=None, sample_with: str = "mcmc",
@@ -617,19 +730,32 @@ class FMPE(_FlowTrainer):
         dev = self._device
         N = self._theta.shape[0]
         x2d = self._x.reshape(N, -1).contiguous()
+        rank, world, part = self._dp()
+        glob = world > 1 and part == "global"
+        if glob:
+            self._dp_agree(N, "number of simulations")
         n_train = int((1 - validation_fraction) * N)
         n_val = N - n_train
         if not resume_training or not hasattr(self, "train_indices"):
-            perm = torch.randperm(N)
-            self.train_indices, self.val_indices = perm[:n_train], perm[n_train:]
+            self.train_indices, self.val_indices = self._dp_split(N, n_train)
         if self._neural_net is None:
             tr = self.train_indices.to(dev)
             self._neural_net = self._build_neural_net(self._theta[tr].cpu(), self._x[tr].cpu())
         net = self._neural_net.to(dev)
         self._neural_net = net
+        if not resume_training:
+            self._dp_sync_net(net)
         P, D = net.layout.n_params, net.layout.D
         B, Bv = min(training_batch_size, n_train), min(training_batch_size, n_val)
         steps, vsteps = n_train // B, (n_val // Bv if Bv > 0 else 0)
+        self._dp_agree(steps, "number of steps per epoch")
+        self._dp_agree(vsteps, "number of validation steps per epoch")
+        if glob and (B % world or Bv % world):
+            raise ValueError(f"partition='global' needs the batch sizes ({B}, {Bv}) divisible by the "
+                             f"number of ranks ({world})")
+        Bl, Bvl = (B // world, Bv // world) if glob else (B, Bv)    # rows of a batch this rank handles
+        o_t, o_v = (rank * Bl, rank * Bvl) if glob else (0, 0)
+        Btot = B if glob else B * world                              # rows behind one update
         if isinstance(validation_times, int):
             validation_times = torch.linspace(net.t_min + validation_times_nugget,
                                               net.t_max - validation_times_nugget, validation_times)
@@ -642,7 +768,15 @@ class FMPE(_FlowTrainer):
         grad = torch.zeros(P, dtype=torch.float32, device=dev)
         loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
         max_norm = float(clip_max_norm) if clip_max_norm is not None else 0.0
-        world = self._dist[1] if self._dist is not None else 1
+        # data-parallel on one node: the gradient sum is our peer-memory kernel inside the epoch graph
+        peer, grad_local = None, grad
+        sumsq = None
+        if world > 1:
+            from .parallel import make_gradient_exchange
+            peer = make_gradient_exchange(P)      # None -> NCCL all-reduce, eager launches
+            if peer is not None:
+                grad_local = torch.zeros(P, dtype=torch.float32, device=dev)
+                sumsq = torch.zeros(peer.n_sumsq, dtype=torch.float32, device=dev)
 
         def converged() -> bool:   # base_vf_inference.py:352-420
             if self.epoch == 0:
@@ -672,12 +806,20 @@ class FMPE(_FlowTrainer):
         def run_epoch():
             loss_acc.zero_()
             for s in range(steps):
-                idx = perm_buf[s * B:(s + 1) * B]
-                tms = torch.rand(B, device=dev)
-                eps = torch.randn(B, D, device=dev)
-                _, gpart, n_part = net.loss_raw(self._theta, x2d, tms, eps, index=idx, g_const=1.0 / (B * world),
+                idx = perm_buf[s * B + o_t:s * B + o_t + Bl]
+                tms = torch.rand(Bl, device=dev)
+                eps = torch.randn(Bl, D, device=dev)
+                _, gpart, n_part = net.loss_raw(self._theta, x2d, tms, eps, index=idx, g_const=1.0 / Btot,
                                                 loss_acc=loss_acc, want_loss=False)
-                L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad), L.stream_ptr()), "reduce")
+                L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad_local), L.stream_ptr()),
+                        "reduce")
+                if peer is not None:
+                    peer.sum(grad_local, grad, net.net._mask, sumsq)
+                    L.check(lib.sbi_b200_adam_clip_step_norm(
+                        L.ptr(net.flat.data), L.ptr(grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
+                        L.ptr(net.net._mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.ptr(sumsq),
+                        peer.n_sumsq, L.stream_ptr()), "adam")
+                    continue
                 if world > 1:
                     torch.distributed.all_reduce(grad)
                 L.check(lib.sbi_b200_adam_clip_step(L.ptr(net.flat.data), L.ptr(grad), L.ptr(self._opt_state),
@@ -689,9 +831,9 @@ class FMPE(_FlowTrainer):
             if vsteps > 0:
                 nt = vt.shape[0]
                 for s in range(vsteps):
-                    idx = vperm_buf[s * Bv:(s + 1) * Bv].repeat(nt).contiguous()
-                    tms = vt.repeat_interleave(Bv).contiguous()
-                    eps = torch.randn(Bv * nt, D, device=dev)
+                    idx = vperm_buf[s * Bv + o_v:s * Bv + o_v + Bvl].repeat(nt).contiguous()
+                    tms = vt.repeat_interleave(Bvl).contiguous()
+                    eps = torch.randn(Bvl * nt, D, device=dev)
                     net.loss_raw(self._theta, x2d, tms, eps, index=idx, g_const=0.0, loss_acc=loss_acc, want_loss=False)
             stats[2:4].copy_(loss_acc)
 
@@ -699,9 +841,12 @@ class FMPE(_FlowTrainer):
             perm_buf[:steps * B].copy_(train_idx[torch.randperm(n_train, device=dev)[:steps * B]])
             if vsteps > 0:
                 vperm_buf[:vsteps * Bv].copy_(val_idx[torch.randperm(n_val, device=dev)[:vsteps * Bv]])
+            if glob:      # one epoch order for all ranks: rank 0's
+                torch.distributed.broadcast(perm_buf, 0)
+                torch.distributed.broadcast(vperm_buf, 0)
 
         graph = None
-        if world == 1 and os.environ.get("SBI_B200_FMPE_GRAPH", "1") != "0" and steps > 0:
+        if (world == 1 or peer is not None) and os.environ.get("SBI_B200_FMPE_GRAPH", "1") != "0" and steps > 0:
             snap = (net.flat.data.clone(), self._opt_state.clone(), self._opt_step.clone())
             fill_perms()
             side = torch.cuda.Stream()
@@ -722,17 +867,20 @@ class FMPE(_FlowTrainer):
                 graph.replay()
             else:
                 run_epoch()
-            tl, tb, vl, vb = stats.tolist()      # the one host sync of the epoch
+            tl, tb, vl, vb = self._dp_sum(stats.tolist())      # the one host sync of the epoch
             if tb > 0 or vb > 0:
                 raise AssertionError("NaN/Inf present in FMPE loss.")
-            train_loss = tl / (steps * B)
-            val_loss = vl / (vsteps * Bv * vt.shape[0]) if vsteps > 0 else float("nan")
+            train_loss = tl / (steps * Btot)
+            val_loss = vl / (vsteps * Bv * (1 if glob else world) * vt.shape[0]) if vsteps > 0 else float("nan")
             # the reference normalises by len(loader) * loader.batch_size, i.e. WITHOUT the repeat over times
             val_loss *= vt.shape[0] if vsteps > 0 else 1.0
+            # base.py:1110 keeps the RAW validation loss in self._val_loss (what _converged compares
+            # with the best loss); only the summaries hold the exponential moving averages
+            # (base_vf_inference.py:589-636), whose spread normalises the stopping rule
+            self._val_loss = val_loss
             if self._summary["training_loss"]:
                 train_loss = (1 - ema_loss_decay) * self._summary["training_loss"][-1] + ema_loss_decay * train_loss
                 val_loss = (1 - ema_loss_decay) * self._summary["validation_loss"][-1] + ema_loss_decay * val_loss
-            self._val_loss = val_loss
             self._summary["training_loss"].append(train_loss)
             self._summary["validation_loss"].append(val_loss)
             self._summary["epoch_durations_sec"].append(time.time() - t0)
@@ -744,6 +892,11 @@ class FMPE(_FlowTrainer):
                 net.flat.data.copy_(self._best_flat)
         self._summary["epochs_trained"].append(self.epoch)
         self._summary["best_validation_loss"].append(self._best_val_loss)
+        if peer is not None:
+            timed_out = peer.error()
+            peer.close()
+            if timed_out:
+                raise RuntimeError("peer-memory gradient exchange timed out (a rank fell behind or died)")
         return deepcopy(net)
 
     def build_posterior(self, density_estimator=None, prior=None, sample_with: str = "ode", **kwargs):

@@ -223,6 +223,8 @@ def _density_build_fn(model: str, input_is_theta: bool, **kw) -> Callable:
     builder = _BUILDERS[model]
 
     def build_fn(batch_theta, batch_x):
+        from ._refabc import register_with_reference
+        register_with_reference()   # virtual subclass of the reference's ABCs if sbi is imported
         if input_is_theta:   # NPE models p(theta | x)
             return builder(batch_x=batch_theta, batch_y=batch_x, **kw)
         return builder(batch_x=batch_x, batch_y=batch_theta, **kw)   # NLE: p(x | theta)

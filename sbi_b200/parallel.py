@@ -97,7 +97,10 @@ class PeerGradientSum:
     between their GPUs; construction is collective (handles are exchanged with all_gather_object).
 
         ex = PeerGradientSum(n_params)                       # once, on every rank
-        ex.sum(grad_local, grad_out, mask, sumsq, opt_step)  # every step, graph-capturable
+        ex.sum(grad_local, grad_out, mask, sumsq)            # every step, graph-capturable
+    The step number that tags the flags is the exchange's own device counter (it only grows: a
+    warm-up pass whose optimizer state is rewound afterwards cannot leave matching flags); pass
+    `opt_step` to tag with a caller-owned counter instead (all ranks must then agree on it).
     """
 
     def __init__(self, n_params: int):
@@ -139,7 +142,7 @@ class PeerGradientSum:
                                "mapping failed on at least one rank)")
 
     def sum(self, grad_local: Tensor, grad_out: Tensor, mask: Optional[Tensor], sumsq: Optional[Tensor],
-            opt_step: Tensor) -> None:
+            opt_step: Optional[Tensor] = None) -> None:
         L, C = self._L, self._C
         L.check(self.lib.sbi_b200_peer_sum(L.ptr(grad_local), self._ptrs, self.world, self.rank, self.n,
                                            L.ptr(grad_out), L.ptr(mask), L.ptr(sumsq), L.ptr(opt_step),

@@ -292,6 +292,8 @@ def classifier_nn(
         raise NotImplementedError(f"sbi_b200 implements the 'resnet' classifier on sm_100a; got {model!r}.")
 
     def build_fn(batch_theta, batch_x):
+        from ._refabc import register_with_reference
+        register_with_reference()
         return build_resnet_classifier(
             batch_x=batch_theta, batch_y=batch_x, z_score_x=z_score_theta, z_score_y=z_score_x,
             hidden_features=hidden_features, embedding_net_x=embedding_net_theta,

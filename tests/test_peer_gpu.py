@@ -126,7 +126,7 @@ def _train_worker(rank, world, port, q):
     theta = prior.sample((4000,))
     x = theta + math.sqrt(0.1) * torch.randn_like(theta)
     torch.manual_seed(0)                               # same split / permutation stream on every rank
-    inf = NPE(prior, density_estimator="nsf", device=f"cuda:{rank}").data_parallel()
+    inf = NPE(prior, density_estimator="nsf", device=f"cuda:{rank}").data_parallel("local")
     est = inf.append_simulations(theta, x).train(training_batch_size=500, max_num_epochs=6)
     flat = est.flat.data.clone()
     both = [torch.zeros_like(flat) for _ in range(world)]
@@ -157,3 +157,131 @@ def test_data_parallel_training_two_gpus(cuda_lib):
     for rank, same, vl in res:
         assert same, f"rank {rank}: replicas diverged"
         assert all(v == v for v in vl) and vl[-1] < vl[0], vl
+
+
+def _run2(target, timeout=600, world=2):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs on one node")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=timeout) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return sorted(res)
+
+
+def _init(rank, world, port):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    return dist
+
+
+def _lg(n, D, seed):
+    import math
+    from torch.distributions import MultivariateNormal
+    torch.manual_seed(seed)
+    prior = MultivariateNormal(torch.zeros(D), 0.1 * torch.eye(D))
+    theta = prior.sample((n,))
+    return prior, theta, theta + math.sqrt(0.1) * torch.randn_like(theta)
+
+
+def _identical(dist, flat, world):
+    both = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    return all(torch.equal(both[0], b) for b in both)
+
+
+def _few_steps_worker(rank, world, port, q):
+    """epochs of 1, 2 and 3 steps.  The warm-up epoch runs through the exchange and the
+    optimizer state is rewound afterwards; the exchange's flags must not match the first real steps.
+    At world size 2 the rank-order sum a+b equals NCCL's, so the peer path must reproduce the NCCL
+    path up to the rounding of the clip norm."""
+    from sbi_b200.inference import NPE
+    dist = _init(rank, world, port)
+    out = []
+    for B in (3600, 1800, 1200):
+        flats = []
+        for nccl in ("0", "1"):
+            os.environ["SBI_B200_NCCL"] = nccl
+            prior, theta, x = _lg(4000, 3, 10 + rank)
+            torch.manual_seed(0)
+            inf = NPE(prior, density_estimator="nsf", device=f"cuda:{rank}").data_parallel("local")
+            est = inf.append_simulations(theta, x).train(training_batch_size=B, max_num_epochs=4)
+            flats.append(est.flat.data.clone())
+        os.environ["SBI_B200_NCCL"] = "0"
+        d = (flats[0] - flats[1]).abs()
+        out.append((B, _identical(dist, flats[0], world), float((d > 5e-5).float().mean()), float(d.max())))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_epochs_of_one_to_three_steps(cuda_lib):
+    for rank, out in _run2(_few_steps_worker):
+        for B, same, frac_off, dmax in out:
+            assert same, f"rank {rank} B={B}: replicas diverged"
+            # (the two paths take the clip norm in different summation orders, so equality is up to
+            # rounding; one stale gradient moves every weight by ~lr = 5e-4)
+            assert frac_off < 1e-3, f"rank {rank} B={B}: peer path differs from the NCCL path " \
+                                    f"({100 * frac_off:.2f}% of the weights by > 5e-5, max {dmax:.3e})"
+
+
+def _global_worker(rank, world, port, q):
+    """partition='global' (SURVEY 8e): same data on every rank, rank 0's split and epoch orders, rank r
+    takes rows [r*B/G, (r+1)*B/G) of each global batch: the run equals the single-GPU run up to the
+    summation order of the gradient partials."""
+    from sbi_b200.inference import FMPE, NPE, NRE_B
+    dist = _init(rank, world, port)
+    prior, theta, x = _lg(4000, 3, 5)                   # identical data on every rank
+    res = {}
+    torch.manual_seed(0)
+    inf = NPE(prior, density_estimator="nsf", device=f"cuda:{rank}").data_parallel("global")
+    est = inf.append_simulations(theta, x).train(training_batch_size=400, max_num_epochs=3)
+    res["npe_same"] = _identical(dist, est.flat.data, world)
+    res["npe_val"] = list(inf.summary["validation_loss"])
+    res["npe_train"] = list(inf.summary["training_loss"])
+    if rank == 0:   # the single-process run on the same seeds
+        torch.manual_seed(0)
+        solo = NPE(prior, density_estimator="nsf", device="cuda:0")
+        solo.append_simulations(theta, x).train(training_batch_size=400, max_num_epochs=3)
+        res["solo_val"] = list(solo.summary["validation_loss"])
+        res["solo_train"] = list(solo.summary["training_loss"])
+    dist.barrier()
+    torch.manual_seed(1)
+    fm = FMPE(prior, device=f"cuda:{rank}").data_parallel("global")
+    e2 = fm.append_simulations(theta, x).train(training_batch_size=400, max_num_epochs=4)
+    res["fm_same"] = _identical(dist, e2.flat.data, world)
+    res["fm_train"] = list(fm.summary["training_loss"])
+    torch.manual_seed(2)
+    nre = NRE_B(prior, device=f"cuda:{rank}").data_parallel("global")
+    e3 = nre.append_simulations(theta, x).train(training_batch_size=400, max_num_epochs=4)
+    res["nre_same"] = _identical(dist, e3.flat.data, world)
+    res["nre_val"] = list(nre.summary["validation_loss"])
+    torch.manual_seed(3 + rank)                         # weak mode for the other two trainers
+    fm = FMPE(prior, device=f"cuda:{rank}").data_parallel("local")
+    e4 = fm.append_simulations(theta, x).train(training_batch_size=400, max_num_epochs=3)
+    res["fm_local_same"] = _identical(dist, e4.flat.data, world)
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_global_batch_data_parallel_all_trainers(cuda_lib):
+    out = dict(_run2(_global_worker, timeout=900))
+    for rank, res in out.items():
+        for k in ("npe_same", "fm_same", "nre_same", "fm_local_same"):
+            assert res[k], f"rank {rank}: {k} failed (replicas diverged)"
+        assert res["fm_train"][-1] < res["fm_train"][0]
+        assert res["nre_val"][-1] < res["nre_val"][0]
+    r0 = out[0]
+    # same batches, same updates: the loss curves of the 2-GPU and the 1-GPU run agree
+    for a, b in zip(r0["npe_train"] + r0["npe_val"], r0["solo_train"] + r0["solo_val"]):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (r0["npe_train"], r0["solo_train"], r0["npe_val"], r0["solo_val"])
