@@ -385,6 +385,21 @@ int sbi_b200_nsf_train_step_host_async(const sbi_nsf_model* m, const sbi_train_w
 /* wait for the last enqueued step and return its result in h_loss_last[2] */
 int sbi_b200_pipe_drain(void* pipe, float* h_loss_last);
 
+/* Data-parallel pipelined host step (one process per GPU): as sbi_b200_nsf_train_step_host_async, with the
+ * gradient sum over NVLink peer memory (sbi_b200_peer_sum, exchange-owned step counter) between the
+ * partial-gradient reduction and clip+Adam; rows of all ranks form one global batch of B * world rows
+ * (reference semantics: one optimizer step on the mean loss of the global batch,
+ * sbi/inference/trainers/base.py:1171-1187).  ws->d_sumsq must hold sbi_b200_peer_blocks(n_params) floats. */
+typedef struct {
+  void* const* h_peer_ptrs;   /* (world) symmetric buffers, own buffer at [rank] (host array) */
+  int world, rank;
+  float* d_grad_local;        /* (n_params) scratch for this rank's reduced gradient */
+} sbi_peer_ctx;
+int sbi_b200_nsf_train_step_host_async_dp(const sbi_nsf_model* m, const sbi_train_ws* ws, void* pipe,
+                                          const sbi_peer_ctx* peer, const float* h_input, const float* h_cond,
+                                          int64_t B, float lr, float beta1, float beta2, float eps,
+                                          float max_norm, float* h_loss_prev, void* stream);
+
 /* log q(input_r | cond) for R host rows (cond: (R,C), or (1,C) when cond_shared). */
 int sbi_b200_nsf_logprob_host(const sbi_nsf_model* m, const sbi_train_ws* ws,
                               const float* h_input, const float* h_cond, int64_t R,

@@ -124,6 +124,10 @@ class TrainWs(C.Structure):
     ]
 
 
+class PeerCtx(C.Structure):
+    _fields_ = [("h_peer_ptrs", C.c_void_p), ("world", C.c_int), ("rank", C.c_int), ("d_grad_local", C.c_void_p)]
+
+
 _EXPORTS = {
     "sbi_b200_abi_version": (C.c_int, []),
     "sbi_b200_device_ok": (C.c_int, []),
@@ -187,6 +191,10 @@ _EXPORTS = {
                                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                                      C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "sbi_b200_pipe_drain": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sbi_b200_nsf_train_step_host_async_dp": (C.c_int, [C.POINTER(NsfModel), C.POINTER(TrainWs), C.c_void_p,
+                                                        C.POINTER(PeerCtx), C.c_void_p, C.c_void_p, C.c_int64,
+                                                        C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                                        C.c_void_p, C.c_void_p]),
     "sbi_b200_nsf_logprob_host": (C.c_int, [C.POINTER(NsfModel), C.POINTER(TrainWs), C.c_void_p,
                                             C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                             C.c_void_p]),

@@ -201,6 +201,50 @@ extern "C" int sbi_b200_nsf_train_step_host_async(const sbi_nsf_model* m, const 
   return rc;
 }
 
+// Data-parallel variant of the pipelined host step (one process per GPU): between the reduction
+// of the per-CTA partial gradients and clip+Adam the flat gradients of all ranks are summed over
+// NVLink peer memory (sbi_b200_peer_sum, csrc/peer.cu; it also emits the sum(g^2) partials).  The
+// upstream gradient is -1/(B * world): rows of all ranks form one global batch.
+extern "C" int sbi_b200_nsf_train_step_host_async_dp(const sbi_nsf_model* m, const sbi_train_ws* ws, void* pipe,
+                                                     const sbi_peer_ctx* peer, const float* h_input,
+                                                     const float* h_cond, int64_t B, float lr, float beta1,
+                                                     float beta2, float eps, float max_norm,
+                                                     float* h_loss_prev, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
+  SbiPipe* p = static_cast<SbiPipe*>(pipe);
+  if (!m || !ws || !p || !peer || !peer->h_peer_ptrs || !peer->d_grad_local || !ws->d_sumsq || !h_input ||
+      !h_cond || B < 1 || B > ws->cap_rows || peer->world < 1)
+    return SBI_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int slot = (int)(p->n & 1);
+  CK(cudaMemcpyAsync(ws->d_input, h_input, sizeof(float) * B * m->D, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ws->d_cond, h_cond, sizeof(float) * B * m->C, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ws->d_loss_acc, 0, 2 * sizeof(float), s));
+  sbi_rows rows;
+  rows.d_input = ws->d_input;
+  rows.d_cond = ws->d_cond;
+  rows.d_index = nullptr;
+  rows.R = B;
+  rows.cond_shared = 0;
+  int rc = sbi_b200_nsf_vjp(m, &rows, nullptr, -1.0f / ((float)B * (float)peer->world), nullptr, ws->d_gpart,
+                            nullptr, nullptr, ws->d_loss_acc, stream);
+  if (rc) return rc;
+  rc = sbi_b200_reduce_partials(ws->d_gpart, sbi_b200_nsf_vjp_parts(B), m->n_params, peer->d_grad_local, stream);
+  if (rc) return rc;
+  rc = sbi_b200_peer_sum(peer->d_grad_local, peer->h_peer_ptrs, peer->world, peer->rank, m->n_params,
+                         ws->d_grad, ws->d_mask, ws->d_sumsq, nullptr, stream);
+  if (rc) return rc;
+  rc = sbi_b200_adam_clip_step_norm(const_cast<float*>(m->d_params), ws->d_grad, ws->d_state, ws->d_step,
+                                    ws->d_mask, m->n_params, lr, beta1, beta2, eps, max_norm, 1.0f,
+                                    ws->d_sumsq, sbi_b200_peer_blocks(m->n_params), stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(p->h_loss[slot], ws->d_loss_acc, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(p->done[slot], s));
+  rc = pipe_wait_prev(p, h_loss_prev);
+  p->n += 1;
+  return rc;
+}
+
 extern "C" int sbi_b200_pipe_drain(void* pipe, float* h_loss_last) {
   sbi::DeviceGuard dev_guard_(pipe);
   SbiPipe* p = static_cast<SbiPipe*>(pipe);
