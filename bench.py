@@ -354,7 +354,7 @@ class StepRunner:
         P = est.layout.n_params
         self.P = P
         dev = cx.dev
-        self.n_part = lib.sbi_b200_nsf_vjp_parts(rows)
+        self.n_part = est.vjp_parts(rows)          # tensor-core step: one slab per 128-row tile
         self.gpart = torch.zeros(self.n_part, P, device=dev)
         self.grad = torch.zeros(P, device=dev)
         self.grad_local = torch.zeros(P, device=dev) if peer is not None else self.grad
@@ -365,7 +365,8 @@ class StepRunner:
         self.mask = est.net._mask
         self.idx_pool = torch.stack([torch.randperm(n_train, device=dev)[:rows] for _ in range(16)])
         self.graphs = None
-        self.launches_per_step = 4 if peer is not None else 3
+        # kernels per step: [operand pack + forward + backward | SIMT vjp] + reduce [+ peer sum] + clip/Adam
+        self.launches_per_step = (3 if est._vjp_uses_tc(rows, True) else 1) + (3 if peer is not None else 2)
 
     def step(self, i):
         cx, L, lib, est, P = self.cx, self.cx.L, self.cx.lib, self.est, self.P
@@ -373,8 +374,7 @@ class StepRunner:
         m = est._model(nbuf=3)
         idx = self.idx_pool[i % self.idx_pool.shape[0]]
         rows = L.Rows(self.theta_d.data_ptr(), self.x_d.data_ptr(), idx.data_ptr(), self.rows, 0)
-        L.check(lib.sbi_b200_nsf_vjp(C.byref(m), C.byref(rows), None, -1.0 / (self.rows * world), None,
-                                     L.ptr(self.gpart), None, None, L.ptr(self.loss_acc), L.stream_ptr()), "vjp")
+        est.vjp(m, rows, self.rows, None, -1.0 / (self.rows * world), None, self.gpart, None, None, self.loss_acc)
         if self.peer is not None:
             L.check(lib.sbi_b200_reduce_partials(L.ptr(self.gpart), self.n_part, P, L.ptr(self.grad_local),
                                                  L.stream_ptr()), "reduce")
@@ -496,8 +496,7 @@ def run_cfg2(args):
         idx = run.idx_pool[i % run.idx_pool.shape[0]]
         rows = L.Rows(theta_d.data_ptr(), x_d.data_ptr(), idx.data_ptr(), B, 0)
         kev[i][0].record()
-        L.check(lib.sbi_b200_nsf_vjp(C.byref(m), C.byref(rows), None, -1.0 / B, None, L.ptr(run.gpart),
-                                     None, None, None, L.stream_ptr()), "vjp")
+        est.vjp(m, rows, B, None, -1.0 / B, None, run.gpart, None, None, None)
         kev[i][1].record()
     torch.cuda.synchronize()
     vjp_ms = sum(a.elapsed_time(b) for a, b in kev) / K
@@ -507,7 +506,7 @@ def run_cfg2(args):
     peaks = _peaks()
     achieved = alg_bytes / (vjp_ms * 1e-3) / 1e9
     traffic = _traffic()
-    vjp_info = _vjp_kernel_info()
+    vjp_info = _vjp_kernel_info(est, B)
 
     # ---- log_prob leg (secondary metric) ---------------------------------------------------------
     R = LOGPROB_ROWS
@@ -539,6 +538,11 @@ def run_cfg2(args):
     ws.d_step, ws.d_mask, ws.d_loss_acc = run.step_ctr.data_ptr(), run.mask.data_ptr(), run.loss_acc.data_ptr()
     ws.cap_rows = st_in.shape[0]
     ws.d_sumsq = run.sumsq.data_ptr()
+    tc_keep = est._tc_train_state(est._model(nbuf=3), pack=False) if est._vjp_uses_tc(B, True) else None
+    if tc_keep is not None:      # the host step runs the tensor-core forward+backward pair
+        save = torch.empty(int(lib.sbi_b200_nsf_vjp_tc_save_bytes(C.byref(est._model(nbuf=3)), B)) // 4 + 1, device=dev)
+        ws.tc_fwd, ws.tc_bwd, ws.tc_pack = (C.addressof(tc_keep[0]), C.addressof(tc_keep[1]), C.addressof(tc_keep[2]))
+        ws.d_save, ws.save_bytes = save.data_ptr(), save.numel() * 4
     h_th2 = [torch.empty(B, DIM).pin_memory() for _ in range(2)]
     h_x2 = [torch.empty(B, DIM).pin_memory() for _ in range(2)]
     h_loss = torch.zeros(2).pin_memory()
@@ -569,8 +573,7 @@ def run_cfg2(args):
             st_c[:B].copy_(b, non_blocking=True)
             run.loss_acc.zero_()
             rows = L.Rows(st_in.data_ptr(), st_c.data_ptr(), None, B, 0)
-            L.check(lib.sbi_b200_nsf_vjp(C.byref(mm), C.byref(rows), None, -1.0 / (B * world), None, L.ptr(run.gpart),
-                                         None, None, L.ptr(run.loss_acc), L.stream_ptr()), "vjp")
+            est.vjp(mm, rows, B, None, -1.0 / (B * world), None, run.gpart, None, None, run.loss_acc)
             L.check(lib.sbi_b200_reduce_partials(L.ptr(run.gpart), run.n_part, P, L.ptr(run.grad), L.stream_ptr()), "reduce")
             dist.all_reduce(run.grad)
             L.check(lib.sbi_b200_adam_clip_step(L.ptr(est.flat.data), L.ptr(run.grad), L.ptr(run.state),
@@ -707,16 +710,13 @@ def run_cfg2(args):
     cx.finish()
 
 
-def _vjp_kernel_info():
-    """Which VJP kernel the library dispatches to at B = 4096 (name for the roofline entry)."""
-    if os.environ.get("SBI_B200_VJP_TC", "1") != "0":
-        try:
-            from sbi_b200 import _lib as L
-            if hasattr(L.load(), "sbi_b200_nsf_vjp_tc_active") and L.load().sbi_b200_nsf_vjp_tc_active():
-                return {"kernel": "nsf_vjp_tc_kernel (tcgen05)", "traffic_key": "nsf_vjp_tc_kernel"}
-        except Exception:
-            pass
-    return {"kernel": "nsf_vjp_kernel<32,2,2,true>", "traffic_key": "nsf_vjp_kernel"}
+def _vjp_kernel_info(est=None, B=BATCH):
+    """Which VJP kernels the library dispatches to at B rows (names for the roofline entry)."""
+    if est is not None and est._vjp_uses_tc(B, True):
+        return {"kernel": "nsf_logprob_tc_kernel<50,10,false,SAVE> + nsf_vjp_tc_kernel<50,10> (tcgen05 forward + "
+                          "backward pair; operand re-pack included in the timing)",
+                "traffic_key": "nsf_vjp_tc", "tc": True}
+    return {"kernel": "nsf_vjp_kernel<32,2,2,true>", "traffic_key": "nsf_vjp_kernel", "tc": False}
 
 
 def _lp_roofline(tc_used, lp_bytes, lp_flops, lp_ms, peaks):

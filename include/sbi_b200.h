@@ -173,6 +173,25 @@ int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc, const 
 int sbi_b200_nsf_inverse_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc, const sbi_rows* rows,
                             float* d_out, float* d_logabsdet, void* stream);
 
+/* ---- tensor-core training step (csrc/nsf_tc.cu forward sweep with activation save + csrc/nsf_vjp_tc.cu
+ * backward sweep): the parameter gradients of  sum_r g_r log q(input_r | cond_r)  -- what
+ * sbi_b200_nsf_vjp computes with d_ginput == d_gcond == NULL, i.e. NFlowsFlow.loss + autograd backward of a
+ * training batch (sbi/neural_nets/estimators/nflows_flow.py:99-109, sbi/inference/trainers/base.py:1171-1180)
+ * -- with every conditioner linear (forward, input gradient, weight gradient) on tcgen05.mma kind::tf32.
+ *   tc_fwd: operand plan of the forward linears (pack.NsfLayout.tc_plan), as for sbi_b200_nsf_logprob_tc;
+ *   tc_bwd: operand plan of the transposed linears (pack.NsfLayout.tc_bwd_plan), same descriptor format;
+ *           both must have been packed from the current parameters (sbi_b200_nsf_tc_pack);
+ *   d_gpart: (sbi_b200_nsf_vjp_tc_parts(R), n_params) partial gradients, reduce with sbi_b200_reduce_partials;
+ *   d_save : caller-owned activation scratch of at least sbi_b200_nsf_vjp_tc_save_bytes(m, R) bytes
+ *            (one slab per 128-row tile in flight: 3 KB per row and layer);
+ *   d_logp (R) and d_loss_acc (2: sum of -log q over finite rows, number of non-finite rows) optional. */
+int sbi_b200_nsf_vjp_tc_supported(const sbi_nsf_model* m, const sbi_nsf_tc* tc_fwd, const sbi_nsf_tc* tc_bwd);
+int sbi_b200_nsf_vjp_tc_parts(int64_t R);
+int64_t sbi_b200_nsf_vjp_tc_save_bytes(const sbi_nsf_model* m, int64_t R);
+int sbi_b200_nsf_vjp_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc_fwd, const sbi_nsf_tc* tc_bwd,
+                        const sbi_rows* rows, const float* d_gout, float g_const, float* d_logp,
+                        float* d_gpart, float* d_loss_acc, float* d_save, int64_t save_bytes, void* stream);
+
 /* ---- masked autoregressive flow (sbi `posterior_nn("maf")`, reference builder
  * sbi/neural_nets/net_builders/flow.py:115-209: T x [MaskedAffineAutoregressiveTransform(MADE,
  * feed-forward blocks, tanh) + RandomPermutation], z-scored input, standardised context).
@@ -360,6 +379,15 @@ typedef struct {
   float* d_loss_acc;     /* (2) */
   int64_t cap_rows;
   float* d_sumsq;        /* (sbi_b200_sumsq_blocks(n_params)) scratch for the clip norm, or NULL */
+  /* optional: run the step's forward+backward on the tensor cores (sbi_b200_nsf_vjp_tc); all NULL / 0
+   * selects the SIMT kernel.  tc_pack covers both operand plans (one sbi_b200_nsf_tc_pack launch per
+   * step re-packs them from the just-updated parameters); d_gpart must then hold
+   * sbi_b200_nsf_vjp_tc_parts(B) slabs and d_save sbi_b200_nsf_vjp_tc_save_bytes(m, B) bytes. */
+  const sbi_nsf_tc* tc_pack;
+  const sbi_nsf_tc* tc_fwd;
+  const sbi_nsf_tc* tc_bwd;
+  float* d_save;
+  int64_t save_bytes;
 } sbi_train_ws;
 
 /* One optimisation step on a host batch (replaces one iteration of

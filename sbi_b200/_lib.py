@@ -121,6 +121,8 @@ class TrainWs(C.Structure):
         ("d_gpart", C.c_void_p), ("d_grad", C.c_void_p), ("d_state", C.c_void_p),
         ("d_step", C.c_void_p), ("d_mask", C.c_void_p), ("d_loss_acc", C.c_void_p),
         ("cap_rows", C.c_int64), ("d_sumsq", C.c_void_p),
+        ("tc_pack", C.c_void_p), ("tc_fwd", C.c_void_p), ("tc_bwd", C.c_void_p),
+        ("d_save", C.c_void_p), ("save_bytes", C.c_int64),
     ]
 
 
@@ -145,6 +147,12 @@ _EXPORTS = {
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_nsf_inverse_tc": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc), C.POINTER(Rows),
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sbi_b200_nsf_vjp_tc_supported": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc), C.POINTER(NsfTc)]),
+    "sbi_b200_nsf_vjp_tc_parts": (C.c_int, [C.c_int64]),
+    "sbi_b200_nsf_vjp_tc_save_bytes": (C.c_int64, [C.POINTER(NsfModel), C.c_int64]),
+    "sbi_b200_nsf_vjp_tc": (C.c_int, [C.POINTER(NsfModel), C.POINTER(NsfTc), C.POINTER(NsfTc), C.POINTER(Rows),
+                                      C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_void_p]),
     "sbi_b200_maf_logprob": (C.c_int, [C.POINTER(MafModel), C.POINTER(Rows), C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "sbi_b200_maf_vjp_parts": (C.c_int, [C.c_int64]),

@@ -10,10 +10,31 @@
     if (e_ != cudaSuccess) return (int)e_; \
   } while (0)
 
+// forward+backward of the staged batch: tensor-core kernels when the workspace carries their operand
+// descriptors, else the SIMT kernel.  Returns the number of partial-gradient slabs written in *n_part.
+static int vjp_staged(const sbi_nsf_model* m, const sbi_train_ws* ws, int64_t B, float g_const, int* n_part,
+                      void* stream) {
+  sbi_rows rows;
+  rows.d_input = ws->d_input;
+  rows.d_cond = ws->d_cond;
+  rows.d_index = nullptr;
+  rows.R = B;
+  rows.cond_shared = 0;
+  if (ws->tc_fwd != nullptr && ws->tc_bwd != nullptr && ws->tc_pack != nullptr && ws->d_save != nullptr) {
+    int rc = sbi_b200_nsf_tc_pack(m, ws->tc_pack, stream);
+    if (rc) return rc;
+    *n_part = sbi_b200_nsf_vjp_tc_parts(B);
+    return sbi_b200_nsf_vjp_tc(m, ws->tc_fwd, ws->tc_bwd, &rows, nullptr, g_const, nullptr, ws->d_gpart,
+                               ws->d_loss_acc, ws->d_save, ws->save_bytes, stream);
+  }
+  *n_part = sbi_b200_nsf_vjp_parts(B);
+  return sbi_b200_nsf_vjp(m, &rows, nullptr, g_const, nullptr, ws->d_gpart, nullptr, nullptr, ws->d_loss_acc,
+                          stream);
+}
+
 // partial-gradient reduction (+ per-block sum of squares when the workspace has room) -> clip + Adam
-static int reduce_and_step(const sbi_nsf_model* m, const sbi_train_ws* ws, int64_t B, float lr, float beta1,
+static int reduce_and_step(const sbi_nsf_model* m, const sbi_train_ws* ws, int n_part, float lr, float beta1,
                            float beta2, float eps, float max_norm, void* stream) {
-  const int n_part = sbi_b200_nsf_vjp_parts(B);
   if (ws->d_sumsq != nullptr) {
     int rc = sbi_b200_reduce_partials_norm(ws->d_gpart, n_part, m->n_params, ws->d_grad, ws->d_mask,
                                            ws->d_sumsq, stream);
@@ -39,16 +60,10 @@ extern "C" int sbi_b200_nsf_train_step_host(const sbi_nsf_model* m, const sbi_tr
   CK(cudaMemcpyAsync(ws->d_input, h_input, sizeof(float) * B * m->D, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ws->d_cond, h_cond, sizeof(float) * B * m->C, cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(ws->d_loss_acc, 0, 2 * sizeof(float), s));
-  sbi_rows rows;
-  rows.d_input = ws->d_input;
-  rows.d_cond = ws->d_cond;
-  rows.d_index = nullptr;
-  rows.R = B;
-  rows.cond_shared = 0;
-  int rc = sbi_b200_nsf_vjp(m, &rows, nullptr, -1.0f / (float)B, nullptr, ws->d_gpart, nullptr,
-                            nullptr, ws->d_loss_acc, stream);
+  int n_part = 0;
+  int rc = vjp_staged(m, ws, B, -1.0f / (float)B, &n_part, stream);
   if (rc) return rc;
-  rc = reduce_and_step(m, ws, B, lr, beta1, beta2, eps, max_norm, stream);
+  rc = reduce_and_step(m, ws, n_part, lr, beta1, beta2, eps, max_norm, stream);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h_loss_out, ws->d_loss_acc, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -183,16 +198,10 @@ extern "C" int sbi_b200_nsf_train_step_host_async(const sbi_nsf_model* m, const 
   CK(cudaMemcpyAsync(ws->d_input, h_input, sizeof(float) * B * m->D, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ws->d_cond, h_cond, sizeof(float) * B * m->C, cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(ws->d_loss_acc, 0, 2 * sizeof(float), s));
-  sbi_rows rows;
-  rows.d_input = ws->d_input;
-  rows.d_cond = ws->d_cond;
-  rows.d_index = nullptr;
-  rows.R = B;
-  rows.cond_shared = 0;
-  int rc = sbi_b200_nsf_vjp(m, &rows, nullptr, -1.0f / (float)B, nullptr, ws->d_gpart, nullptr, nullptr,
-                            ws->d_loss_acc, stream);
+  int n_part = 0;
+  int rc = vjp_staged(m, ws, B, -1.0f / (float)B, &n_part, stream);
   if (rc) return rc;
-  rc = reduce_and_step(m, ws, B, lr, beta1, beta2, eps, max_norm, stream);
+  rc = reduce_and_step(m, ws, n_part, lr, beta1, beta2, eps, max_norm, stream);
   if (rc) return rc;
   CK(cudaMemcpyAsync(p->h_loss[slot], ws->d_loss_acc, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(p->done[slot], s));
@@ -220,16 +229,10 @@ extern "C" int sbi_b200_nsf_train_step_host_async_dp(const sbi_nsf_model* m, con
   CK(cudaMemcpyAsync(ws->d_input, h_input, sizeof(float) * B * m->D, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ws->d_cond, h_cond, sizeof(float) * B * m->C, cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(ws->d_loss_acc, 0, 2 * sizeof(float), s));
-  sbi_rows rows;
-  rows.d_input = ws->d_input;
-  rows.d_cond = ws->d_cond;
-  rows.d_index = nullptr;
-  rows.R = B;
-  rows.cond_shared = 0;
-  int rc = sbi_b200_nsf_vjp(m, &rows, nullptr, -1.0f / ((float)B * (float)peer->world), nullptr, ws->d_gpart,
-                            nullptr, nullptr, ws->d_loss_acc, stream);
+  int n_part = 0;
+  int rc = vjp_staged(m, ws, B, -1.0f / ((float)B * (float)peer->world), &n_part, stream);
   if (rc) return rc;
-  rc = sbi_b200_reduce_partials(ws->d_gpart, sbi_b200_nsf_vjp_parts(B), m->n_params, peer->d_grad_local, stream);
+  rc = sbi_b200_reduce_partials(ws->d_gpart, n_part, m->n_params, peer->d_grad_local, stream);
   if (rc) return rc;
   rc = sbi_b200_peer_sum(peer->d_grad_local, peer->h_peer_ptrs, peer->world, peer->rank, m->n_params,
                          ws->d_grad, ws->d_mask, ws->d_sumsq, nullptr, stream);

@@ -36,6 +36,7 @@
 #include "nsf.cuh"
 
 #include "tc_common.cuh"
+#include "nsf_tc_save.cuh"
 #include "device.cuh"
 
 namespace sbi {
@@ -216,11 +217,16 @@ __device__ __forceinline__ void rqs_inverse_fast(const float (&p)[32], const Rqs
 // INV = true : sampling direction x = T^{-1}(noise | cond): rows.d_input holds the noise, the
 //              layers run T-1 .. 0 with LU^{-1} first and the inverse spline; `noise` receives x
 //              (R,D) and `logp` (optional) log|det dx/dnoise|  (sbi_b200_nsf_inverse).
-template <int H, int KB, bool INV>
+//
+// SAVE = true (training forward, INV = false): every layer's conditioner intermediates, raw spline
+// parameters, layer input and coupling output of the tile go to the activation scratch `save`
+// (layout: nsf_tc_save.cuh) for the tensor-core backward kernel (nsf_vjp_tc.cu), together with the
+// final base-space point and the row's log-density.
+template <int H, int KB, bool INV, bool SAVE = false>
 __global__ void __launch_bounds__(kThreads, 2)
 nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ sbi_nsf_tc tc,
                       const __grid_constant__ sbi_rows rows, float* __restrict__ logp,
-                      float* __restrict__ noise) {
+                      float* __restrict__ noise, float* __restrict__ save) {
   constexpr int HP8 = (H + 7) & ~7;
   constexpr int NCH = HP8 / 8;      // K-steps / 8-column chunks of the hidden operand
   constexpr int KC0 = H / 8;        // first chunk that holds context columns
@@ -237,6 +243,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
   const int C = m.C;
   const int nkc = (H + C + 7) / 8 - KC0;     // K-steps that cover the context columns
   const int64_t ntiles = (rows.R + kRows - 1) / kRows;
+  const TcSave SV = tc_save_layout(m.NB, m.TRmax, m.T);
 
   if (tid == 0) {
     for (int s = 0; s < kSlots; ++s) mbar_init(&full[s], 1);
@@ -435,6 +442,8 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
       const int kid8 = __ldg(tab + 1);
       int stage = 0;
       float h[NC];
+      float* svl = SAVE ? save + (size_t)tile * SV.tile_stride + (size_t)l * SV.layer_stride : nullptr;
+      if (SAVE && half == 1) tc_save_row16(svl + SV.zin, row, zs, D);      // layer input z_l
 
       // ---- sampling: z <- U^{-1} L^{-1} (z - b) on the thread's row (order of lu_inverse, nsf.cuh)
       if (INV && half == 1 && __ldg(v.LT + SBI_L_HAS_LU)) {
@@ -527,6 +536,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
         const float* b2 = b1 + 64;
         const float* bc = b1 + 128;
         // A = [relu(h) | ctx]
+        if (SAVE) tc_save_cols<NC>(svl + SV.h(b), row, half, h);
         {
           float a[NC];
 #pragma unroll
@@ -553,6 +563,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           read_acc(cG, g);
 #pragma unroll
           for (int q = 0; q < NC; ++q) sg[q] = sigmoid_fast(g[q] + bc[q]);
+          if (SAVE) tc_save_cols<NC>(svl + SV.s(b), row, half, sg);
         }
         wait_acc(0);
         {
@@ -560,6 +571,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           read_acc(cD, d);
 #pragma unroll
           for (int q = 0; q < NC; ++q) d[q] = relu_f(d[q] + b1[q]);
+          if (SAVE) tc_save_cols<NC>(svl + SV.a1(b), row, half, d);
           write_a(d);
         }
         hand_over();
@@ -575,13 +587,22 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           // h += (W2 a + b2) * gate
           float d[NC];
           read_acc(cD, d);
+          if (SAVE) {
 #pragma unroll
-          for (int q = 0; q < NC; ++q) h[q] = fmaf(d[q] + b2[q], sg[q], h[q]);
+            for (int q = 0; q < NC; ++q) d[q] += b2[q];
+            tc_save_cols<NC>(svl + SV.t2(b), row, half, d);
+#pragma unroll
+            for (int q = 0; q < NC; ++q) h[q] = fmaf(d[q], sg[q], h[q]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < NC; ++q) h[q] = fmaf(d[q] + b2[q], sg[q], h[q]);
+          }
         }
       }
 
       // ---- final layer passes + spline on the transformed features ----
       {
+        if (SAVE) tc_save_cols<NC>(svl + SV.hf, row, half, h);
         write_a(h);
         const float* bf = bl + 64 + m.NB * 192;
         const int ns = __ldg(tab);
@@ -607,6 +628,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
             const float* bff = bf + (f0 + f) * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) q[i] = (i < 3 * KB - 1) ? q[i] + bff[i] : 0.f;
+            if (SAVE) tc_save_prm(svl + SV.prm, row, m.TRmax, f0 + f, q);
             const int j = __ldg(v.trf + f0 + f);
             const float x = zs[j * kRows + row];
             float y, ld;
@@ -631,6 +653,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
       // ---- LULinear on the row (half 1: it has one spline feature less, and it also writes the
       //      next layer's identity columns):  z <- L (U z) + b, in place ----
       group_sync();      // both halves' spline outputs are in zs
+      if (SAVE && half == 1) tc_save_row16(svl + SV.v, row, zs, D);         // coupling output v_l
       if (!INV && half == 1 && __ldg(v.LT + SBI_L_HAS_LU)) {
         const float4* U4 = reinterpret_cast<const float4*>(sm + L.lum);
         const float4* L4 = U4 + kLuMax * kLuMax / 4;
@@ -682,7 +705,13 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
       if (!INV) {
         float ss = 0.f;
         for (int d = 0; d < D; ++d) ss = fmaf(zs[d * kRows + row], zs[d * kRows + row], ss);
-        logp[row0 + row] = -0.5f * ss + (lds[row] + ldacc) + ld_const;
+        const float lp = -0.5f * ss + (lds[row] + ldacc) + ld_const;
+        if (logp != nullptr) logp[row0 + row] = lp;
+        if (SAVE) {
+          tc_save_row16(save + (size_t)tile * SV.tile_stride + SV.zt, row, zs, D);
+          float* lpt = save + (size_t)tile * SV.tile_stride + SV.lp;
+          lpt[row] = lp;
+        }
         if (noise != nullptr)
           for (int d = 0; d < D; ++d) noise[(row0 + row) * D + d] = zs[d * kRows + row];
       } else {
@@ -759,7 +788,24 @@ extern "C" int sbi_b200_nsf_logprob_tc(const sbi_nsf_model* m, const sbi_nsf_tc*
   }
   const int64_t ntiles = (rows->R + tc::kRows - 1) / tc::kRows;
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)tc_num_sms() * 2);
-  k<<<grid, tc::kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *tc, *rows, d_logp, d_noise);
+  k<<<grid, tc::kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *tc, *rows, d_logp, d_noise, nullptr);
+  return (int)cudaGetLastError();
+}
+
+int sbi::tc::launch_forward_save(const sbi_nsf_model* m, const sbi_nsf_tc* tc, const sbi_rows* rows, float* d_logp,
+                                 float* d_save, cudaStream_t s) {
+  const int nslot = tc_plan_slots(m, tc);
+  const tc::TcSmem L = tc::tc_smem_layout(*m, tc->stage_cap, nslot);
+  auto k = tc::nsf_logprob_tc_kernel<50, 10, false, true>;
+  static int smem_set_[sbi::kMaxDev] = {0};
+  int& smem_set = smem_set_[sbi::cur_dev()];
+  if (smem_set < L.total_bytes) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes) != cudaSuccess)
+      return SBI_ESMEM;
+    smem_set = L.total_bytes;
+  }
+  const int grid = (int)((rows->R + tc::kRows - 1) / tc::kRows);      // one tile per CTA: `d_save` slab = blockIdx
+  k<<<grid, tc::kThreads, L.total_bytes, s>>>(*m, *tc, *rows, d_logp, nullptr, d_save);
   return (int)cudaGetLastError();
 }
 
@@ -784,6 +830,6 @@ extern "C" int sbi_b200_nsf_inverse_tc(const sbi_nsf_model* m, const sbi_nsf_tc*
   }
   const int64_t ntiles = (rows->R + tc::kRows - 1) / tc::kRows;
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)tc_num_sms() * 2);
-  k<<<grid, tc::kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *tc, *rows, d_logabsdet, d_out);
+  k<<<grid, tc::kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *tc, *rows, d_logabsdet, d_out, nullptr);
   return (int)cudaGetLastError();
 }

@@ -270,4 +270,93 @@ SBI_HD float rqs_backward(const float* p, int st, const RqsConst& c, float x, fl
   return gx;
 }
 
+// Same function with the parameters and their gradients in per-thread register arrays (stride 1):
+// every loop has a compile-time trip count and every index is a constant after unrolling, so neither
+// array is ever addressed dynamically (used by the tensor-core training kernel, nsf_vjp_tc.cu).
+template <int K>
+SBI_HD float rqs_backward_reg(const float (&p)[32], const RqsConst& c, float x, float gy, float gl,
+                              float (&g)[32]) {
+  static_assert(3 * K - 1 <= 32 && K <= kRqsMaxBins, "bins");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) g[i] = 0.f;
+  const RqsBin q = rqs_locate<true>(p, 1, c, x, false);
+  if (!q.inside) return gy;
+  const float wb = q.wb, hb = q.hb, d0 = q.d0, d1 = q.d1;
+  const float delta = hb / wb;
+  const float th = (x - q.xk) / wb;
+  const float omt = 1.f - th;
+  const float tomt = th * omt;
+  const float s2 = d0 + d1 - 2.f * delta;
+  const float num = hb * (delta * th * th + d0 * tomt);
+  const float den = delta + s2 * tomt;
+  const float e = d1 * th * th + 2.f * delta * tomt + d0 * omt * omt;
+  const float iden = 1.f / den, ie = 1.f / e;
+  const float omt2 = 1.f - 2.f * th;
+  const float dnum_dth = hb * (2.f * delta * th + d0 * omt2);
+  const float dden_dth = s2 * omt2;
+  const float dy_dth = (dnum_dth * den - num * dden_dth) * iden * iden;
+  const float de_dth = 2.f * d1 * th + 2.f * delta * omt2 - 2.f * d0 * omt;
+  const float dld_dth = de_dth * ie - 2.f * dden_dth * iden;
+  const float dy_ddel = (hb * th * th * den - num * (1.f - 2.f * tomt)) * iden * iden;
+  const float dld_ddel = 2.f / delta + 2.f * tomt * ie - 2.f * (1.f - 2.f * tomt) * iden;
+  const float dy_dd0 = (hb * tomt * den - num * tomt) * iden * iden;
+  const float dy_dd1 = (-num * tomt) * iden * iden;
+  const float dld_dd0 = omt * omt * ie - 2.f * tomt * iden;
+  const float dld_dd1 = th * th * ie - 2.f * tomt * iden;
+  const float dy_dhb = (delta * th * th + d0 * tomt) * iden;
+  const float Gth = gy * dy_dth + gl * dld_dth;
+  const float Gdel = gy * dy_ddel + gl * dld_ddel;
+  const float Gd0 = gy * dy_dd0 + gl * dld_dd0;
+  const float Gd1 = gy * dy_dd1 + gl * dld_dd1;
+  const float iw = 1.f / wb;
+  const float gx = Gth * iw;
+  const float gxk = -Gth * iw;
+  const float gwb = -(Gth * th + Gdel * delta) * iw;
+  const float ghb = gy * dy_dhb + Gdel * iw;
+  const float gyk = gy;
+  const int b = q.b;
+  const float gA_w = (b >= 1) ? (gxk - gwb) : 0.f;
+  const float gB_w = (b <= K - 2) ? gwb : 0.f;
+  const float gA_h = (b >= 1) ? (gyk - ghb) : 0.f;
+  const float gB_h = (b <= K - 2) ? ghb : 0.f;
+  const float twoB = 2.f * c.B;
+  {
+    const float scale = (1.f - c.min_w * (float)K) * twoB;
+    const float is = 1.f / q.aw.s;
+    float dot = 0.f;
+#pragma unroll
+    for (int m = 0; m < kRqsMaxBins; ++m)
+      if (m < K) dot += (q.aw.e[m] * is) * (scale * ((m < b ? gA_w : 0.f) + (m <= b ? gB_w : 0.f)));
+#pragma unroll
+    for (int m = 0; m < kRqsMaxBins; ++m)
+      if (m < K) {
+        const float gsm = scale * ((m < b ? gA_w : 0.f) + (m <= b ? gB_w : 0.f));
+        g[m] = (q.aw.e[m] * is) * (gsm - dot) * c.isq;
+      }
+  }
+  {
+    const float scale = (1.f - c.min_h * (float)K) * twoB;
+    const float is = 1.f / q.ah.s;
+    float dot = 0.f;
+#pragma unroll
+    for (int m = 0; m < kRqsMaxBins; ++m)
+      if (m < K) dot += (q.ah.e[m] * is) * (scale * ((m < b ? gA_h : 0.f) + (m <= b ? gB_h : 0.f)));
+#pragma unroll
+    for (int m = 0; m < kRqsMaxBins; ++m)
+      if (m < K && K + m < 32) {
+        const float gsm = scale * ((m < b ? gA_h : 0.f) + (m <= b ? gB_h : 0.f));
+        g[K + m] = (q.ah.e[m] * is) * (gsm - dot) * c.isq;
+      }
+  }
+#pragma unroll
+  for (int m = 0; m < kRqsMaxBins; ++m)
+    if (m < K - 1 && 2 * K + m < 32) {
+      float v = 0.f;
+      if (m == b - 1) v += Gd0 * rqs_sigmoid(p[2 * K + m]);
+      if (m == b) v += Gd1 * rqs_sigmoid(p[2 * K + m]);
+      g[2 * K + m] = v;
+    }
+  return gx;
+}
+
 }  // namespace sbi

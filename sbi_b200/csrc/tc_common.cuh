@@ -154,7 +154,8 @@ static __global__ void tc_pack_kernel(const float* __restrict__ params, const in
 // k % kSlots.  A stage is fetched (TMA bulk copy, completion on full[slot]) as soon as the stage
 // that used its slot kSlots stages earlier is known to be complete, which every warp learns each
 // time it passes an accumulator barrier (a tcgen05.commit covers every MMA issued before it).
-struct Issuer {
+template <int NSLOT>
+struct IssuerT {
   uint32_t tbase;       // TMEM base (lane 0, column 0)
   bool leader;          // the elected lane of this warp
   int warp;             // this warp; stage k is issued by warp k % 8, fetched by warp (k+4) % 8
@@ -174,10 +175,10 @@ struct Issuer {
   bool reverse;         // layers are walked T-1 .. 0 (sampling direction)
 
   __device__ __forceinline__ void pump() {
-    while (fetched < done + kSlots && f_tile < ntiles) {
+    while (fetched < done + NSLOT && f_tile < ntiles) {
       const int32_t* t = tab + (reverse ? T - 1 - f_l : f_l) * SBI_NSF_TC_STRIDE;
       const int off = __ldg(t + 4 + 4 * f_s), nfl = __ldg(t + 5 + 4 * f_s);
-      const uint32_t slot = fetched % kSlots;
+      const uint32_t slot = fetched % NSLOT;
       if (leader && (int)((fetched + 4u) & 7u) == warp) {
         mbar_arrive_expect_tx(&full[slot], (uint32_t)nfl * 4u);
         bulk_g2s(ring + (size_t)slot * cap, tcw + off, (uint32_t)nfl * 4u, &full[slot]);
@@ -192,8 +193,8 @@ struct Issuer {
   __device__ __forceinline__ void begin(int stage_floats) {
     mine = (int)(it & 7u) == warp;
     if (!mine) return;
-    const uint32_t s = it % kSlots;
-    mbar_wait(&full[s], (it / kSlots) & 1u);
+    const uint32_t s = it % NSLOT;
+    mbar_wait(&full[s], (it / NSLOT) & 1u);
     // (the shuffles only tell the compiler that these values are warp-uniform)
     sbase = __shfl_sync(0xffffffffu, smem_u32(ring + (size_t)s * cap), 0);
     lo_off = __shfl_sync(0xffffffffu, (uint32_t)stage_floats * 2u, 0);   // (floats / 2) * 4 bytes
@@ -237,6 +238,27 @@ struct Issuer {
     pump();
   }
 };
+using Issuer = IssuerT<kSlots>;
+
+// instruction descriptor with an explicit M (64 or 128)
+__device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T : one K = 8 step of kind::tf32, both operands from shared memory
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 }  // namespace tc
 }  // namespace sbi

@@ -414,6 +414,83 @@ class FlowEstimator(nn.Module):
         L.check(lib.sbi_b200_nsf_tc_pack(C.byref(m), C.byref(tc), L.stream_ptr()), "nsf_tc_pack")
         return tc
 
+    # ---- fused forward+backward of a batch (parameter / input / condition gradients) --------------
+    #: rows from which the training VJP runs on the tensor cores (csrc/nsf_vjp_tc.cu) when only parameter
+    #: gradients are wanted; SBI_B200_VJP_TC=0 disables, =1 forces
+    VJP_TC_MIN_ROWS = int(os.environ.get("SBI_B200_VJP_TC_MIN_ROWS", 1024))
+
+    def _tc_train_state(self, m, pack: bool = True):
+        """(tc_fwd, tc_bwd, tc_both) operand descriptors for the tensor-core training step, freshly
+        packed from the current parameters by ONE pack launch over both plans (`tc_both`), or None."""
+        if self.fam.name != "nsf" or os.environ.get("SBI_B200_VJP_TC", "") == "0":
+            return None
+        flat = self.net.flat
+        st = self._cache.get("tc_train")
+        if st is None or st["dev"] != flat.device:
+            pf, pb = self.layout.tc_plan(), (self.layout.tc_bwd_plan() if hasattr(self.layout, "tc_bwd_plan") else None)
+            st = {"dev": flat.device, "ok": pf is not None and pb is not None}
+            if st["ok"]:
+                import numpy as np
+                dev = flat.device
+                st.update(nf=pf["n_words"], nb=pb["n_words"], cap_f=pf["stage_cap"], cap_b=pb["stage_cap"],
+                          src=torch.as_tensor(np.concatenate([pf["src"], pb["src"]]), device=dev),
+                          tab_f=torch.as_tensor(pf["tab"], device=dev), tab_b=torch.as_tensor(pb["tab"], device=dev),
+                          tcw=torch.empty(pf["n_words"] + pb["n_words"], dtype=torch.float32, device=dev))
+            self._cache["tc_train"] = st
+        if not st["ok"]:
+            return None
+        lib = L.load()
+        both = L.NsfTc(st["nf"] + st["nb"], st["cap_f"], st["src"].data_ptr(), st["tab_f"].data_ptr(),
+                       st["tcw"].data_ptr())
+        tcf = L.NsfTc(st["nf"], st["cap_f"], st["src"].data_ptr(), st["tab_f"].data_ptr(), st["tcw"].data_ptr())
+        tcb = L.NsfTc(st["nb"], st["cap_b"], st["src"].data_ptr() + 4 * st["nf"], st["tab_b"].data_ptr(),
+                      st["tcw"].data_ptr() + 4 * st["nf"])
+        if not lib.sbi_b200_nsf_vjp_tc_supported(C.byref(m), C.byref(tcf), C.byref(tcb)):
+            st["ok"] = False
+            return None
+        if pack:
+            L.check(lib.sbi_b200_nsf_tc_pack(C.byref(m), C.byref(both), L.stream_ptr()), "nsf_tc_pack")
+        return tcf, tcb, both
+
+    def vjp_parts(self, R: int, param_grads_only: bool = True) -> int:
+        """Number of partial-gradient slabs `vjp` writes for R rows."""
+        if self._vjp_uses_tc(R, param_grads_only):
+            return L.load().sbi_b200_nsf_vjp_tc_parts(R)
+        return self.fam.fn("vjp_parts")(R)
+
+    def _vjp_uses_tc(self, R: int, param_grads_only: bool) -> bool:
+        env = os.environ.get("SBI_B200_VJP_TC", "")
+        if self.fam.name != "nsf" or env == "0" or not param_grads_only:
+            return False
+        if R < self.VJP_TC_MIN_ROWS and env != "1":
+            return False
+        st = self._cache.get("tc_train")
+        if st is not None and st["dev"] == self.net.flat.device:
+            return bool(st["ok"])
+        return self._tc_train_state(self._model(nbuf=3)) is not None
+
+    def vjp(self, m, rows, R: int, gout, g_const: float, logp, gpart, ginput=None, gcond=None, loss_acc=None):
+        """One launch (pair) of the fused forward+backward of `R` rows: partial parameter gradients of
+        sum_r g_r log q_r into `gpart` ((vjp_parts(R, ...), n_params)), optionally the gradients
+        w.r.t. the inputs / conditions, the log-probs and the loss statistics.  Tensor-core kernels when
+        only parameter gradients are wanted (the trainer's case), else the SIMT kernel."""
+        lib = L.load()
+        if ginput is None and gcond is None and self._vjp_uses_tc(R, True):
+            tcs = self._tc_train_state(m)
+            if tcs is not None:
+                nbytes = int(lib.sbi_b200_nsf_vjp_tc_save_bytes(C.byref(m), R))
+                save = self._cache.get("vjp_save")
+                if save is None or save.numel() * 4 < nbytes or save.device != self.net.flat.device:
+                    save = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.net.flat.device)
+                    self._cache["vjp_save"] = save
+                L.check(lib.sbi_b200_nsf_vjp_tc(C.byref(m), C.byref(tcs[0]), C.byref(tcs[1]), C.byref(rows), L.ptr(gout),
+                                                g_const, L.ptr(logp), L.ptr(gpart), L.ptr(loss_acc), L.ptr(save),
+                                                save.numel() * 4, L.stream_ptr()), "nsf_vjp_tc")
+                return
+        L.check(self.fam.fn("vjp")(C.byref(m), C.byref(rows), L.ptr(gout), g_const, L.ptr(logp), L.ptr(gpart),
+                                   L.ptr(ginput), L.ptr(gcond), L.ptr(loss_acc), L.stream_ptr()),
+                f"{self.fam.name}_vjp")
+
     # ---- raw kernel entry (no autograd) --------------------------------------------------------------
     def _logprob_raw(self, inp: Tensor, ctx: Tensor, shared: bool, want_noise=False,
                      index: Optional[Tensor] = None, n_rows: Optional[int] = None,
@@ -454,15 +531,14 @@ class _NsfLogProb(torch.autograd.Function):
         lib = L.load()
         need_flat, need_inp, need_cond = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         R = inp.shape[0]
-        n_part = est.fam.fn("vjp_parts")(R)
+        n_part = est.vjp_parts(R, not (need_inp or need_cond))
         gpart = est._gpart(n_part)
         ginp = torch.empty_like(inp) if need_inp else None
         gcond = torch.empty(R, cond.shape[1], dtype=torch.float32, device=inp.device) if need_cond else None
         m = est._model(nbuf=3)
         rows = L.Rows(inp.data_ptr(), cond.data_ptr(), None, R, 1 if shared else 0)
         g = g.contiguous().float()
-        L.check(est.fam.fn("vjp")(C.byref(m), C.byref(rows), L.ptr(g), 0.0, None, L.ptr(gpart),
-                                  L.ptr(ginp), L.ptr(gcond), None, L.stream_ptr()), f"{est.fam.name}_vjp")
+        est.vjp(m, rows, R, g, 0.0, None, gpart, ginp, gcond, None)
         gflat = None
         if need_flat:
             gflat = torch.empty(est.layout.n_params, dtype=torch.float32, device=inp.device)

@@ -183,8 +183,8 @@ class _FlowTrainer:
               force_first_round_loss: bool = False, discard_prior_samples: bool = False,
               retrain_from_scratch: bool = False, show_train_summary: bool = False,
               dataloader_kwargs: Optional[dict] = None) -> NSFEstimator:
-        if calibration_kernel is not None:
-            raise NotImplementedError("calibration_kernel is not supported on the fused path")
+        if calibration_kernel is not None and self._swap:
+            raise ValueError("calibration_kernel is an argument of the posterior-estimator trainers (NPE)")
         if self._theta is None:
             raise RuntimeError("call append_simulations() first")
         lib = L.load()
@@ -247,7 +247,7 @@ class _FlowTrainer:
         vperm_buf = torch.empty(max(vsteps * Bv, 1), dtype=torch.int64, device=dev)
         grad = torch.zeros(P, dtype=torch.float32, device=dev)
         sumsq = torch.zeros(lib.sbi_b200_sumsq_blocks(P), dtype=torch.float32, device=dev)
-        n_part = net.fam.fn("vjp_parts")(Bl)
+        n_part = net.vjp_parts(Bl)
         gpart = net._gpart(n_part)
         loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
         val_lp = torch.empty(max(vsteps * Bv, 1), dtype=torch.float32, device=dev)
@@ -263,6 +263,16 @@ class _FlowTrainer:
             if peer is not None:
                 grad_local = torch.zeros(P, dtype=torch.float32, device=dev)
 
+        # calibration kernel (npe_base.py:373-378, :563-575): loss_r = K(x_r) * (-log q_r); the weights of
+        # all simulations are evaluated once, a step's upstream gradient is -K(x_r) / B per row
+        w_all = None
+        if calibration_kernel is not None:
+            w_all = torch.as_tensor(calibration_kernel(self._x), dtype=torch.float32).reshape(-1).to(dev).contiguous()
+            if w_all.shape[0] != N:
+                raise ValueError("calibration_kernel(x) must return one weight per simulation")
+            g_rows = torch.empty(Bl, dtype=torch.float32, device=dev)
+            lp_rows = torch.empty(Bl, dtype=torch.float32, device=dev)
+
         def run_epoch():
             """All kernels of one epoch on the current stream (graph-capturable)."""
             m_tr = net._model(nbuf=3)
@@ -271,9 +281,15 @@ class _FlowTrainer:
                 o = s * B + (rank * Bl if glob else 0)
                 idx = perm_buf[o:o + Bl]
                 rows = L.Rows(inp_all.data_ptr(), cond_all.data_ptr(), idx.data_ptr(), Bl, 0)
-                L.check(net.fam.fn("vjp")(C.byref(m_tr), C.byref(rows), None, -1.0 / Btot,
-                                          None, L.ptr(gpart), None, None, L.ptr(loss_acc),
-                                          L.stream_ptr()), "flow_vjp")
+                if w_all is None:
+                    net.vjp(m_tr, rows, Bl, None, -1.0 / Btot, None, gpart, None, None, loss_acc)
+                else:
+                    w = w_all[idx]
+                    torch.mul(w, -1.0 / Btot, out=g_rows)
+                    net.vjp(m_tr, rows, Bl, g_rows, 0.0, lp_rows, gpart, None, None, None)
+                    fin = torch.isfinite(lp_rows)
+                    loss_acc[0] -= (torch.where(fin, lp_rows, torch.zeros_like(lp_rows)) * w).sum()
+                    loss_acc[1] += (~fin).sum()
                 if peer is not None:   # gradients summed over NVLink peer memory (csrc/peer.cu)
                     L.check(lib.sbi_b200_reduce_partials(L.ptr(gpart), n_part, P, L.ptr(grad_local),
                                                          L.stream_ptr()), "reduce_partials")
@@ -313,9 +329,14 @@ class _FlowTrainer:
                 else:
                     L.check(net.fam.fn("logprob")(C.byref(m_ev), C.byref(rows), L.ptr(vlp), None,
                                                   L.stream_ptr()), "flow_logprob")
-                # -sum of the finite log-probs and the count of non-finite ones, one fused launch
-                L.check(lib.sbi_b200_nll_stats(L.ptr(vlp), v_hi - v_lo, L.ptr(stats[2:]), L.stream_ptr()),
-                        "nll_stats")
+                if w_all is None:
+                    # -sum of the finite log-probs and the count of non-finite ones, one fused launch
+                    L.check(lib.sbi_b200_nll_stats(L.ptr(vlp), v_hi - v_lo, L.ptr(stats[2:]), L.stream_ptr()),
+                            "nll_stats")
+                else:
+                    fin = torch.isfinite(vlp)
+                    stats[2] = -(torch.where(fin, vlp, torch.zeros_like(vlp)) * w_all[vrows]).sum()
+                    stats[3] = (~fin).sum().float()
 
         def fill_perms():
             perm_buf.copy_(train_idx[torch.randperm(n_train, device=dev)[:steps * B]])

@@ -300,6 +300,77 @@ class NsfLayout(_LayoutOps):
         return dict(src=src, tab=tab.reshape(-1).astype(np.int32),
                     stage_cap=int((stage_cap + 31) & ~31), n_words=int(off))
 
+    def tc_bwd_plan(self):
+        """Gather map + stage table of the TRANSPOSED linears for the tcgen05 training kernel's
+        input-gradient chain (kernel sbi_b200/csrc/nsf_vjp_tc.cu): dX = dY W needs, as the B operand
+        [N = in-features][K = out-features] in the same K-major no-swizzle layout, B[n][k] = W[k][n].
+        Stages of a layer in the order the backward sweep uses them (aux = number of K-steps):
+            final layer, one pass per <= 2 spline features:  N = 64 (hidden), K = 32 * nf
+            per block b = NB-1 .. 0:  W2^T (N = 64, K = 56),  W1^T (N = 64, K = 56)
+            initial layer, identity-feature columns only:  N = 16, K = 56
+        Same return format as tc_plan (the context columns are not needed: training never asks for
+        the condition's gradient on this path)."""
+        D, C, H, NB, T = self.D, self.C, self.H, self.NB, self.T
+        if self.tc_plan() is None or self.IDp > 16:
+            return None
+        Hp, Cp, K0p, PR, NPAR = self.Hp, self.Cp, self.K0p, self.PR, self.NPAR
+        HP8 = (H + 7) & ~7
+        tab = np.zeros((T, L.SBI_NSF_TC_STRIDE), np.int32)
+        chunks, off, stage_cap = [], 0, 0
+
+        def block(N, K, fill):
+            blk = np.full((K // 4, N, 4), -1, np.int64)
+            n = np.arange(N)[:, None]
+            k = np.arange(K)[None, :]
+            vals = fill(n + 0 * k, k + 0 * n)
+            blk[(k // 4) + 0 * n, n + 0 * k, (k % 4) + 0 * n] = vals
+            return blk.reshape(-1)
+
+        for l in range(T):
+            lt = self.layer_tab[l]
+            n_id, n_tr = int(lt[L.L_NID]), int(lt[L.L_NTR])
+            stages = []
+            wf = int(lt[L.L_WF])
+            f0 = 0
+            while f0 < n_tr:
+                nf = min(2, n_tr - f0)
+
+                def fill_f(n, k, f0=f0, nf=nf):
+                    f, i = k // 32, k % 32
+                    ok = (n < H) & (f < nf) & (i < NPAR)
+                    return np.where(ok, wf + ((f0 + np.minimum(f, nf - 1)) * PR + np.minimum(i, NPAR - 1)) * Hp
+                                    + np.minimum(n, H - 1), -1)
+
+                stages.append((block(64, 32 * nf, fill_f), 64, 4 * nf))
+                f0 += nf
+            for b in range(NB - 1, -1, -1):
+                t = L.L_BLK0 + 6 * b
+                for w in (int(lt[t + 2]), int(lt[t + 0])):          # W2 then W1
+
+                    def fill_h(n, k, w=w):
+                        ok = (n < H) & (k < H)
+                        return np.where(ok, w + np.minimum(k, H - 1) * Hp + np.minimum(n, H - 1), -1)
+
+                    stages.append((block(64, HP8, fill_h), 64, HP8 // 8))
+            w0 = int(lt[L.L_W0])
+
+            def fill_0(n, k, w0=w0, n_id=n_id):
+                ok = (n < n_id) & (k < H)
+                return np.where(ok, w0 + np.minimum(k, H - 1) * K0p + Cp + np.minimum(n, max(n_id - 1, 0)), -1)
+
+            stages.append((block(16, HP8, fill_0), 16, HP8 // 8))
+            tab[l, 0], tab[l, 1] = len(stages), (n_tr + 1) // 2
+            for s, (hi, N, aux) in enumerate(stages):
+                nfl = 2 * hi.size
+                tab[l, 4 + 4 * s: 8 + 4 * s] = (off, nfl, N, aux)
+                chunks.append(hi)
+                chunks.append(np.where(hi >= 0, -2 - hi, -1))
+                off += nfl
+                stage_cap = max(stage_cap, nfl)
+        src = np.concatenate(chunks).astype(np.int32)
+        return dict(src=src, tab=tab.reshape(-1).astype(np.int32),
+                    stage_cap=int((stage_cap + 31) & ~31), n_words=int(off))
+
     def fill_struct(self, s: "L.NsfModel", nbuf: int):
         s.D, s.C, s.H, s.NB, s.KB, s.T = self.D, self.C, self.H, self.NB, self.KB, self.T
         s.Dp, s.Cp, s.IDp, s.Hp, s.PR = self.Dp, self.Cp, self.IDp, self.Hp, self.PR

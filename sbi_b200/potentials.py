@@ -169,17 +169,20 @@ class RatioBasedPotential(BasePotential):
 
 def posterior_estimator_based_potential(posterior_estimator, prior, x_o=None, enable_transform: bool = True):
     device = str(posterior_estimator.flat.device)
+    prior = prior_to_device(prior, device)      # the unconstraining transform's constants live with the chains
     return (PosteriorBasedPotential(posterior_estimator, prior, x_o, device),
             mcmc_transform(prior, device=device, enable_transform=enable_transform))
 
 
 def likelihood_estimator_based_potential(likelihood_estimator, prior, x_o=None, enable_transform: bool = True):
     device = str(likelihood_estimator.flat.device)
+    prior = prior_to_device(prior, device)      # the unconstraining transform's constants live with the chains
     return (LikelihoodBasedPotential(likelihood_estimator, prior, x_o, device),
             mcmc_transform(prior, device=device, enable_transform=enable_transform))
 
 
 def ratio_estimator_based_potential(ratio_estimator, prior, x_o=None, enable_transform: bool = True):
     device = str(ratio_estimator.flat.device)
+    prior = prior_to_device(prior, device)      # the unconstraining transform's constants live with the chains
     return (RatioBasedPotential(ratio_estimator, prior, x_o, device),
             mcmc_transform(prior, device=device, enable_transform=enable_transform))

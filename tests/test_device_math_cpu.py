@@ -30,6 +30,14 @@ void h_inv(const float* p, int K, float B, float isq, float x, float* y, float* 
 float h_bwd(const float* p, int K, float B, float isq, float x, float gy, float gl, float* g) {
   return sbi::rqs_backward(p, 1, mk(K, B, isq), x, gy, gl, g, 1);
 }
+// the register-array variant of the tensor-core training kernel (K = 10 instantiated there)
+float h_bwd_reg10(const float* p, float B, float isq, float x, float gy, float gl, float* g) {
+  float pp[32] = {0}, gg[32];
+  for (int i = 0; i < 29; ++i) pp[i] = p[i];
+  const float gx = sbi::rqs_backward_reg<10>(pp, mk(10, B, isq), x, gy, gl, gg);
+  for (int i = 0; i < 32; ++i) g[i] = gg[i];
+  return gx;
+}
 }
 '''
 
@@ -44,6 +52,7 @@ def hostlib():
                            "-o", so, src])
     lib = ctypes.CDLL(so)
     lib.h_bwd.restype = ctypes.c_float
+    lib.h_bwd_reg10.restype = ctypes.c_float
     return lib
 
 
@@ -88,3 +97,17 @@ def test_rqs_forward_inverse_backward(hostlib, K):
     assert worst["y"] < 5e-5 and worst["ld"] < 5e-4
     assert worst["gx"] < 2e-3 and worst["gp"] < 2e-3
     assert worst["inv"] < 5e-3
+
+
+def test_rqs_backward_register_variant_equals_strided(hostlib):
+    """rqs_backward_reg<10> (tensor-core training kernel) == rqs_backward bit for bit."""
+    K, B, isq = 10, 3.0, 1 / np.sqrt(50)
+    rng = np.random.default_rng(3)
+    for t in range(400):
+        p = (rng.standard_normal(3 * K - 1) * 3).astype(np.float32)
+        x = np.float32(rng.uniform(-3.4, 3.4)) if t > 3 else np.float32([-3.0, 3.0, 0.0, 5.0][t])
+        gy, gl = rng.standard_normal(2)
+        g1, g2 = np.zeros(3 * K - 1, np.float32), np.zeros(32, np.float32)
+        a = hostlib.h_bwd(p.ctypes.data_as(FP), K, cf(B), cf(isq), cf(x), cf(gy), cf(gl), g1.ctypes.data_as(FP))
+        b = hostlib.h_bwd_reg10(p.ctypes.data_as(FP), cf(B), cf(isq), cf(x), cf(gy), cf(gl), g2.ctypes.data_as(FP))
+        assert a == b and np.array_equal(g1, g2[:29]) and not g2[29:].any()

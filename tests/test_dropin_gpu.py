@@ -92,13 +92,21 @@ def test_reference_nre_b_rejection_on_b200_resnet(cuda_lib, ref):
 
 
 def test_reference_fmpe_on_b200_mlp(cuda_lib, ref):
+    """The reference's FMPE trainer (base_vf_inference.py:206-350) on the sm_100a flow-matching
+    estimator.  The reference's VectorFieldPosterior needs zuko's ODE solver at construction (absent
+    offline), so the trained estimator is sampled through sbi_b200's posterior (SDE and ODE)."""
     from sbi.inference import FMPE
+    from sbi.neural_nets.estimators.base import ConditionalVectorFieldEstimator
     from sbi_b200.flowmatching import posterior_flow_nn
+    from sbi_b200.posteriors import VectorFieldPosterior
     prior, theta, x, x_o = _task(D=2, n=6000)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         inf = FMPE(prior, vf_estimator=posterior_flow_nn("mlp"), device="cuda", show_progress_bars=False)
-        inf.append_simulations(theta, x).train(training_batch_size=500, max_num_epochs=60)
-        post = inf.build_posterior(sample_with="sde")
-        s = post.sample((1000,), x=x_o, show_progress_bars=False)
-    _check(s, x_o, tol_mean=0.1, tol_std=0.35)
+        est = inf.append_simulations(theta, x).train(training_batch_size=500, max_num_epochs=60)
+    assert isinstance(est, ConditionalVectorFieldEstimator) and est.flat.is_cuda
+    tl = inf.summary["training_loss"]
+    assert tl[-1] < tl[0]
+    for how in ("sde", "ode"):
+        s = VectorFieldPosterior(est, prior, device="cuda", sample_with=how).sample((1000,), x=x_o)
+        _check(s, x_o, tol_mean=0.1, tol_std=0.35)

@@ -87,6 +87,54 @@ def test_nsf_tc_plan_reproduces_the_linears(D, C):
         assert seen == n_tr
 
 
+@pytest.mark.parametrize("D,C", [(10, 10), (2, 2), (5, 7), (16, 3)])
+def test_nsf_tc_bwd_plan_holds_the_transposed_linears(D, C):
+    """Backward chain operands (pack.NsfLayout.tc_bwd_plan): B[n][k] = W[k][n] for every linear, in the
+    order the backward sweep consumes them."""
+    lay = NsfLayout(D=D, C=C)
+    plan = lay.tc_bwd_plan()
+    assert plan is not None
+    H, Hp, Cp, K0p, PR, NPAR = lay.H, lay.Hp, lay.Cp, lay.K0p, lay.PR, lay.NPAR
+    params = np.random.default_rng(2).standard_normal(lay.n_params)
+    vals = _apply(plan["src"], params)
+    tab = plan["tab"].reshape(lay.T, L.SBI_NSF_TC_STRIDE)
+    for l in range(lay.T):
+        lt = lay.layer_tab[l]
+        n_id, n_tr = int(lt[L.L_NID]), int(lt[L.L_NTR])
+        npass = (n_tr + 1) // 2
+        assert int(tab[l, 0]) == npass + 2 * lay.NB + 1 and int(tab[l, 1]) == npass
+        st = [tab[l, 4 + 4 * s: 8 + 4 * s] for s in range(int(tab[l, 0]))]
+        for off, nfl, N, aux in st:
+            assert nfl <= plan["stage_cap"]
+            assert np.array_equal(vals[off + nfl // 2: off + nfl], -vals[off: off + nfl // 2])
+        wf = params[int(lt[L.L_WF]):][: n_tr * PR * Hp].reshape(n_tr * PR, Hp)
+        for p in range(npass):
+            off, nfl, N, aux = st[p]
+            nf = min(2, n_tr - 2 * p)
+            assert N == 64 and aux == 4 * nf
+            blk = _unblock(vals[off: off + nfl // 2], 64, 32 * nf)
+            for f in range(nf):
+                w = wf[(2 * p + f) * PR: (2 * p + f) * PR + NPAR, :H]            # (NPAR, H)
+                assert np.array_equal(blk[:H, 32 * f: 32 * f + NPAR], w.T)
+                assert not blk[:, 32 * f + NPAR: 32 * (f + 1)].any()
+            assert not blk[H:].any()
+        s = npass
+        for b in range(lay.NB - 1, -1, -1):
+            t = L.L_BLK0 + 6 * b
+            for wo in (int(lt[t + 2]), int(lt[t + 0])):
+                w = params[wo:][: Hp * Hp].reshape(Hp, Hp)
+                off, nfl, N, aux = st[s]
+                blk = _unblock(vals[off: off + nfl // 2], 64, 56)
+                assert N == 64 and aux == 7 and np.array_equal(blk[:H, :H], w[:H, :H].T)
+                assert not blk[H:].any() and not blk[:, H:].any()
+                s += 1
+        off, nfl, N, aux = st[s]
+        w0 = params[int(lt[L.L_W0]):][: Hp * K0p].reshape(Hp, K0p)
+        blk = _unblock(vals[off: off + nfl // 2], 16, 56)
+        assert N == 16 and np.array_equal(blk[:n_id, :H], w0[:H, Cp: Cp + n_id].T)
+        assert not blk[n_id:].any() and not blk[:, H:].any()
+
+
 def test_nsf_tc_plan_rejects_what_the_kernel_does_not_instantiate():
     assert NsfLayout(D=4, C=3, H=32).tc_plan() is None          # hidden width
     assert NsfLayout(D=4, C=20).tc_plan() is None               # H + C > 64

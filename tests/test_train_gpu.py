@@ -223,3 +223,30 @@ def test_npe_fit_linear_gaussian(cuda_lib):
     lp = post.log_prob(samples[:500].cuda(), x=x_o).cpu()
     true = MultivariateNormal(x_o[0] / 2, 0.05 * torch.eye(D)).log_prob(samples[:500])
     assert (lp - true).mean().abs() < 0.25
+
+
+def test_calibration_kernel_weights_the_loss(cuda_lib):
+    """npe_base.py:373-378, :563-575: loss_r = calibration_kernel(x_r) * (-log q_r).  A constant kernel of
+    2 doubles the logged losses of the same run; a Gaussian kernel around x_o trains and stays finite."""
+    from torch.distributions import MultivariateNormal
+    from sbi_b200.inference import NPE
+    D = 3
+    prior = MultivariateNormal(torch.zeros(D), 0.1 * torch.eye(D))
+    torch.manual_seed(0)
+    theta = prior.sample((6000,))
+    x = theta + math.sqrt(0.1) * torch.randn_like(theta)
+
+    def run(kernel):
+        torch.manual_seed(1)
+        inf = NPE(prior, density_estimator="nsf", device="cuda")
+        inf.append_simulations(theta, x).train(training_batch_size=500, max_num_epochs=3, calibration_kernel=kernel)
+        return inf.summary
+
+    base = run(None)
+    twice = run(lambda xx: 2.0 * torch.ones(xx.shape[0], device=xx.device))
+    assert abs(twice["training_loss"][0] - 2 * base["training_loss"][0]) < 1e-3 * abs(base["training_loss"][0])
+    assert abs(twice["validation_loss"][0] - 2 * base["validation_loss"][0]) < 2e-2 * abs(base["validation_loss"][0])
+    x_o = torch.tensor([0.3, -0.2, 0.1])
+    local = run(lambda xx: torch.exp(-((xx - x_o.to(xx.device)) ** 2).sum(-1) / 0.5))
+    assert all(math.isfinite(v) for v in local["training_loss"] + local["validation_loss"])
+    assert local["validation_loss"][-1] < local["validation_loss"][0]
