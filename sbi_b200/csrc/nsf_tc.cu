@@ -37,6 +37,7 @@
 
 #include "tc_common.cuh"
 #include "nsf_tc_save.cuh"
+#include "rqs_fast.cuh"
 #include "device.cuh"
 
 namespace sbi {
@@ -61,145 +62,6 @@ __host__ __device__ inline TcSmem tc_smem_layout(const sbi_nsf_model& m, int sta
   L.bar_bytes = fl * 4;
   L.total_bytes = L.bar_bytes + (nslot + 2) * 8 + 16;
   return L;
-}
-
-// ---- epilogue math of the bulk-evaluation path ------------------------------------------------
-// Same formulas as the SIMT kernels (rqs.cuh, common.cuh) evaluated with the hardware
-// approximations ex2/lg2/rcp (about 2 ulp each) instead of the correctly rounded library calls:
-// after the 3xTF32 linears the log-density already carries ~1e-5 of rounding, and these
-// functions are 40% of the instructions of this kernel.  tests/test_nsf_tc_gpu.py holds the
-// result to the SIMT kernel within 5e-4 and to the fp64 oracle within the common 2e-3.
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// 1 / (1 + 2^(-x log2 e)); x -> -inf gives rcp(inf) = 0, x -> +inf gives 1
-__device__ __forceinline__ float sigmoid_fast(float x) {
-  return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x));
-}
-__device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
-
-// Monotone rational-quadratic spline, forward direction, parameters in registers
-// (p[0,K) widths, [K,2K) heights, [2K,3K-1) derivatives; restates rqs_forward of rqs.cuh:
-// softmax -> min-size affine -> cumulative knots in [-B,B] -> bin = last knot <= x).
-template <int K>
-__device__ __forceinline__ void rqs_forward_fast(const float (&p)[32], const RqsConst& c, float x,
-                                                 float& y, float& ld) {
-  const float B = c.B;
-  if (!(x >= -B && x <= B)) { y = x; ld = 0.f; return; }
-  float ew[K], eh[K];
-  float mw = -INFINITY, mh = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    ew[i] = p[i] * c.isq;
-    eh[i] = p[K + i] * c.isq;
-    mw = fmaxf(mw, ew[i]);
-    mh = fmaxf(mh, eh[i]);
-  }
-  float sw = 0.f, sh = 0.f;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    ew[i] = __expf(ew[i] - mw);
-    eh[i] = __expf(eh[i] - mh);
-    sw += ew[i];
-    sh += eh[i];
-  }
-  const float rw = __fdividef(1.f - c.min_w * (float)K, sw);
-  const float rh = __fdividef(1.f - c.min_h * (float)K, sh);
-  float cw = 0.f, ch = 0.f, lo_w = -B, lo_h = -B;
-  float xk = -B, xk1 = B, yk = -B, yk1 = B, r0 = c.edge_raw, r1 = c.edge_raw;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    cw += fmaf(rw, ew[i], c.min_w);
-    ch += fmaf(rh, eh[i], c.min_h);
-    const float hi_w = (i == K - 1) ? B : fmaf(2.f * B, cw, -B);
-    const float hi_h = (i == K - 1) ? B : fmaf(2.f * B, ch, -B);
-    if (x >= lo_w) {
-      xk = lo_w; xk1 = hi_w; yk = lo_h; yk1 = hi_h;
-      r0 = (i == 0) ? c.edge_raw : p[2 * K + (i > 0 ? i - 1 : 0)];
-      r1 = (i == K - 1) ? c.edge_raw : p[2 * K + (i < K - 1 ? i : 0)];
-    }
-    lo_w = hi_w;
-    lo_h = hi_h;
-  }
-  const float wb = xk1 - xk, hb = yk1 - yk;
-  const float d0 = c.min_d + softplus_fast(r0), d1 = c.min_d + softplus_fast(r1);
-  const float iw = __fdividef(1.f, wb);
-  const float delta = hb * iw;
-  const float th = (x - xk) * iw;
-  const float omt = 1.f - th;
-  const float tomt = th * omt;
-  const float num = hb * (delta * th * th + d0 * tomt);
-  const float den = delta + (d0 + d1 - 2.f * delta) * tomt;
-  y = yk + __fdividef(num, den);
-  const float dnum = delta * delta * (d1 * th * th + 2.f * delta * tomt + d0 * omt * omt);
-  ld = __logf(dnum) - 2.f * __logf(den);
-}
-
-// Inverse direction (sampling): x = spline^{-1}(y), ld = log dx/dy; restates rqs_inverse of rqs.cuh
-// (bin search on the heights axis, root of the quadratic in the numerically stable form).
-template <int K>
-__device__ __forceinline__ void rqs_inverse_fast(const float (&p)[32], const RqsConst& c, float yin,
-                                                 float& x, float& ld) {
-  const float B = c.B;
-  if (!(yin >= -B && yin <= B)) { x = yin; ld = 0.f; return; }
-  float ew[K], eh[K];
-  float mw = -INFINITY, mh = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    ew[i] = p[i] * c.isq;
-    eh[i] = p[K + i] * c.isq;
-    mw = fmaxf(mw, ew[i]);
-    mh = fmaxf(mh, eh[i]);
-  }
-  float sw = 0.f, sh = 0.f;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    ew[i] = __expf(ew[i] - mw);
-    eh[i] = __expf(eh[i] - mh);
-    sw += ew[i];
-    sh += eh[i];
-  }
-  const float rw = __fdividef(1.f - c.min_w * (float)K, sw);
-  const float rh = __fdividef(1.f - c.min_h * (float)K, sh);
-  float cw = 0.f, ch = 0.f, lo_w = -B, lo_h = -B;
-  float xk = -B, xk1 = B, yk = -B, yk1 = B, r0 = c.edge_raw, r1 = c.edge_raw;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    cw += fmaf(rw, ew[i], c.min_w);
-    ch += fmaf(rh, eh[i], c.min_h);
-    const float hi_w = (i == K - 1) ? B : fmaf(2.f * B, cw, -B);
-    const float hi_h = (i == K - 1) ? B : fmaf(2.f * B, ch, -B);
-    if (yin >= lo_h) {
-      xk = lo_w; xk1 = hi_w; yk = lo_h; yk1 = hi_h;
-      r0 = (i == 0) ? c.edge_raw : p[2 * K + (i > 0 ? i - 1 : 0)];
-      r1 = (i == K - 1) ? c.edge_raw : p[2 * K + (i < K - 1 ? i : 0)];
-    }
-    lo_w = hi_w;
-    lo_h = hi_h;
-  }
-  const float wb = xk1 - xk, hb = yk1 - yk;
-  const float d0 = c.min_d + softplus_fast(r0), d1 = c.min_d + softplus_fast(r1);
-  const float delta = __fdividef(hb, wb);
-  const float dy = yin - yk;
-  const float s2 = d0 + d1 - 2.f * delta;
-  const float a = dy * s2 + hb * (delta - d0);
-  const float b = hb * d0 - dy * s2;
-  const float cc = -delta * dy;
-  const float disc = b * b - 4.f * a * cc;
-  const float root = __fdividef(2.f * cc, -b - sqrtf(disc));
-  x = fmaf(root, wb, xk);
-  const float omr = 1.f - root;
-  const float tomt = root * omr;
-  const float den = delta + s2 * tomt;
-  const float dnum = delta * delta * (d1 * root * root + 2.f * delta * tomt + d0 * omr * omr);
-  ld = -(__logf(dnum) - 2.f * __logf(den));
 }
 
 // Two threads share a row: `half` 0 owns hidden columns [0, HP8/2), `half` 1 owns [HP8/2, HP8)
@@ -435,6 +297,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
     float ldacc = 0.f;
 
     for (int li = 0; li < m.T; ++li) {
+      SBI_TL(1000 * (li + 1));
       const int l = INV ? m.T - 1 - li : li;
       const NsfLayerView v = layer_view(m, l);
       const int32_t* tab = tc.d_tab + l * SBI_NSF_TC_STRIDE;
@@ -516,6 +379,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
         iss.end(0);
       }
       ++stage;
+      SBI_TL(1000 * (li + 1) + 1);
       // dense LU factors: forward needs this layer's after the spline, sampling needs the next
       // processed layer's before its conditioner; either way the previous contents were last
       // read before the barrier above
@@ -529,6 +393,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
 #pragma unroll
         for (int q = 0; q < NC; ++q) h[q] = d[q] + blh[q];     // columns >= H: zero weights + zero bias
       }
+      SBI_TL(1000 * (li + 1) + 2);
 
       // ---- residual blocks ----
       for (int b = 0; b < m.NB; ++b) {
@@ -555,6 +420,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           iss.end(0);
         }
         stage += 2;
+        SBI_TL(1000 * (li + 1) + 10 * b + 13);
         // gate = sigmoid(Wc ctx + bc) while W1 relu(h) is on the tensor core
         float sg[NC];
         wait_acc(1);
@@ -565,6 +431,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           for (int q = 0; q < NC; ++q) sg[q] = sigmoid_fast(g[q] + bc[q]);
           if (SAVE) tc_save_cols<NC>(svl + SV.s(b), row, half, sg);
         }
+        SBI_TL(1000 * (li + 1) + 10 * b + 14);
         wait_acc(0);
         {
           float d[NC];
@@ -582,6 +449,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
           iss.end(0);
         }
         ++stage;
+        SBI_TL(1000 * (li + 1) + 10 * b + 15);
         wait_acc(0);
         {
           // h += (W2 a + b2) * gate
@@ -598,6 +466,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
             for (int q = 0; q < NC; ++q) h[q] = fmaf(d[q] + b2[q], sg[q], h[q]);
           }
         }
+        SBI_TL(1000 * (li + 1) + 10 * b + 16);
       }
 
       // ---- final layer passes + spline on the transformed features ----
@@ -616,6 +485,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
             iss.end(p);
           }
         }
+        SBI_TL(1000 * (li + 1) + 40);
         for (int p = 0; p < np; ++p) {
           const int aux = __ldg(tab + 7 + 4 * (stage + p));
           const int f0 = aux & 0xffff, nf = aux >> 16;
@@ -637,6 +507,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
             zs[j * kRows + row] = y;
             ldacc += ld;
           }
+          SBI_TL(1000 * (li + 1) + 41 + p);
           if (p + 2 < np) {
             // region p&1 has been read by everyone: pass p+2 may overwrite it
             hand_over();
@@ -653,6 +524,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
       // ---- LULinear on the row (half 1: it has one spline feature less, and it also writes the
       //      next layer's identity columns):  z <- L (U z) + b, in place ----
       group_sync();      // both halves' spline outputs are in zs
+      SBI_TL(1000 * (li + 1) + 50);
       if (SAVE && half == 1) tc_save_row16(svl + SV.v, row, zs, D);         // coupling output v_l
       if (!INV && half == 1 && __ldg(v.LT + SBI_L_HAS_LU)) {
         const float4* U4 = reinterpret_cast<const float4*>(sm + L.lum);
@@ -699,6 +571,7 @@ nsf_logprob_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_cons
     }
 
     // ---- base density ----
+    SBI_TL(9000);
     if (half == 0) lds[row] = ldacc;
     group_sync();
     if (half == 1 && row0 + row < rows.R) {
@@ -833,3 +706,17 @@ extern "C" int sbi_b200_nsf_inverse_tc(const sbi_nsf_model* m, const sbi_nsf_tc*
   k<<<grid, tc::kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *tc, *rows, d_logabsdet, d_out, nullptr);
   return (int)cudaGetLastError();
 }
+
+#ifdef SBI_TC_TIMELINE
+// tuning builds only: copy out and reset the phase timeline of CTA 0; returns the number of (id, clock) pairs
+extern "C" int sbi_b200_debug_timeline_fwd(unsigned long long* out, int cap) {
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, sbi::tc::g_tl_n, sizeof(int));
+  if (n > cap) n = cap;
+  cudaMemcpyFromSymbol(out, sbi::tc::g_tl, (size_t)n * 2 * sizeof(unsigned long long));
+  const int zero = 0;
+  cudaMemcpyToSymbol(sbi::tc::g_tl_n, &zero, sizeof(int));
+  return n;
+}
+#endif

@@ -37,6 +37,7 @@
 
 #include "tc_common.cuh"
 #include "nsf_tc_save.cuh"
+#include "rqs_fast.cuh"
 #include "device.cuh"
 
 namespace sbi {
@@ -50,10 +51,11 @@ constexpr int kStLd = 65;                       // feature rows per K-slab of a 
 constexpr int kStFloats = 32 * kStLd * 4;       // [128 rows / 4][65][4]
 
 struct BwdSmem {
-  int dz, ctx, gr, lum, stg, ring;   // float offsets
+  int dz, ctx, gr, lum, stg, obuf, ring;   // float offsets
   int bar_bytes, total_bytes;
 };
-__host__ __device__ inline BwdSmem bwd_smem_layout(int stage_cap) {
+// ldmax: longest packed weight row (floats) of the model, max(Hp, Cp + IDp, Cp)
+__host__ __device__ inline BwdSmem bwd_smem_layout(int stage_cap, int ldmax) {
   BwdSmem L;
   int fl = 0;
   L.dz = fl;  fl += 16 * kRows;
@@ -63,19 +65,54 @@ __host__ __device__ inline BwdSmem bwd_smem_layout(int stage_cap) {
   fl = (fl + 31) & ~31;
   L.stg = fl; fl += 4 * kStFloats;               // [A'0 | B'0 | A'1 | B'1]
   fl = (fl + 31) & ~31;
+  L.obuf = fl; fl += 64 * ldmax + 64;            // one weight-gradient block [<= 64 rows][ld] + its bias row
+  fl = (fl + 31) & ~31;
   L.ring = fl; fl += kBwdSlots * stage_cap;
   L.bar_bytes = fl * 4;
-  L.total_bytes = L.bar_bytes + (kBwdSlots + 2 + 2) * 8 + 16;
+  L.total_bytes = L.bar_bytes + (kBwdSlots + 2 + 2 + 1) * 8 + 16;
   return L;
+}
+__host__ __device__ inline int bwd_ldmax(const sbi_nsf_model& m) {
+  int a = m.Hp > m.Cp + m.IDp ? m.Hp : m.Cp + m.IDp;
+  return a > m.Cp ? a : m.Cp;
 }
 
 // where the accumulators of one weight-gradient MMA go in the partial-gradient slab
 struct DwGeo {
-  int oW, ldw;     // weight block: entry (m, n) at oW + m * ldw + n for n < nX
+  int oW, ldw;     // weight block: entry (m, n) at oW + m * ldw + n for n < nX   (ldw % 4 == 0, oW % 4 == 0)
   int oB;          // bias: entry m at oB + m   (column `ones` of the accumulator)
   int nX, ones;    // X columns that are weight columns; index of the ones column
-  int Mv, N;       // valid output rows; accumulator columns (multiple of 16)
+  int Mv, N;       // rows of the block incl. zero padding rows (Mv % 4 == 0); accumulator columns (multiple of 16)
 };
+
+// accumulators of one weight-gradient MMA (M = 64: rows 16q .. 16q+15 sit in lanes 0..15 of lane quarter q)
+// -> the shared-memory image of the block, laid out exactly like the block in the parameter buffer
+// ([Mv][ldw] weights, then the Mv bias entries), from where ONE thread sends it to the CTA's
+// partial-gradient slab with two TMA bulk copies (coalesced, asynchronous; scattered per-lane global
+// stores of the same data cost 1.3 us per weight gradient).  Columns >= nX of a row are padding and take
+// a zero gradient.  One copy of the code for all call sites (the kernel is instruction-fetch bound).
+__device__ __noinline__ void dw_read_fn(uint32_t taddr, const DwGeo g, float* obuf, int mrow, int col0,
+                                        bool holds_rows) {
+  if (col0 >= g.N) return;                          // warp-uniform
+  float v[32];
+  ld_cols<4>(taddr + col0, v);
+  wait_ld();
+  if (holds_rows && mrow < g.Mv) {
+    float4* orow = reinterpret_cast<float4*>(obuf + mrow * g.ldw + col0);
+    float bv = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int n = col0 + 4 * c;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n + i == g.ones) bv = v[4 * c + i];
+      if (n < g.ldw)
+        orow[c] = make_float4(n < g.nX ? v[4 * c] : 0.f, n + 1 < g.nX ? v[4 * c + 1] : 0.f,
+                              n + 2 < g.nX ? v[4 * c + 2] : 0.f, n + 3 < g.nX ? v[4 * c + 3] : 0.f);
+    }
+    if (g.ones >= col0 && g.ones < col0 + 32) obuf[g.Mv * g.ldw + mrow] = bv;
+  }
+}
 
 template <int H, int KB>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -89,11 +126,12 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
   constexpr int NG = NC / 4;
   static_assert(HP8 % 8 == 0 && NC % 4 == 0 && H > NC && H < HP8 + 1 && HP8 <= 64, "hidden width");
   extern __shared__ __align__(128) float sm[];
-  const BwdSmem L = bwd_smem_layout(tcb.stage_cap);
+  const BwdSmem L = bwd_smem_layout(tcb.stage_cap, bwd_ldmax(m));
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(sm) + L.bar_bytes);
   uint64_t* bars = full + kBwdSlots;          // two accumulator barriers of the dX chain
   uint64_t* dwbar = bars + 2;                 // one barrier per weight-gradient slot
-  uint32_t* tbase_s = reinterpret_cast<uint32_t*>(dwbar + 2);
+  uint64_t* obar = dwbar + 2;                 // the output image has been read by its bulk copies
+  uint32_t* tbase_s = reinterpret_cast<uint32_t*>(obar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = m.C, D = m.D, Cp = m.Cp, Hp = m.Hp;
   const int64_t ntiles = (rows.R + kRows - 1) / kRows;
@@ -105,6 +143,7 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
     mbar_init(&bars[1], 1);
     mbar_init(&dwbar[0], 1);
     mbar_init(&dwbar[1], 1);
+    mbar_init(obar, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -118,6 +157,7 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
   __syncthreads();
   fence_after();
   const uint32_t tbase = *tbase_s;
+  SBI_TL(100);
 
   const float* __restrict__ P = m.d_params;
   float* dzs = sm + L.dz;
@@ -172,39 +212,44 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
   // element (feature n, row) of a transposed staging buffer
   auto st_put = [&](float* buf, int n, float v) { buf[((row >> 2) * kStLd + n) * 4 + (row & 3)] = v; };
   // accumulators of the weight-gradient MMA in `slot` -> this CTA's partial gradients
-  auto dw_read = [&](int slot, const DwGeo& g) {
-    const int mrow = (warp & 3) * 16 + lane;          // M = 64: rows 16q .. 16q+15 sit in lanes 0..15 of quarter q
-#pragma unroll
-    for (int c8 = 0; c8 < 4; ++c8) {
-      const int col0 = half * 32 + 8 * c8;
-      if (col0 < g.N) {                                 // warp-uniform
-        float v[8];
-        ld8(tlane + cW + 64 * slot + col0, v);
-        wait_ld();
-        if (lane < 16 && mrow < g.Mv) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int n = col0 + i;
-            float* dst = nullptr;
-            if (n < g.nX) dst = gp + g.oW + mrow * g.ldw + n;
-            else if (n == g.ones) dst = gp + g.oB + mrow;
-            if (dst != nullptr) *dst = accum ? (*dst + v[i]) : v[i];
-          }
-        }
-      }
-    }
-  };
-  // make `slot` reusable: wait for the MMA chain that last used it and drain its accumulators
+  float* obuf = sm + L.obuf;
+  bool opend = false;          // the output image holds a block that has not been sent yet
+  uint32_t nflush = 0u;        // blocks sent so far (phase of obar)
+  DwGeo ogeo = geo0;
+  // make `slot` reusable: wait for the MMA chain that last used it and move its accumulators into the
+  // output image (whose previous block has been read out by then).  The caller passes a CTA barrier
+  // (hand_over / fence_async_smem + group_sync) and then dw_flush() before the next dw_free.
   auto dw_free = [&](int slot) {
     const bool pend = slot ? pend1 : pend0;
     if (!pend) return;
     mbar_wait(&dwbar[slot], (bpar >> (2 + slot)) & 1u);
     bpar ^= 1u << (2 + slot);
+    if (nflush > 0u) {
+      // the previous block's copies were issued a whole stage ago: they have read the image by now
+      if (tid == 0) {
+        bulk_wait_read();
+        mbar_arrive(obar);
+      }
+      mbar_wait(obar, (nflush - 1u) & 1u);
+    }
     __syncwarp();
     fence_after();
-    dw_read(slot, slot ? geo1 : geo0);
+    ogeo = slot ? geo1 : geo0;
+    dw_read_fn(tlane + cW + 64 * slot, ogeo, obuf, (warp & 3) * 16 + lane, half * 32, lane < 16);
     fence_before();        // the accumulator reads are ordered before the next MMA into this region
     if (slot) pend1 = false; else pend0 = false;
+    opend = true;
+  };
+  // after the barrier that followed dw_free: one thread sends the image to the partial-gradient slab
+  auto dw_flush = [&]() {
+    if (!opend) return;
+    if (tid == 0) {
+      bulk_s2g(gp + ogeo.oW, obuf, (uint32_t)(ogeo.Mv * ogeo.ldw) * 4u, accum);
+      bulk_s2g(gp + ogeo.oB, obuf + ogeo.Mv * ogeo.ldw, (uint32_t)ogeo.Mv * 4u, accum);
+      bulk_commit();
+    }
+    opend = false;
+    ++nflush;
   };
   // dW = A'^T-staged dY (M = 64 feature rows) x B'-staged X (N feature rows), K = 128 tile rows
   auto dw_issue = [&](int slot, const DwGeo& g) {
@@ -245,6 +290,7 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
   // dense LU factors of layer l, zero-padded to 16x16: [U | L | bias 16 | diag 16]   (as nsf_tc.cu)
   auto prep_lu = [&](int l) {
     const int* LT = m.d_layer_tab + l * SBI_NSF_LAYER_STRIDE;
+    if (!__ldg(LT + SBI_L_HAS_LU)) return;
     const float* lo = P + __ldg(LT + SBI_L_LU_LOWER);
     const float* up = P + __ldg(LT + SBI_L_LU_UPPER);
     const float* dg = P + __ldg(LT + SBI_L_LU_DIAG);
@@ -302,10 +348,9 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
           }
         }
       } else {
-        const float4* zt = reinterpret_cast<const float4*>(svt + SV.zt + row * 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t = __ldcg(zt + i);
+          const float4 t = __ldcg(tc_grp(svt + SV.zt, i, row));
           // (rows past the end of the batch were never saved: their gradient is exactly zero)
           dzs[(4 * i + 0) * kRows + row] = live ? -g * t.x : 0.f;
           dzs[(4 * i + 1) * kRows + row] = live ? -g * t.y : 0.f;
@@ -313,12 +358,10 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
           dzs[(4 * i + 3) * kRows + row] = live ? -g * t.w : 0.f;
         }
       }
-      if (!accum) {      // every entry of the partial slab is defined (padding stays zero)
-        float4* z4 = reinterpret_cast<float4*>(gp);
-        for (int e = tid; e < m.n_params / 4; e += kRowThreads) z4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      prep_lu(m.T - 1);
       group_sync();
     }
+    SBI_TL(101);
 
     for (int li = 0; li < m.T; ++li) {
       const int l = m.T - 1 - li;
@@ -326,46 +369,69 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
       const int32_t* tab = tcb.d_tab + l * SBI_NSF_TC_STRIDE;
       const float* svl = svt + (size_t)l * SV.layer_stride;
       int stage = 0;
+      SBI_TL(1000 * (li + 1));
+
+      // saved activations travel from L2 while the LU section runs: the final-layer input (X of the
+      // final layer's weight gradient) and the spline parameters of this thread's first feature
+      float xh[NC], qn[32], xn = 0.f;
+      int jn = 0;
+      tc_load_cols<NC>(svl + SV.hf, row, half, xh);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) qn[i] = 0.f;
+      if (half < v.n_tr) {
+        tc_load_prm(svl + SV.prm, row, m.TRmax, half, qn);
+        jn = __ldg(v.trf + half);
+        xn = tc_load_row16_at(svl + SV.zin, row, jn);
+      }
 
       // ================= LULinear backward (y = U v, z' = L y + b) =================
       if (__ldg(v.LT + SBI_L_HAS_LU)) {
-        dw_free(0);              // the row-major scratch below lives in the staging buffers
-        dw_free(1);
-        prep_lu(l);
-        group_sync();
-        float* V = stg;
+        float vr[kLuMax];
+        if (half == 0) tc_load_row16(svl + SV.v, row, vr);      // in flight across the waits below
+        // the row-major scratch below lives in the staging buffers of the slot that is reused next
+        const int lslot = (int)(dwn & 1u);
+        dw_free(lslot);
+        SBI_TL(1000 * (li + 1) + 90);
+        fence_async_smem();
+        group_sync();            // (the dense factors of this layer were built a layer ago: prep_lu below)
+        dw_flush();
+        SBI_TL(1000 * (li + 1) + 91);
+        float* V = stg + (2 * lslot) * kStFloats;
         float* Y = V + 16 * kRows;
         float* DY = Y + 16 * kRows;
         const float* U = sm + L.lum;
         const float* Lw = U + kLuMax * kLuMax;
         float dyr[kLuMax];
-        if (half == 1) {
-          float vr[kLuMax], dzr[kLuMax];
-          const float4* v4 = reinterpret_cast<const float4*>(svl + SV.v + row * 16);
+        if (half == 0) {
+          // y = U v on the thread's row (half 1 does dy meanwhile)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 t = __ldcg(v4 + i);
-            vr[4 * i] = t.x; vr[4 * i + 1] = t.y; vr[4 * i + 2] = t.z; vr[4 * i + 3] = t.w;
+          for (int i = 0; i < kLuMax; ++i) {
+            float y = 0.f;
+#pragma unroll
+            for (int j = 0; j < kLuMax; ++j)
+              if (j >= i) y = fmaf(U[i * kLuMax + j], vr[j], y);        // padded entries are zero
+            if (i < D) {
+              V[i * kRows + row] = vr[i];
+              Y[i * kRows + row] = y;
+            }
           }
+        } else {
+          // dy = dz + L^T dz (strictly lower part)
+          float dzr[kLuMax];
 #pragma unroll
           for (int i = 0; i < kLuMax; ++i) dzr[i] = (i < D) ? dzs[i * kRows + row] : 0.f;
 #pragma unroll
           for (int i = 0; i < kLuMax; ++i) {
-            float y = 0.f, dy = dzr[i];
+            float dy = dzr[i];
 #pragma unroll
-            for (int j = 0; j < kLuMax; ++j) {
-              if (j >= i) y = fmaf(U[i * kLuMax + j], vr[j], y);        // padded entries are zero
+            for (int j = 0; j < kLuMax; ++j)
               if (j > i) dy = fmaf(Lw[j * kLuMax + i], dzr[j], dy);
-            }
             dyr[i] = dy;
-            if (i < D) {
-              V[i * kRows + row] = vr[i];
-              Y[i * kRows + row] = y;
-              DY[i * kRows + row] = dy;
-            }
+            if (i < D) DY[i * kRows + row] = dy;
           }
         }
         group_sync();
+        SBI_TL(1000 * (li + 1) + 92);
         // parameter gradients: one (i,j) pair per thread, reduction over the tile rows (order of
         // lu_backward, nsf.cu)
         {
@@ -374,32 +440,63 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
           for (int t = tid; t < D * D + D; t += kRowThreads) {
             float a = 0.f;
             float* dst;
+            // dot products over the 128 tile rows, four independent partial sums; every lane reads a
+            // different feature row (same bank at the same offset), so lane k starts 4k rows in
+            const int rot = 4 * lane;
+            auto dot = [&](const float* p, const float* q) {
+              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+              for (int r = 0; r < kRows; r += 4) {
+                const int rr = (r + rot) & (kRows - 1);
+                const float4 x4 = *reinterpret_cast<const float4*>(p + rr);
+                const float4 y4 = *reinterpret_cast<const float4*>(q + rr);
+                a0 = fmaf(x4.x, y4.x, a0); a1 = fmaf(x4.y, y4.y, a1);
+                a2 = fmaf(x4.z, y4.z, a2); a3 = fmaf(x4.w, y4.w, a3);
+              }
+              return (a0 + a1) + (a2 + a3);
+            };
+            auto rsum = [&](const float* p) {
+              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+              for (int r = 0; r < kRows; r += 4) {
+                const float4 x4 = *reinterpret_cast<const float4*>(p + ((r + rot) & (kRows - 1)));
+                a0 += x4.x; a1 += x4.y; a2 += x4.z; a3 += x4.w;
+              }
+              return (a0 + a1) + (a2 + a3);
+            };
             if (t < D * D) {
               const int i = t / D, j = t % D;
               if (i > j) {
-                for (int r = 0; r < kRows; ++r) a = fmaf(dzs[i * kRows + r], Y[j * kRows + r], a);
+                a = dot(dzs + i * kRows, Y + j * kRows);
                 dst = gp + o_lo + i * (i - 1) / 2 + j;
               } else if (i < j) {
-                for (int r = 0; r < kRows; ++r) a = fmaf(DY[i * kRows + r], V[j * kRows + r], a);
+                a = dot(DY + i * kRows, V + j * kRows);
                 dst = gp + o_up + i * D - i * (i + 1) / 2 + (j - i - 1);
               } else {
-                float gs = 0.f;
-                for (int r = 0; r < kRows; ++r) {
-                  a = fmaf(DY[i * kRows + r], V[i * kRows + r], a);
-                  gs += GRs[r];
-                }
+                a = dot(DY + i * kRows, V + i * kRows);
+                const float gs = rsum(GRs);
                 a = (a + gs / U[i * kLuMax + i]) * sigmoid_f(__ldg(P + o_dg + i));
                 dst = gp + o_dg + i;
               }
             } else {
               const int i = t - D * D;
-              for (int r = 0; r < kRows; ++r) a += dzs[i * kRows + r];
+              a = rsum(dzs + i * kRows);
               dst = gp + o_bi + i;
             }
             *dst = accum ? (*dst + a) : a;
           }
+          // the arrays are padded to a multiple of 4 entries: padding takes a zero gradient (every
+          // entry of the slab is written by this kernel; nothing is zero-filled beforehand)
+          if (!accum && tid >= kRowThreads - 4) {
+            const int k = tid - (kRowThreads - 4);
+            const int ntri = D * (D - 1) / 2;
+            const int o = k == 0 ? o_lo : k == 1 ? o_up : k == 2 ? o_dg : o_bi;
+            const int n = k < 2 ? ntri : D;
+            for (int e = n; e < ((n + 3) & ~3); ++e) gp[o + e] = 0.f;
+          }
         }
         group_sync();
+        SBI_TL(1000 * (li + 1) + 93);
         if (half == 1) {
           // dv = U^T dy
 #pragma unroll
@@ -415,29 +512,37 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
         }
         group_sync();
       }
+      if (l > 0) prep_lu(l - 1);     // next layer's dense factors: first read a whole layer of barriers later
+      SBI_TL(1000 * (li + 1) + 1);
 
       // ================= final layer + spline backward, passes of <= 2 features =================
       const int np = __ldg(tab + 1);
       const int oWF = __ldg(v.LT + SBI_L_WF), oBF = __ldg(v.LT + SBI_L_BF);
       {
-        float xh[NC];
-        tc_load_cols<NC>(svl + SV.hf, row, half, xh);
         for (int p = 0; p < np; ++p) {
           const int f = 2 * p + half;
           const int nf = min(2, v.n_tr - 2 * p);
           const bool has = f < v.n_tr;                     // warp-uniform
           const int aset = (p & 1) * cA2;
+          // this pass's parameters were requested a pass (or the LU section) ago; request the next
+          float q[32];
+          const float x = xn;
+          const int j = jn;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) q[i] = qn[i];
+          if (f + 2 < v.n_tr) {
+            tc_load_prm(svl + SV.prm, row, m.TRmax, f + 2, qn);
+            jn = __ldg(v.trf + f + 2);
+            xn = tc_load_row16_at(svl + SV.zin, row, jn);
+          }
           if (p >= 2) wait_acc(p & 1);                     // the MMA that read this A set is done
           const int slot = (int)(dwn & 1u);
           dw_free(slot);
           float* As = stg + (2 * slot) * kStFloats;
           float* Bs = As + kStFloats;
           if (has) {
-            float q[32], dq[32];
-            tc_load_prm(svl + SV.prm, row, m.TRmax, f, q);
-            const int j = __ldg(v.trf + f);
-            const float x = __ldcg(svl + SV.zin + row * 16 + j);
-            const float gx = rqs_backward_reg<KB>(q, rc, x, dzs[j * kRows + row], GRs[row], dq);
+            float dq[32];
+            const float gx = rqs_backward_fast<KB>(q, rc, x, dzs[j * kRows + row], GRs[row], dq);
             dzs[j * kRows + row] = gx;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -449,8 +554,10 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 32; ++i) st_put(As, 32 * half + i, dq[i]);
           }
+          if (p < 2) {      // the X operand (final-layer input) of pass p - 2 is still in this slot
 #pragma unroll
-          for (int q = 0; q < NC; ++q) st_put(Bs, cbase + q, q == q_one ? 1.f : xh[q]);
+            for (int q = 0; q < NC; ++q) st_put(Bs, cbase + q, q == q_one ? 1.f : xh[q]);
+          }
           hand_over();
           {
             uint32_t acc = p > 0 ? 1u : 0u;
@@ -462,21 +569,29 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
           g.oW = oWF + 2 * p * m.PR * Hp; g.ldw = Hp; g.oB = oBF + 2 * p * m.PR;
           g.nX = H; g.ones = H; g.Mv = 32 * nf; g.N = 64;
           dw_issue(slot, g);
+        dw_flush();
+          dw_flush();
+          SBI_TL(1000 * (li + 1) + 10 + p);
         }
-        for (int p = max(0, np - 2); p < np; ++p) wait_acc(p & 1);
         stage += np;
       }
+      // (loads of saved activations are requested one wait ahead of their use throughout the blocks)
+      float sv[NC], t2[NC];
+      if (m.NB > 0) {
+        tc_load_cols<NC>(svl + SV.s(m.NB - 1), row, half, sv);
+        tc_load_cols<NC>(svl + SV.t2(m.NB - 1), row, half, t2);
+      }
+      for (int p = max(0, np - 2); p < np; ++p) wait_acc(p & 1);
       float dh[NC];
       read_acc(cD, dh);
+      SBI_TL(1000 * (li + 1) + 20);
 
       // ================= residual blocks, last to first =================
       for (int b = m.NB - 1; b >= 0; --b) {
         const int* BT = v.LT + SBI_L_BLK0 + 6 * b;
-        float dT[NC];
+        float dT[NC], a1[NC];
+        tc_load_cols<NC>(svl + SV.a1(b), row, half, a1);
         {
-          float sv[NC], t2[NC];
-          tc_load_cols<NC>(svl + SV.s(b), row, half, sv);
-          tc_load_cols<NC>(svl + SV.t2(b), row, half, t2);
           // ---- dWc = dG^T ctx  (GLU gate; no input gradient wanted for the context)
           const int slot = (int)(dwn & 1u);
           dw_free(slot);
@@ -494,15 +609,17 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
           fence_async_smem();
           group_sync();
           DwGeo g;
-          g.oW = __ldg(BT + 4); g.ldw = Cp; g.oB = __ldg(BT + 5); g.nX = Cp; g.ones = Cp; g.Mv = H; g.N = Nc;
+          g.oW = __ldg(BT + 4); g.ldw = Cp; g.oB = __ldg(BT + 5); g.nX = Cp; g.ones = Cp; g.Mv = Hp; g.N = Nc;
           dw_issue(slot, g);
+        dw_flush();
+          dw_flush();
         }
-        float a1[NC];
-        tc_load_cols<NC>(svl + SV.a1(b), row, half, a1);
+        SBI_TL(1000 * (li + 1) + 30 + 10 * b);
         // ---- dW2 = dT^T a1 ;  dA1 = (dT W2) * [a1 > 0]
         {
           const int slot = (int)(dwn & 1u);
           dw_free(slot);
+          SBI_TL(1000 * (li + 1) + 70 + 10 * b);
           float* As = stg + (2 * slot) * kStFloats;
           float* Bs = As + kStFloats;
 #pragma unroll
@@ -510,27 +627,35 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
             st_put(As, cbase + q, dT[q]);
             st_put(Bs, cbase + q, q == q_one ? 1.f : a1[q]);
           }
+          SBI_TL(1000 * (li + 1) + 71 + 10 * b);
           write_a(dT, 0);
+          SBI_TL(1000 * (li + 1) + 72 + 10 * b);
           hand_over();
+          SBI_TL(1000 * (li + 1) + 73 + 10 * b);
           {
             uint32_t acc = 0u;
             iss.begin(__ldg(tab + 5 + 4 * stage));
             iss.block(cD, 0, NCH, 0, 64, acc);
             iss.end(0);
           }
+          SBI_TL(1000 * (li + 1) + 74 + 10 * b);
           ++stage;
           DwGeo g;
-          g.oW = __ldg(BT + 2); g.ldw = Hp; g.oB = __ldg(BT + 3); g.nX = H; g.ones = H; g.Mv = H; g.N = 64;
+          g.oW = __ldg(BT + 2); g.ldw = Hp; g.oB = __ldg(BT + 3); g.nX = H; g.ones = H; g.Mv = Hp; g.N = 64;
           dw_issue(slot, g);
+        dw_flush();
+          dw_flush();
         }
+        SBI_TL(1000 * (li + 1) + 31 + 10 * b);
+        float hb[NC];
+        tc_load_cols<NC>(svl + SV.h(b), row, half, hb);
         wait_acc(0);
         float dA[NC];
         read_acc(cD, dA);
 #pragma unroll
         for (int q = 0; q < NC; ++q) dA[q] = a1[q] > 0.f ? dA[q] : 0.f;
+        SBI_TL(1000 * (li + 1) + 32 + 10 * b);
         // ---- dW1 = dA1^T relu(h_b) ;  dh += (dA1 W1) * [h_b > 0]
-        float hb[NC];
-        tc_load_cols<NC>(svl + SV.h(b), row, half, hb);
         {
           const int slot = (int)(dwn & 1u);
           dw_free(slot);
@@ -551,8 +676,15 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
           }
           ++stage;
           DwGeo g;
-          g.oW = __ldg(BT + 0); g.ldw = Hp; g.oB = __ldg(BT + 1); g.nX = H; g.ones = H; g.Mv = H; g.N = 64;
+          g.oW = __ldg(BT + 0); g.ldw = Hp; g.oB = __ldg(BT + 1); g.nX = H; g.ones = H; g.Mv = Hp; g.N = 64;
           dw_issue(slot, g);
+        dw_flush();
+          dw_flush();
+        }
+        SBI_TL(1000 * (li + 1) + 33 + 10 * b);
+        if (b > 0) {
+          tc_load_cols<NC>(svl + SV.s(b - 1), row, half, sv);
+          tc_load_cols<NC>(svl + SV.t2(b - 1), row, half, t2);
         }
         wait_acc(1);
         {
@@ -561,6 +693,7 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
 #pragma unroll
           for (int q = 0; q < NC; ++q) dh[q] += hb[q] > 0.f ? d[q] : 0.f;
         }
+        SBI_TL(1000 * (li + 1) + 34 + 10 * b);
       }
 
       // ================= initial layer: dW0 = dh^T [ctx | id | 1], d(identity features) =================
@@ -578,7 +711,7 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
           if (n < Cp) val = n < C ? ctx_s[n * kRows + row] : 0.f;
           else if (n < K0p) {
             const int i = n - Cp;
-            if (i < v.n_id) val = __ldcg(svl + SV.zin + row * 16 + __ldg(v.idf + i));
+            if (i < v.n_id) val = tc_load_row16_at(svl + SV.zin, row, __ldg(v.idf + i));
           } else if (n == K0p) val = 1.f;
           st_put(Bs, n, val);
         }
@@ -593,8 +726,10 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
         ++stage;
         DwGeo g;
         g.oW = __ldg(v.LT + SBI_L_W0); g.ldw = K0p; g.oB = __ldg(v.LT + SBI_L_B0); g.nX = K0p; g.ones = K0p;
-        g.Mv = H; g.N = N0;
+        g.Mv = Hp; g.N = N0;
         dw_issue(slot, g);
+        dw_flush();
+        SBI_TL(1000 * (li + 1) + 60);
         wait_acc(0);
         if (half == 0) {
           float d[16];
@@ -609,12 +744,18 @@ nsf_vjp_tc_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant
         group_sync();
       }
     }
+    SBI_TL(9000);
     // the tile's last weight gradients
-    dw_free(0);
-    dw_free(1);
-    group_sync();
+    for (int k = 0; k < 2; ++k) {
+      dw_free((int)((dwn + k) & 1u));     // older slot first
+      fence_async_smem();
+      group_sync();
+      dw_flush();
+    }
   }
+  SBI_TL(9001);
 
+  if (tid == 0) bulk_wait_all();
   fence_before();
   group_sync();
   if (warp == 0)
@@ -634,7 +775,7 @@ static int vjp_tc_ok(const sbi_nsf_model* m, const sbi_nsf_tc* tcf, const sbi_ns
   if (!sbi_b200_nsf_tc_supported(m, tcf)) return 0;
   if (!tcb || !tcb->d_tab || !tcb->d_tcw || tcb->stage_cap <= 0 || (tcb->stage_cap & 31)) return 0;
   if (m->IDp > 16 || m->Cp + m->IDp + 1 > 64 || m->Cp + 1 > 64) return 0;
-  const tc::BwdSmem L = tc::bwd_smem_layout(tcb->stage_cap);
+  const tc::BwdSmem L = tc::bwd_smem_layout(tcb->stage_cap, tc::bwd_ldmax(*m));
   return L.total_bytes <= 227 * 1024 ? 1 : 0;
 }
 
@@ -669,7 +810,7 @@ extern "C" int sbi_b200_nsf_vjp_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc_
   if (!vjp_tc_ok(m, tc_fwd, tc_bwd)) return SBI_ESMEM;
   if (save_bytes < sbi_b200_nsf_vjp_tc_save_bytes(m, rows->R)) return SBI_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
-  const tc::BwdSmem Lb = tc::bwd_smem_layout(tc_bwd->stage_cap);
+  const tc::BwdSmem Lb = tc::bwd_smem_layout(tc_bwd->stage_cap, tc::bwd_ldmax(*m));
   auto kb = tc::nsf_vjp_tc_kernel<50, 10>;
   {
     static int set_b_[sbi::kMaxDev] = {0};
@@ -699,3 +840,17 @@ extern "C" int sbi_b200_nsf_vjp_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc_
   }
   return (int)cudaGetLastError();
 }
+
+#ifdef SBI_TC_TIMELINE
+// tuning builds only: copy out and reset the phase timeline of CTA 0; returns the number of (id, clock) pairs
+extern "C" int sbi_b200_debug_timeline_bwd(unsigned long long* out, int cap) {
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, sbi::tc::g_tl_n, sizeof(int));
+  if (n > cap) n = cap;
+  cudaMemcpyFromSymbol(out, sbi::tc::g_tl, (size_t)n * 2 * sizeof(unsigned long long));
+  const int zero = 0;
+  cudaMemcpyToSymbol(sbi::tc::g_tl_n, &zero, sizeof(int));
+  return n;
+}
+#endif

@@ -11,6 +11,23 @@
 namespace sbi {
 namespace tc {
 
+// Phase timeline of CTA 0 (tuning builds only: -DSBI_TC_TIMELINE, profiles/tc_timeline.py): thread 0
+// appends (id, clock64) pairs to a global buffer read back through sbi_b200_debug_timeline_{fwd,bwd}().
+#ifdef SBI_TC_TIMELINE
+static __device__ unsigned long long g_tl[4096];     // one copy per translation unit
+static __device__ int g_tl_n;
+#define SBI_TL(id)                                                                        \
+  do {                                                                                    \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && g_tl_n < 2047) {                           \
+      g_tl[2 * g_tl_n] = (unsigned long long)(id);                                        \
+      g_tl[2 * g_tl_n + 1] = clock64();                                                   \
+      ++g_tl_n;                                                                           \
+    }                                                                                     \
+  } while (0)
+#else
+#define SBI_TL(id) do { } while (0)
+#endif
+
 constexpr int kRows = 128;        // rows per tile
 constexpr int kRowThreads = 256;  // two threads per row (column halves)
 constexpr int kThreads = 256;     // 8 row warps, which also take turns issuing MMAs and TMA copies
@@ -259,6 +276,23 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d, uint64_t adesc, uint64_t
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// TMA bulk copy shared -> global (bulk async-group of the calling thread); bytes % 16 == 0, both
+// addresses 16-byte aligned.  `add`: element-wise fp32 reduction into global instead of a plain store.
+__device__ __forceinline__ void bulk_s2g(float* dst_gmem, const float* src_smem, uint32_t bytes, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the committed groups have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// the committed groups are complete (their global writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 }  // namespace tc
 }  // namespace sbi

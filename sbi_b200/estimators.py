@@ -417,7 +417,7 @@ class FlowEstimator(nn.Module):
     # ---- fused forward+backward of a batch (parameter / input / condition gradients) --------------
     #: rows from which the training VJP runs on the tensor cores (csrc/nsf_vjp_tc.cu) when only parameter
     #: gradients are wanted; SBI_B200_VJP_TC=0 disables, =1 forces
-    VJP_TC_MIN_ROWS = int(os.environ.get("SBI_B200_VJP_TC_MIN_ROWS", 1024))
+    VJP_TC_MIN_ROWS = int(os.environ.get("SBI_B200_VJP_TC_MIN_ROWS", 256))
 
     def _tc_train_state(self, m, pack: bool = True):
         """(tc_fwd, tc_bwd, tc_both) operand descriptors for the tensor-core training step, freshly
