@@ -197,12 +197,14 @@ int sbi_b200_nsf_vjp_tc(const sbi_nsf_model* m, const sbi_nsf_tc* tc_fwd, const 
  * feed-forward blocks, tanh) + RandomPermutation], z-scored input, standardised context).
  * Masked weights are stored already multiplied by their masks. */
 #define SBI_MAF_LAYER_STRIDE 32
+#define SBI_MAF_AFFINE 0
+#define SBI_MAF_RQS 1
 enum {
   SBI_M_W0 = 0,   /* [Hp][Dp] masked initial layer */
   SBI_M_B0 = 1,
   SBI_M_WC = 2,   /* [Hp][Cp] context layer */
   SBI_M_BC = 3,
-  SBI_M_WF = 4,   /* [OUTp][Hp] masked final layer; row 2d = unconstrained scale, 2d+1 = shift */
+  SBI_M_WF = 4,   /* [OUTp][Hp] masked final layer; rows OUTM*d .. OUTM*d+OUTM-1 parameterise feature d */
   SBI_M_BF = 5,
   SBI_M_PERM = 6, /* offset into perm_tab: perm[D] then inverse perm[D] */
   SBI_M_BLK0 = 8  /* per feed-forward block b: W at SBI_M_BLK0+2b ([Hp][Hp] masked), bias at +1 */
@@ -213,6 +215,12 @@ typedef struct {
   int32_t rpc0, rpc1, rpcf;        /* rows per weight chunk: initial(+context), hidden, final */
   int32_t wcap, nbuf, n_params;
   int32_t scale_softplus;          /* 1: softplus(s)+1e-3 (what sbi's maf computes), 0: sigmoid(s+2)+1e-3 */
+  /* element-wise transform the MADE parameterises (`head`):
+   *   SBI_MAF_AFFINE (0): OUTM = 2, row 2d = unconstrained scale, 2d+1 = shift (`maf`, flow.py:115-209)
+   *   SBI_MAF_RQS    (1): OUTM = 3*KB-1 raw spline parameters per feature, linear tails (`maf_rqs`,
+   *                       flow.py:212-330: MaskedPiecewiseRationalQuadraticAutoregressiveTransform) */
+  int32_t head, KB, OUTM;
+  float tail_bound, min_w, min_h, min_d, isq;
   float ld_zscore;
   const float* d_params;
   const int32_t* d_layer_tab;      /* T * SBI_MAF_LAYER_STRIDE */
@@ -333,6 +341,12 @@ typedef struct {
  * d_cond (R,C) or (1,C) when cond_shared, d_time (R,) or (1,) when time_shared -> d_v (R,D). */
 int sbi_b200_fm_forward(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
                         int32_t time_shared, float* d_v, void* stream);
+/* the same velocity field and its exact divergence sum_i dv_i/dtheta_i (d_div (R,); d_v optional): the
+ * right-hand side of the augmented neural ODE behind `VectorFieldPosterior.log_prob`
+ * (sbi/samplers/ode_solvers/zuko_ode.py:80-124 -> zuko FreeFormJacobianTransform(exact=True);
+ * sbi/inference/potentials/vector_field_potential.py:145-212). */
+int sbi_b200_fm_forward_div(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
+                            int32_t time_shared, float* d_v, float* d_div, void* stream);
 /* flow-matching loss of a batch and its parameter gradient (FlowMatchingEstimator.loss :270-347
  * + backward): rows = (theta_0, x) pairs, d_time (R,) in [0,1], d_eps (R,D) ~ N(0,I).
  * d_loss (R,) optional; d_gpart (n_part, n_params) partial gradients of sum_r g_r * loss_r. */
@@ -340,6 +354,29 @@ int sbi_b200_fm_vjp_parts(int64_t R);
 int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
                          const float* d_eps, const float* d_gout, float g_const, float* d_loss,
                          float* d_gpart, float* d_loss_acc, void* stream);
+
+/* ---- adaptive Dormand-Prince 5(4) with the step control on the device (csrc/ode.cu), replacing the
+ * host-side loop of the solver the reference delegates to (zuko.utils.odeint; call sites
+ * sbi/samplers/ode_solvers/zuko_ode.py:80-124, sbi/inference/posteriors/vector_field_posterior.py:436-505).
+ * The state is a flat fp32 vector of n entries; d_k holds the 7 stage derivatives (7 x n).  One step =
+ * k_0 given (first-same-as-last), for i = 1..6: sbi_b200_ode_stage(i) then the caller's right-hand side at
+ * time d_ctrl->t_stage into k_i; then sbi_b200_ode_error_commit.  Before the first step: stage 0 (copies y,
+ * sets t_stage = t) and the right-hand side into k_0.  The host only polls d_ctrl->done. */
+typedef struct {
+  float t, h, t1, dir;      /* clock, signed step, end time, +1 / -1 */
+  float atol, rtol;
+  float t_stage;            /* time of the stage just prepared (input of the right-hand side) */
+  float en;                 /* error norm of the last step */
+  int32_t nfe, nsteps, naccept;
+  int32_t done;             /* 0 running, 1 reached t1, 2 max_steps exhausted */
+  int32_t max_steps;
+  int32_t pad_[3];
+} sbi_ode_ctrl;
+int sbi_b200_ode_red_size(int64_t n);        /* floats of scratch the error reduction needs */
+int sbi_b200_ode_stage(const float* d_y, const float* d_k, float* d_yi, int64_t n, int32_t stage,
+                       sbi_ode_ctrl* d_ctrl, void* stream);
+int sbi_b200_ode_error_commit(float* d_y, float* d_k, float* d_y5, float* d_red, int64_t n,
+                              sbi_ode_ctrl* d_ctrl, void* stream);
 
 /* ---- multi-GPU: gradient sum over NVLink peer memory (csrc/peer.cu), replacing the NCCL all-reduce +
  * norm pass of the data-parallel step (reference semantics: clip_grad_norm_ + Adam on the summed

@@ -54,7 +54,11 @@ class MafModel(C.Structure):
         ("Dp", C.c_int32), ("Cp", C.c_int32), ("Hp", C.c_int32), ("OUTp", C.c_int32),
         ("rpc0", C.c_int32), ("rpc1", C.c_int32), ("rpcf", C.c_int32),
         ("wcap", C.c_int32), ("nbuf", C.c_int32), ("n_params", C.c_int32),
-        ("scale_softplus", C.c_int32), ("ld_zscore", C.c_float),
+        ("scale_softplus", C.c_int32),
+        ("head", C.c_int32), ("KB", C.c_int32), ("OUTM", C.c_int32),
+        ("tail_bound", C.c_float), ("min_w", C.c_float), ("min_h", C.c_float), ("min_d", C.c_float),
+        ("isq", C.c_float),
+        ("ld_zscore", C.c_float),
         ("d_params", C.c_void_p), ("d_layer_tab", C.c_void_p), ("d_perm_tab", C.c_void_p),
         ("d_stats", C.c_void_p),
     ]
@@ -169,6 +173,13 @@ _EXPORTS = {
     "sbi_b200_ratio_vjp_parts": (C.c_int, [C.c_int64]),
     "sbi_b200_ratio_vjp": (C.c_int, [C.POINTER(RatioModel), C.POINTER(Pairs), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sbi_b200_fm_forward_div": (C.c_int, [C.POINTER(FmModel), C.POINTER(Rows), C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "sbi_b200_ode_red_size": (C.c_int, [C.c_int64]),
+    "sbi_b200_ode_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                     C.c_void_p]),
+    "sbi_b200_ode_error_commit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                            C.c_void_p]),
     "sbi_b200_fm_forward": (C.c_int, [C.POINTER(FmModel), C.POINTER(Rows), C.c_void_p, C.c_int32, C.c_void_p,
                                       C.c_void_p]),
     "sbi_b200_fm_vjp_parts": (C.c_int, [C.c_int64]),

@@ -30,10 +30,16 @@ struct FmSmem {
   int LD;
   int TN, CTX, SC, TGT, ABP, AB, HMP, HS, ZS, TEB, X1, X2, STAT, RED, OUT;
   int dH, dTE;
+  int UH, dAB, dHt, dUt, DIV;     // trace mode: normalised LayerNorm inputs per layer, tangent buffers, divergence
   int ring, bar_bytes, total_bytes;
 };
 
-__host__ __device__ inline FmSmem fm_smem_layout(const sbi_fm_model& m, int TM, bool train) {
+// mode 0: evaluation; 1: training (everything the backward needs); 2: exact-trace evaluation (keeps what
+// the forward-mode tangents need: pre-activations of every gelu, the normalised LayerNorm inputs and 1/std)
+enum { kFmEval = 0, kFmTrain = 1, kFmTrace = 2 };
+
+__host__ __device__ inline FmSmem fm_smem_layout(const sbi_fm_model& m, int TM, int mode) {
+  const bool train = mode == kFmTrain, trace = mode == kFmTrace;
   FmSmem L;
   L.LD = TM + 4;
   int rows = 0;
@@ -41,12 +47,12 @@ __host__ __device__ inline FmSmem fm_smem_layout(const sbi_fm_model& m, int TM, 
   L.TN = take(m.Dp);
   L.CTX = take(m.Cp);
   L.SC = take(m.TEp);
-  L.TGT = take(m.Dp);
-  L.ABP = take(train ? 2 * m.Hp : 0);
+  L.TGT = take(trace ? 0 : m.Dp);
+  L.ABP = take(train || trace ? 2 * m.Hp : 0);
   L.AB = take(2 * m.Hp);
-  L.HMP = take(train ? m.Hp : 0);
+  L.HMP = take(train || trace ? m.Hp : 0);
   L.HS = take((train ? m.NL + 1 : 1) * m.Hp);
-  L.ZS = take((train ? m.NL : 1) * m.Hp);
+  L.ZS = take((train || trace ? m.NL : 1) * m.Hp);
   L.TEB = take(m.Hp);
   L.X1 = take(m.Hp);
   L.X2 = take(train ? m.Hp : 0);
@@ -55,6 +61,11 @@ __host__ __device__ inline FmSmem fm_smem_layout(const sbi_fm_model& m, int TM, 
   L.OUT = take(m.Dp);
   L.dH = take(train ? m.Hp : 0);
   L.dTE = take(train ? m.Hp : 0);
+  L.UH = take(trace ? m.NL * m.Hp : 0);
+  L.dAB = take(trace ? 2 * m.Hp : 0);
+  L.dHt = take(trace ? m.Hp : 0);
+  L.dUt = take(trace ? m.Hp : 0);
+  L.DIV = take(trace ? 1 : 0);
   int fl = rows * L.LD;
   fl = (fl + 31) & ~31;
   L.ring = fl;
@@ -112,7 +123,7 @@ __device__ __forceinline__ void fm_load(const sbi_fm_model& m, const sbi_rows& r
       tn = (tht - (1.f - t) * mu0) / sdt;
     }
     TN[d * LD + r] = tn;
-    TGT[d * LD + r] = tg;
+    if (TRAIN) TGT[d * LD + r] = tg;
   }
   float* CTX = sm + L.CTX;
   for (int e = threadIdx.x; e < TM * Cp; e += kConsumerThreads) {
@@ -141,10 +152,13 @@ __device__ __forceinline__ void fm_load(const sbi_fm_model& m, const sbi_rows& r
   consumer_sync();
 }
 
-// network forward.  TRAIN keeps pre-activations / per-layer states for the backward.
-template <Role R, int TM, int RN, bool TRAIN>
+// network forward.  MODE kFmTrain keeps pre-activations / per-layer states for the backward, kFmTrace what
+// the forward-mode tangents of the exact trace need (fm_trace_kernel).
+template <Role R, int TM, int RN, int MODE>
 __device__ __forceinline__ void fm_net_forward(const sbi_fm_model& m, WPipe& pipe, float* sm, const FmSmem& L) {
   constexpr int LD = Tile<TM>::LD;
+  constexpr bool TRAIN = MODE == kFmTrain;
+  constexpr bool KEEP = MODE != kFmEval;       // pre-activations are kept
   const float* __restrict__ P = m.d_params;
   const int* T = m.d_tab;
   const int Hp = m.Hp, H = m.H;
@@ -159,7 +173,7 @@ __device__ __forceinline__ void fm_net_forward(const sbi_fm_model& m, WPipe& pip
                              const int n = n0 + g + i * ng;
                              const float b = __ldg(bi + n);
                              const float4 z = make_float4(acc[i][0] + b, acc[i][1] + b, acc[i][2] + b, acc[i][3] + b);
-                             if (TRAIN) st4(ABP + n * LD + r0, z);
+                             if (KEEP) st4(ABP + n * LD + r0, z);
                              st4(AB + n * LD + r0, make_float4(gelu_f(z.x), gelu_f(z.y), gelu_f(z.z), gelu_f(z.w)));
                            }
                          });
@@ -171,7 +185,7 @@ __device__ __forceinline__ void fm_net_forward(const sbi_fm_model& m, WPipe& pip
                              const int n = Hp + n0 + g + i * ng;
                              const float b = __ldg(bc + n - Hp);
                              const float4 z = make_float4(acc[i][0] + b, acc[i][1] + b, acc[i][2] + b, acc[i][3] + b);
-                             if (TRAIN) st4(ABP + n * LD + r0, z);
+                             if (KEEP) st4(ABP + n * LD + r0, z);
                              st4(AB + n * LD + r0, make_float4(gelu_f(z.x), gelu_f(z.y), gelu_f(z.z), gelu_f(z.w)));
                            }
                          });
@@ -187,7 +201,7 @@ __device__ __forceinline__ void fm_net_forward(const sbi_fm_model& m, WPipe& pip
                              const int n = n0 + g + i * ng;
                              const float b = __ldg(bm + n);
                              const float4 z = make_float4(acc[i][0] + b, acc[i][1] + b, acc[i][2] + b, acc[i][3] + b);
-                             if (TRAIN) st4(HMP + n * LD + r0, z);
+                             if (KEEP) st4(HMP + n * LD + r0, z);
                              st4(Hcur + n * LD + r0, make_float4(gelu_f(z.x), gelu_f(z.y), gelu_f(z.z), gelu_f(z.w)));
                            }
                          });
@@ -210,7 +224,7 @@ __device__ __forceinline__ void fm_net_forward(const sbi_fm_model& m, WPipe& pip
     const int* LT = T + SBI_F_LAYER0 + 4 * l;
     float* Hin = Hcur;
     float* Hout = TRAIN ? Hin + Hp * LD : Hin;
-    float* Z = sm + L.ZS + (TRAIN ? l : 0) * Hp * LD;
+    float* Z = sm + L.ZS + (KEEP ? l : 0) * Hp * LD;
     const float* bl = P + __ldg(LT + 1);
     fwd_stage<R, TM, RN>(pipe, P + __ldg(LT + 0), Hp, Hp, m.rpc_h, Hin,
                          [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
@@ -221,7 +235,7 @@ __device__ __forceinline__ void fm_net_forward(const sbi_fm_model& m, WPipe& pip
                              const float4 z = make_float4(acc[i][0] + b, acc[i][1] + b, acc[i][2] + b, acc[i][3] + b);
                              const float4 te = ld4(TEB + n * LD + r0);
                              const float4 ho = ld4(Hin + n * LD + r0);
-                             if (TRAIN) st4(Z + n * LD + r0, z);
+                             if (KEEP) st4(Z + n * LD + r0, z);
                              st4(U + n * LD + r0, make_float4(gelu_f(z.x) + te.x + ho.x, gelu_f(z.y) + te.y + ho.y,
                                                               gelu_f(z.z) + te.z + ho.z, gelu_f(z.w) + te.w + ho.w));
                            }
@@ -238,9 +252,12 @@ __device__ __forceinline__ void fm_net_forward(const sbi_fm_model& m, WPipe& pip
       constexpr int PARTS = kConsumerThreads / TM;
       const float* ga = P + __ldg(LT + 2);
       const float* be = P + __ldg(LT + 3);
-      for (int k = p; k < Hp; k += PARTS)
-        Hout[k * LD + r] = k < H ? (U[k * LD + r] - mean) * rstd * __ldg(ga + k) + __ldg(be + k) : 0.f;
-      if (TRAIN && p == 0) {
+      for (int k = p; k < Hp; k += PARTS) {
+        const float uh = k < H ? (U[k * LD + r] - mean) * rstd : 0.f;
+        Hout[k * LD + r] = k < H ? uh * __ldg(ga + k) + __ldg(be + k) : 0.f;
+        if (MODE == kFmTrace) sm[L.UH + (l * Hp + k) * LD + r] = uh;
+      }
+      if (KEEP && p == 0) {
         sm[L.STAT + (2 * l) * LD + r] = mean;
         sm[L.STAT + (2 * l + 1) * LD + r] = rstd;
       }
@@ -269,20 +286,20 @@ fm_forward_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant_
                   const float* __restrict__ time, int time_shared, float* __restrict__ v) {
   constexpr int LD = Tile<TM>::LD;
   extern __shared__ __align__(128) float sm[];
-  const FmSmem L = fm_smem_layout(m, TM, false);
+  const FmSmem L = fm_smem_layout(m, TM, kFmEval);
   WPipe pipe = make_pipe(m.nbuf, m.wcap, sm, L.ring, L.bar_bytes);
   const int64_t ntiles = (rows.R + TM - 1) / TM;
   if (threadIdx.x >= kConsumerThreads) {
     if (threadIdx.x == kConsumerThreads)
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-        fm_net_forward<kProducer, TM, RN, false>(m, pipe, sm, L);
+        fm_net_forward<kProducer, TM, RN, kFmEval>(m, pipe, sm, L);
     return;
   }
   const float* __restrict__ st = m.d_stats;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * TM;
     fm_load<TM, false>(m, rows, time, time_shared, nullptr, row0, sm, L);
-    fm_net_forward<kConsumer, TM, RN, false>(m, pipe, sm, L);
+    fm_net_forward<kConsumer, TM, RN, kFmEval>(m, pipe, sm, L);
     for (int e = threadIdx.x; e < TM * m.D; e += kConsumerThreads) {
       const int r = e / m.D, d = e % m.D;
       if (row0 + r < rows.R) {
@@ -294,6 +311,142 @@ fm_forward_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant_
   }
 }
 
+// =================================================================================================
+// v(theta, t; x) AND its exact divergence  sum_i d v_i / d theta_i  (the integrand of the neural-ODE
+// log-probability: zuko FreeFormJacobianTransform(exact=True) computes the same diagonal with D reverse-mode
+// passes through autograd, /root/reference/sbi/samplers/ode_solvers/zuko_ode.py:80-124,
+// /root/reference/sbi/inference/potentials/vector_field_potential.py:145-212).  Here: one forward that keeps
+// every gelu pre-activation and the normalised LayerNorm inputs in shared memory, then D forward-mode
+// tangents e_i through the same linears (the time embedding and the condition branch do not depend on
+// theta):   d a = gelu'(.) W_i[:, i] / sd_t,i  ->  W_m  ->  NL x [ gelu'(z) (W_l dh) + dh -> LayerNorm tangent ]
+// -> row i of W_o.  Tangent i only needs output i, so the last linear is one dot product per row.
+template <Role R, int TM, int RN>
+__device__ __forceinline__ void fm_tangent_pass(const sbi_fm_model& m, WPipe& pipe, float* sm, const FmSmem& L,
+                                                int i, const float* inv_sdt /* [TM] */) {
+  constexpr int LD = Tile<TM>::LD;
+  constexpr int PARTS = kConsumerThreads / TM;
+  const float* __restrict__ P = m.d_params;
+  const int* T = m.d_tab;
+  const int Hp = m.Hp, H = m.H;
+  float* dAB = sm + L.dAB;
+  float* dH = sm + L.dHt;
+  float* dU = sm + L.dUt;
+  if (R == kConsumer) {
+    const float* wi = P + __ldg(T + SBI_F_WI);
+    const float* ABP = sm + L.ABP;
+    for (int e = threadIdx.x; e < Hp * TM; e += kConsumerThreads) {
+      const int n = e / TM, r = e % TM;
+      dAB[n * LD + r] = n < H ? dgelu_f(ABP[n * LD + r]) * __ldg(wi + n * m.Dp + i) * inv_sdt[r] : 0.f;
+    }
+    consumer_sync();
+  }
+  {
+    const float* HMP = sm + L.HMP;
+    fwd_stage<R, TM, RN>(pipe, P + __ldg(T + SBI_F_WM), Hp, 2 * Hp, m.rpc_m, dAB,
+                         [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
+#pragma unroll
+                           for (int q = 0; q < RN; ++q) {
+                             const int n = n0 + g + q * ng;
+                             const float4 z = ld4(HMP + n * LD + r0);
+                             st4(dH + n * LD + r0, make_float4(dgelu_f(z.x) * acc[q][0], dgelu_f(z.y) * acc[q][1],
+                                                               dgelu_f(z.z) * acc[q][2], dgelu_f(z.w) * acc[q][3]));
+                           }
+                         });
+  }
+  for (int l = 0; l < m.NL; ++l) {
+    const int* LT = T + SBI_F_LAYER0 + 4 * l;
+    const float* Z = sm + L.ZS + l * Hp * LD;
+    fwd_stage<R, TM, RN>(pipe, P + __ldg(LT + 0), Hp, Hp, m.rpc_h, dH,
+                         [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
+#pragma unroll
+                           for (int q = 0; q < RN; ++q) {
+                             const int n = n0 + g + q * ng;
+                             const float4 z = ld4(Z + n * LD + r0);
+                             const float4 h = ld4(dH + n * LD + r0);
+                             st4(dU + n * LD + r0, make_float4(fmaf(dgelu_f(z.x), acc[q][0], h.x), fmaf(dgelu_f(z.y), acc[q][1], h.y),
+                                                               fmaf(dgelu_f(z.z), acc[q][2], h.z), fmaf(dgelu_f(z.w), acc[q][3], h.w)));
+                           }
+                         });
+    if (R == kConsumer) {   // d LayerNorm(u) = gamma / std * (du - mean(du) - u_hat mean(u_hat du))
+      float* RED = sm + L.RED;
+      const float* UH = sm + L.UH + l * Hp * LD;
+      const float m1 = row_reduce<TM>(H, RED, [&](int k, int r) { return dU[k * LD + r]; }) / (float)H;
+      const float m2 = row_reduce<TM>(H, RED, [&](int k, int r) { return UH[k * LD + r] * dU[k * LD + r]; }) / (float)H;
+      const int r = threadIdx.x % TM, p = threadIdx.x / TM;
+      const float rstd = sm[L.STAT + (2 * l + 1) * LD + r];
+      const float* ga = P + __ldg(LT + 2);
+      for (int k = p; k < Hp; k += PARTS)
+        dH[k * LD + r] = k < H ? __ldg(ga + k) * rstd * (dU[k * LD + r] - m1 - UH[k * LD + r] * m2) : 0.f;
+      consumer_sync();
+    }
+  }
+  if (R == kConsumer) {
+    float* RED = sm + L.RED;
+    const float* wo = P + __ldg(T + SBI_F_WO) + (size_t)i * Hp;
+    const float dv = row_reduce<TM>(H, RED, [&](int k, int r) { return __ldg(wo + k) * dH[k * LD + r]; });
+    if (threadIdx.x < TM) {
+      const float sd0 = __ldg(m.d_stats + m.Dp + i);
+      sm[L.DIV + threadIdx.x] += dv * sqrtf(1.f + sd0 * sd0);
+    }
+    consumer_sync();
+  }
+}
+
+template <int TM, int RN>
+__global__ void __launch_bounds__(kThreads, 1)
+fm_trace_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sbi_rows rows,
+                const float* __restrict__ time, int time_shared, float* __restrict__ v,
+                float* __restrict__ div) {
+  constexpr int LD = Tile<TM>::LD;
+  extern __shared__ __align__(128) float sm[];
+  const FmSmem L = fm_smem_layout(m, TM, kFmTrace);
+  WPipe pipe = make_pipe(m.nbuf, m.wcap, sm, L.ring, L.bar_bytes);
+  const int64_t ntiles = (rows.R + TM - 1) / TM;
+  if (threadIdx.x >= kConsumerThreads) {
+    if (threadIdx.x == kConsumerThreads)
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        fm_net_forward<kProducer, TM, RN, kFmTrace>(m, pipe, sm, L);
+        for (int i = 0; i < m.D; ++i) fm_tangent_pass<kProducer, TM, RN>(m, pipe, sm, L, i, nullptr);
+      }
+    return;
+  }
+  const float* __restrict__ st = m.d_stats;
+  __shared__ float s_inv[TM];
+  // the condition half of the merge layer's input never carries a tangent
+  for (int e = threadIdx.x; e < m.Hp * LD; e += kConsumerThreads) sm[L.dAB + m.Hp * LD + e] = 0.f;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TM;
+    fm_load<TM, false>(m, rows, time, time_shared, nullptr, row0, sm, L);
+    fm_net_forward<kConsumer, TM, RN, kFmTrace>(m, pipe, sm, L);
+    if (v != nullptr)
+      for (int e = threadIdx.x; e < TM * m.D; e += kConsumerThreads) {
+        const int r = e / m.D, d = e % m.D;
+        if (row0 + r < rows.R) {
+          const float sd0 = __ldg(st + m.Dp + d);
+          v[(row0 + r) * m.D + d] = sm[L.OUT + d * LD + r] * sqrtf(1.f + sd0 * sd0) - __ldg(st + d);
+        }
+      }
+    if (threadIdx.x < TM) sm[L.DIV + threadIdx.x] = 0.f;
+    for (int i = 0; i < m.D; ++i) {
+      if (threadIdx.x < TM) {       // 1 / sd_t,i of the row (fm_load's standardisation)
+        const int64_t gr = row0 + threadIdx.x;
+        float inv = 0.f;
+        if (gr < rows.R) {
+          const float t = __ldg(time + (time_shared ? 0 : gr));
+          const float a = (1.f - t) * __ldg(st + m.Dp + i);
+          inv = rsqrtf(a * a + t * t + 1e-6f);
+        }
+        s_inv[threadIdx.x] = inv;
+      }
+      consumer_sync();
+      fm_tangent_pass<kConsumer, TM, RN>(m, pipe, sm, L, i, s_inv);
+    }
+    if (threadIdx.x < TM && row0 + threadIdx.x < rows.R) div[row0 + threadIdx.x] = sm[L.DIV + threadIdx.x];
+    consumer_sync();
+  }
+}
+
+
 template <int TM, int RN, int RK>
 __global__ void __launch_bounds__(kThreads, 1)
 fm_vjp_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sbi_rows rows,
@@ -302,7 +455,7 @@ fm_vjp_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sb
   constexpr int LD = Tile<TM>::LD;
   constexpr int PARTS = kConsumerThreads / TM;
   extern __shared__ __align__(128) float sm[];
-  const FmSmem L = fm_smem_layout(m, TM, true);
+  const FmSmem L = fm_smem_layout(m, TM, kFmTrain);
   WPipe pipe = make_pipe(m.nbuf, m.wcap, sm, L.ring, L.bar_bytes);
   const int64_t ntiles = (rows.R + TM - 1) / TM;
   const float* __restrict__ P = m.d_params;
@@ -313,7 +466,7 @@ fm_vjp_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sb
     if (threadIdx.x == kConsumerThreads) {
       auto noop = [](int, int, float(&)[RK][4], bool) {};
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        fm_net_forward<kProducer, TM, RN, true>(m, pipe, sm, L);
+        fm_net_forward<kProducer, TM, RN, kFmTrain>(m, pipe, sm, L);
         dx_stage<kProducer, TM, RK>(pipe, P + __ldg(T + SBI_F_WO), m.Dp, Hp, m.rpc_o, nullptr, Hp, noop);
         for (int l = m.NL - 1; l >= 0; --l)
           dx_stage<kProducer, TM, RK>(pipe, P + __ldg(T + SBI_F_LAYER0 + 4 * l), Hp, Hp, m.rpc_h, nullptr, Hp, noop);
@@ -339,7 +492,7 @@ fm_vjp_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sb
     const bool accum = iter > 0;
     const int64_t row0 = tile * TM;
     fm_load<TM, true>(m, rows, time, 0, eps, row0, sm, L);
-    fm_net_forward<kConsumer, TM, RN, true>(m, pipe, sm, L);
+    fm_net_forward<kConsumer, TM, RN, kFmTrain>(m, pipe, sm, L);
     // loss_r = mean_d (v_out - target)^2 ; dOUT = g_r * 2/D * (v_out - target)   (in place in OUT)
     {
       float lsum = 0.f, bad = 0.f;
@@ -515,12 +668,29 @@ extern "C" int sbi_b200_fm_forward(const sbi_fm_model* m, const sbi_rows* rows, 
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_time || !d_v) return SBI_EINVAL;
   if (rows->R == 0) return 0;
   constexpr int TM = 32;
-  const FmSmem L = fm_smem_layout(*m, TM, false);
+  const FmSmem L = fm_smem_layout(*m, TM, kFmEval);
   auto k = fm_forward_kernel<TM, 2>;
   if ((rc = fm_set_smem<0>(k, L.total_bytes))) return rc;
   const int64_t ntiles = (rows->R + TM - 1) / TM;
   const int grid = (int)std::min<int64_t>(ntiles, fm_num_sms());
   k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *rows, d_time, time_shared, d_v);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int sbi_b200_fm_forward_div(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
+                                       int32_t time_shared, float* d_v, float* d_div, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
+  int rc = fm_check(m);
+  if (rc) return rc;
+  if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_time || !d_div) return SBI_EINVAL;
+  if (rows->R == 0) return 0;
+  constexpr int TM = 16;
+  const FmSmem L = fm_smem_layout(*m, TM, kFmTrace);
+  auto k = fm_trace_kernel<TM, 2>;
+  if ((rc = fm_set_smem<2>(k, L.total_bytes))) return rc;
+  const int64_t ntiles = (rows->R + TM - 1) / TM;
+  const int grid = (int)std::min<int64_t>(ntiles, fm_num_sms());
+  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *rows, d_time, time_shared, d_v, d_div);
   return (int)cudaGetLastError();
 }
 
@@ -537,7 +707,7 @@ extern "C" int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows,
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 1 || !d_time || !d_eps || !d_gpart) return SBI_EINVAL;
   constexpr int TM = 16;
-  const FmSmem L = fm_smem_layout(*m, TM, true);
+  const FmSmem L = fm_smem_layout(*m, TM, kFmTrain);
   auto k = fm_vjp_kernel<TM, 2, 2>;
   if ((rc = fm_set_smem<1>(k, L.total_bytes))) return rc;
   const int grid = sbi_b200_fm_vjp_parts(rows->R);

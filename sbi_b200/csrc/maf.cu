@@ -4,6 +4,9 @@
 //   z-score -> T x [ affine autoregressive transform (MADE conditioner, feed-forward masked blocks,
 //   tanh, context added after the first masked layer) -> fixed random permutation ] -> N(0, I)
 //
+// and, with head == SBI_MAF_RQS, for `build_maf_rqs` (flow.py:212-330): the same MADE emits 3K-1 raw
+// spline parameters per feature and the element-wise map is the monotone rational-quadratic spline
+// with linear tails (rqs.cuh; MaskedPiecewiseRationalQuadraticAutoregressiveTransform),
 // restating nflows 0.14 MaskedAffineAutoregressiveTransform / MADE / RandomPermutation
 // (oracle/nflows_port/transforms/{autoregressive,made,permutations}.py).
 // Same CTA structure as the NSF kernels (stages.cuh): 8 consumer warps + 1 TMA producer warp, a
@@ -15,6 +18,7 @@
 
 #include "stages.cuh"
 #include "device.cuh"
+#include "rqs.cuh"
 
 namespace sbi {
 
@@ -80,6 +84,14 @@ __device__ __forceinline__ float maf_dscale(const sbi_maf_model& m, float s) {
   return g * (1.f - g);
 }
 
+__device__ __forceinline__ RqsConst maf_rqs_const(const sbi_maf_model& m) {
+  RqsConst c;
+  c.K = m.KB; c.B = m.tail_bound; c.isq = m.isq;
+  c.min_w = m.min_w; c.min_h = m.min_h; c.min_d = m.min_d;
+  c.edge_raw = logf(expf(1.f - m.min_d) - 1.f);
+  return c;
+}
+
 // MADE conditioner: OUT = Wf tanh(... tanh(W1 (W0 z + b0 + Wc ctx + bc) + b1) ...) + bf.
 // Writes H_0 .. H_NB into sm+L.HB and the 2D autoregressive parameters into sm+L.OUT.
 template <Role R, int TM, int RN>
@@ -139,11 +151,22 @@ __device__ __forceinline__ void maf_affine_forward(const sbi_maf_model& m, const
   constexpr int LD = Tile<TM>::LD;
   const float* OUT = sm + L.OUT;
   float* LDF = sm + L.LDF;
-  for (int t = threadIdx.x; t < m.D * TM; t += kConsumerThreads) {
-    const int d = t / TM, r = t % TM;
-    const float sc = maf_scale(m, OUT[(2 * d) * LD + r]);
-    Zout[__ldg(v.iperm + d) * LD + r] = sc * Zin[d * LD + r] + OUT[(2 * d + 1) * LD + r];
-    LDF[d * LD + r] = logf(sc);
+  if (m.head == SBI_MAF_RQS) {
+    const RqsConst rc = maf_rqs_const(m);
+    for (int t = threadIdx.x; t < m.D * TM; t += kConsumerThreads) {
+      const int d = t / TM, r = t % TM;
+      float y, ld;
+      rqs_forward(OUT + (m.OUTM * d) * LD + r, LD, rc, Zin[d * LD + r], y, ld);
+      Zout[__ldg(v.iperm + d) * LD + r] = y;
+      LDF[d * LD + r] = ld;
+    }
+  } else {
+    for (int t = threadIdx.x; t < m.D * TM; t += kConsumerThreads) {
+      const int d = t / TM, r = t % TM;
+      const float sc = maf_scale(m, OUT[(2 * d) * LD + r]);
+      Zout[__ldg(v.iperm + d) * LD + r] = sc * Zin[d * LD + r] + OUT[(2 * d + 1) * LD + r];
+      LDF[d * LD + r] = logf(sc);
+    }
   }
   consumer_sync();
   for (int r = threadIdx.x; r < TM; r += kConsumerThreads) {
@@ -245,11 +268,22 @@ maf_inverse_kernel(const __grid_constant__ sbi_maf_model m, const __grid_constan
       for (int it = 0; it < m.D; ++it) {
         made_forward<kConsumer, TM, RN>(m, v, pipe, sm, L, X);
         const bool last = (it == m.D - 1);
-        for (int t = threadIdx.x; t < m.D * TM; t += kConsumerThreads) {
-          const int d = t / TM, r = t % TM;
-          const float sc = maf_scale(m, OUT[(2 * d) * LD + r]);
-          X[d * LD + r] = (Yp[d * LD + r] - OUT[(2 * d + 1) * LD + r]) / sc;
-          if (last) Y[d * LD + r] = logf(sc);   // Y is free now: stash log scale
+        if (m.head == SBI_MAF_RQS) {
+          const RqsConst rc = maf_rqs_const(m);
+          for (int t = threadIdx.x; t < m.D * TM; t += kConsumerThreads) {
+            const int d = t / TM, r = t % TM;
+            float xv, ld;
+            rqs_inverse(OUT + (m.OUTM * d) * LD + r, LD, rc, Yp[d * LD + r], xv, ld);
+            X[d * LD + r] = xv;
+            if (last) Y[d * LD + r] = -ld;      // forward log-derivative (ld = log dx/dy)
+          }
+        } else {
+          for (int t = threadIdx.x; t < m.D * TM; t += kConsumerThreads) {
+            const int d = t / TM, r = t % TM;
+            const float sc = maf_scale(m, OUT[(2 * d) * LD + r]);
+            X[d * LD + r] = (Yp[d * LD + r] - OUT[(2 * d + 1) * LD + r]) / sc;
+            if (last) Y[d * LD + r] = logf(sc);   // Y is free now: stash log scale
+          }
         }
         consumer_sync();
       }
@@ -378,14 +412,24 @@ maf_vjp_kernel(const __grid_constant__ sbi_maf_model m, const __grid_constant__ 
       const float* ZSl = sm + L.ZS + l * Dp * LD;
       made_forward<kConsumer, TM, RN>(m, v, pipe, sm, L, ZSl);
       // affine + permutation backward
-      for (int t = threadIdx.x; t < m.D * TM; t += kConsumerThreads) {
-        const int d = t / TM, r = t % TM;
-        const float dzn = dZ[__ldg(v.iperm + d) * LD + r];
-        const float s = OUT[(2 * d) * LD + r];
-        const float sc = maf_scale(m, s);
-        dOUT[(2 * d) * LD + r] = (dzn * ZSl[d * LD + r] + GR[r] / sc) * maf_dscale(m, s);
-        dOUT[(2 * d + 1) * LD + r] = dzn;
-        dZ2[d * LD + r] = dzn * sc;
+      if (m.head == SBI_MAF_RQS) {
+        const RqsConst rc = maf_rqs_const(m);
+        for (int t = threadIdx.x; t < m.D * TM; t += kConsumerThreads) {
+          const int d = t / TM, r = t % TM;
+          const float dzn = dZ[__ldg(v.iperm + d) * LD + r];
+          dZ2[d * LD + r] = rqs_backward(OUT + (m.OUTM * d) * LD + r, LD, rc, ZSl[d * LD + r], dzn, GR[r],
+                                         dOUT + (m.OUTM * d) * LD + r, LD);
+        }
+      } else {
+        for (int t = threadIdx.x; t < m.D * TM; t += kConsumerThreads) {
+          const int d = t / TM, r = t % TM;
+          const float dzn = dZ[__ldg(v.iperm + d) * LD + r];
+          const float s = OUT[(2 * d) * LD + r];
+          const float sc = maf_scale(m, s);
+          dOUT[(2 * d) * LD + r] = (dzn * ZSl[d * LD + r] + GR[r] / sc) * maf_dscale(m, s);
+          dOUT[(2 * d + 1) * LD + r] = dzn;
+          dZ2[d * LD + r] = dzn * sc;
+        }
       }
       consumer_sync();
       float* dHa = sm + L.dHa;
@@ -393,7 +437,7 @@ maf_vjp_kernel(const __grid_constant__ sbi_maf_model m, const __grid_constant__ 
       // final layer
       {
         const float* Hf = sm + L.HB + m.NB * Hp * LD;
-        gemm_dw<TM>(dOUT, 2 * m.D, Hf, m.H, Hp, gp + __ldg(v.LT + SBI_M_WF), gp + __ldg(v.LT + SBI_M_BF), accum);
+        gemm_dw<TM>(dOUT, m.OUTM * m.D, Hf, m.H, Hp, gp + __ldg(v.LT + SBI_M_WF), gp + __ldg(v.LT + SBI_M_BF), accum);
         const bool act = m.NB > 0;   // H_NB = tanh(.) iff there is at least one block
         dx_stage<kConsumer, TM, RK>(pipe, nullptr, m.OUTp, Hp, m.rpcf, dOUT, Hp,
                                     [&](int k0, int r0, float(&acc)[RK][4], bool first) {
@@ -496,7 +540,11 @@ static int maf_num_sms() { return sbi::dev_num_sms(); }
 static int maf_check(const sbi_maf_model* m) {
   if (!m || !m->d_params || !m->d_layer_tab || !m->d_perm_tab || !m->d_stats) return SBI_EINVAL;
   if (m->D < 1 || m->C < 1 || m->H < 1 || m->T < 1 || m->NB < 0 || m->NB > 8) return SBI_EINVAL;
-  if (m->Dp != round4(m->D) || m->Cp != round4(m->C) || m->Hp != round4(m->H) || m->OUTp != round4(2 * m->D))
+  if (m->head != SBI_MAF_AFFINE && m->head != SBI_MAF_RQS) return SBI_EINVAL;
+  if (m->OUTM != (m->head == SBI_MAF_AFFINE ? 2 : 3 * m->KB - 1)) return SBI_EINVAL;
+  if (m->head == SBI_MAF_RQS && (m->KB < 2 || m->KB > kRqsMaxBins || !(m->tail_bound > 0.f))) return SBI_EINVAL;
+  if (m->Dp != round4(m->D) || m->Cp != round4(m->C) || m->Hp != round4(m->H) ||
+      m->OUTp != round4(m->OUTM * m->D))
     return SBI_EINVAL;
   if ((m->rpc0 & 3) || (m->rpc1 & 3) || (m->rpcf & 3) || m->rpc0 < 4 || m->rpc1 < 4 || m->rpcf < 4) return SBI_EINVAL;
   if (m->nbuf < 2 || m->nbuf > 8) return SBI_EINVAL;

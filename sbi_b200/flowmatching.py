@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import warnings
 from typing import Any, Callable, Optional, Tuple
 
 import torch
@@ -176,6 +177,27 @@ class FlowMatchingEstimator(nn.Module):
         L.check(lib.sbi_b200_fm_forward(C.byref(m), C.byref(rows), L.ptr(tt), 1 if t_shared else 0, L.ptr(v),
                                         L.stream_ptr()), "fm_forward")
         return v.reshape(*bshape, *self.input_shape)
+
+    def forward_and_divergence(self, input: Tensor, condition: Tensor, time: Tensor):
+        """(v, sum_i dv_i/dtheta_i): the velocity in ORIGINAL space and its exact divergence w.r.t. the
+        input, one kernel (csrc/fm.cu `fm_trace_kernel`: forward + D forward-mode tangents).  input (R, D),
+        condition (R, C) or (1, C), time scalar or (R,)."""
+        lib = L.load()
+        L.require_cuda(input, "input")
+        inp = input.reshape(-1, self.layout.D).contiguous().float()
+        R = inp.shape[0]
+        cond = condition.reshape(-1, self.layout.C).contiguous().float()
+        shared = cond.shape[0] == 1
+        time = torch.as_tensor(time, dtype=torch.float32, device=inp.device)
+        t_shared = time.numel() == 1
+        tt = (time.reshape(1) if t_shared else time.reshape(-1)).contiguous()
+        v = torch.empty_like(inp)
+        div = torch.empty(R, dtype=torch.float32, device=inp.device)
+        m = self._model(nbuf=2)
+        rows = L.Rows(inp.data_ptr(), cond.data_ptr(), None, R, 1 if shared else 0)
+        L.check(lib.sbi_b200_fm_forward_div(C.byref(m), C.byref(rows), L.ptr(tt), 1 if t_shared else 0, L.ptr(v),
+                                            L.ptr(div), L.stream_ptr()), "fm_forward_div")
+        return v, div
 
     def ode_fn(self, input: Tensor, condition: Tensor, times: Tensor) -> Tensor:
         """flowmatching_estimator.py:349-372: the flow's ODE right-hand side is the velocity itself."""
@@ -384,17 +406,147 @@ def odeint_dopri5(f: Callable[[Tensor, float], Tensor], y0: Tensor, t0: float, t
     return y, nfe
 
 
+class DeviceDopri5:
+    """Adaptive Dormand-Prince 5(4) with the step control on the device (csrc/ode.cu; restates the solver
+    the reference delegates to, zuko.utils.odeint, behind zuko_ode.py:80-124).  One step is a fixed launch
+    sequence -- 6 x [stage combination -> right-hand side] -> error norm -> accept / commit / next step
+    size -- captured once as a CUDA graph; the host replays it and polls the `done` flag every `poll`
+    steps (one sync per `poll` steps instead of one `.item()` per step).
+
+    rhs(y: Tensor (n,), t_ptr: int, out: Tensor (n,)) launches the right-hand side on the current stream,
+    reading its time from the device scalar at address `t_ptr`."""
+
+    _OFF_TSTAGE, _I_NFE, _I_NSTEPS, _I_NACC, _I_DONE, _I_MAX = 6, 8, 9, 10, 11, 12
+
+    def __init__(self, n: int, device, rhs: Callable, atol: float = 1e-6, rtol: float = 1e-5,
+                 max_steps: int = 10_000, poll: int = 4, use_graph: bool = True):
+        self.lib = L.load()
+        self.n, self.rhs, self.atol, self.rtol, self.max_steps, self.poll = n, rhs, atol, rtol, max_steps, poll
+        self.y = torch.empty(n, dtype=torch.float32, device=device)
+        self.yi = torch.empty(n, dtype=torch.float32, device=device)
+        self.y5 = torch.empty(n, dtype=torch.float32, device=device)
+        self.k = torch.empty(7, n, dtype=torch.float32, device=device)
+        self.red = torch.empty(self.lib.sbi_b200_ode_red_size(n), dtype=torch.float32, device=device)
+        self.ctrl = torch.zeros(16, dtype=torch.float32, device=device)
+        self.ctrl_i = self.ctrl.view(torch.int32)
+        self.t_ptr = self.ctrl.data_ptr() + 4 * self._OFF_TSTAGE
+        self._host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        self.use_graph = use_graph
+        self.graph = None
+
+    def _stage(self, i: int):
+        L.check(self.lib.sbi_b200_ode_stage(L.ptr(self.y), L.ptr(self.k), L.ptr(self.yi), self.n, i,
+                                            self.ctrl.data_ptr(), L.stream_ptr()), "ode_stage")
+
+    def _step(self):
+        for i in range(1, 7):
+            self._stage(i)
+            self.rhs(self.yi, self.t_ptr, self.k[i])
+        L.check(self.lib.sbi_b200_ode_error_commit(L.ptr(self.y), L.ptr(self.k), L.ptr(self.y5), L.ptr(self.red),
+                                                   self.n, self.ctrl.data_ptr(), L.stream_ptr()), "ode_error_commit")
+
+    def solve(self, y0: Tensor, t0: float, t1: float):
+        """Integrate from t0 to t1 (either direction); returns (y(t1) as a view of the solver's state,
+        right-hand-side evaluations, steps, accepted steps)."""
+        import numpy as np
+        direction = 1.0 if t1 >= t0 else -1.0
+        h0 = direction * min(abs(t1 - t0), 0.05)
+        c = np.zeros(16, np.float32)
+        c[0:6] = [t0, h0, t1, direction, self.atol, self.rtol]
+        ci = c.view(np.int32)
+        ci[self._I_NFE], ci[self._I_MAX] = 1, self.max_steps
+        if abs(t1 - t0) <= 1e-12:
+            ci[self._I_DONE] = 1
+        self.ctrl.copy_(torch.from_numpy(c))
+        self.y.copy_(y0.reshape(-1))
+        self._stage(0)                                   # yi = y, t_stage = t0
+        self.rhs(self.yi, self.t_ptr, self.k[0])         # k_0 (also sets the kernel's attributes before capture)
+        if self.use_graph and self.graph is None:
+            snap = (self.y.clone(), self.k[0].clone(), self.ctrl.clone())
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._step()                             # warm-up outside capture
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step()
+            self.y.copy_(snap[0]); self.k[0].copy_(snap[1]); self.ctrl.copy_(snap[2])
+        while True:
+            for _ in range(self.poll):
+                if self.graph is not None:
+                    self.graph.replay()
+                else:
+                    self._step()
+            self._host.copy_(self.ctrl, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            hi = self._host.view(torch.int32)
+            done = int(hi[self._I_DONE])
+            if done:
+                break
+        if done == 2:
+            warnings.warn(f"dopri5: max_steps={self.max_steps} reached at t={float(self._host[0]):.4f}", stacklevel=2)
+        return self.y, int(hi[self._I_NFE]), int(hi[self._I_NSTEPS]), int(hi[self._I_NACC])
+
+
+def _fm_rhs(est: FlowMatchingEstimator, cond: Tensor, R: int, with_div: bool):
+    """Right-hand side launcher for DeviceDopri5: state = theta (R, D) [| log|det| (R)]."""
+    lib = L.load()
+    D = est.layout.D
+    m = est._model(nbuf=2)
+    keep = (m, cond)
+
+    def rhs(y: Tensor, t_ptr: int, out: Tensor):
+        rows = L.Rows(y.data_ptr(), keep[1].data_ptr(), None, R, 1)
+        if with_div:
+            L.check(lib.sbi_b200_fm_forward_div(C.byref(keep[0]), C.byref(rows), t_ptr, 1, out.data_ptr(),
+                                                out.data_ptr() + 4 * R * D, L.stream_ptr()), "fm_forward_div")
+        else:
+            L.check(lib.sbi_b200_fm_forward(C.byref(keep[0]), C.byref(rows), t_ptr, 1, out.data_ptr(),
+                                            L.stream_ptr()), "fm_forward")
+    return rhs
+
+
 @torch.no_grad()
 def sample_ode(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, atol: float = 1e-6,
-               rtol: float = 1e-5, return_nfe: bool = False):
+               rtol: float = 1e-5, return_nfe: bool = False, device_control: bool = True):
     """Draw theta ~ q(theta | x): base N(mean_base, std_base) at t = t_max, integrate to t = t_min
-    (VectorFieldPosterior.sample_via_ode, vector_field_posterior.py:436-465)."""
+    (VectorFieldPosterior.sample_via_ode, vector_field_posterior.py:436-465).  `device_control=False` keeps
+    the host-side loop (`odeint_dopri5`) for comparison."""
     dev = est.net.flat.device
-    cond = condition.reshape(1, *est.condition_shape).to(dev).float()
-    y0 = est._mean_base.to(dev) + est._std_base.to(dev) * torch.randn(num_samples, est.layout.D, device=dev)
-    y, nfe = odeint_dopri5(lambda y, t: est.forward(y, cond, torch.tensor(t, device=dev)), y0, est.t_max, est.t_min,
-                           atol=atol, rtol=rtol)
+    cond = condition.reshape(1, *est.condition_shape).to(dev).float().reshape(1, -1).contiguous()
+    D = est.layout.D
+    y0 = est._mean_base.to(dev) + est._std_base.to(dev) * torch.randn(num_samples, D, device=dev)
+    if not device_control:
+        y, nfe = odeint_dopri5(lambda y, t: est.forward(y, cond, torch.tensor(t, device=dev)), y0, est.t_max, est.t_min,
+                               atol=atol, rtol=rtol)
+        return (y, nfe) if return_nfe else y
+    solver = DeviceDopri5(num_samples * D, dev, _fm_rhs(est, cond, num_samples, False), atol=atol, rtol=rtol)
+    y, nfe, _, _ = solver.solve(y0, est.t_max, est.t_min)
+    y = y.reshape(num_samples, D).clone()
     return (y, nfe) if return_nfe else y
+
+
+@torch.no_grad()
+def log_prob_ode(est: FlowMatchingEstimator, theta: Tensor, condition: Tensor, atol: float = 1e-6,
+                 rtol: float = 1e-5, return_nfe: bool = False):
+    """log q(theta | x) of the flow-matching posterior through the probability-flow ODE with the EXACT
+    trace: integrate [theta, 0] from t_min to t_max with d log|det| / dt = div v, then
+    log q = log N(z(t_max); mean_base, std_base) + log|det|   (zuko_ode.py:80-124 -> zuko
+    NormalizingFlow(FreeFormJacobianTransform(exact=True), DiagNormal); vector_field_potential.py:145-212)."""
+    dev = est.net.flat.device
+    D = est.layout.D
+    th = theta.reshape(-1, D).to(dev).float().contiguous()
+    R = th.shape[0]
+    cond = condition.reshape(1, *est.condition_shape).to(dev).float().reshape(1, -1).contiguous()
+    y0 = torch.cat([th.reshape(-1), torch.zeros(R, device=dev)])
+    solver = DeviceDopri5(R * D + R, dev, _fm_rhs(est, cond, R, True), atol=atol, rtol=rtol)
+    y, nfe, _, _ = solver.solve(y0, est.t_min, est.t_max)
+    z, ladj = y[:R * D].reshape(R, D), y[R * D:]
+    mu, sd = est._mean_base.to(dev).reshape(1, D), est._std_base.to(dev).reshape(1, D)
+    base = (-0.5 * ((z - mu) / sd) ** 2 - torch.log(sd) - 0.5 * math.log(2 * math.pi)).sum(1)
+    lp = base + ladj
+    return (lp, nfe) if return_nfe else lp
 
 
 @torch.no_grad()

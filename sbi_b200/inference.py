@@ -74,6 +74,10 @@ class _FlowTrainer:
             epoch_durations_sec=[])
         self._graphs = {}
         self._dist = None   # (rank, world) when data-parallel
+        # multi-round bookkeeping (npe_base.py:188-299): round of every appended block and its proposal
+        self._data_round_index: list = []
+        self._proposal_roundwise: list = []
+        self._round_rows: list = []          # rows of every appended block
 
     # ------------------------------------------------------------------ data
     def data_parallel(self, partition: str = "global"):
@@ -144,20 +148,45 @@ class _FlowTrainer:
                            exclude_invalid_x: Optional[bool] = None, data_device: Optional[str] = None):
         """Store simulations (npe_base.py:188-299): float32 only, rows with NaN/Inf in x are
         dropped (user_input_checks.py:708-765, sbiutils.py:491-525)."""
-        if proposal is not None:
-            raise NotImplementedError("multi-round (proposal != prior) training is out of scope")
+        if not hasattr(self, "_data_round_index"):      # trainers with their own __init__ (NRE, FMPE)
+            self._data_round_index, self._proposal_roundwise, self._round_rows = [], [], []
+        # round of this block (npe_base.py:224-241): prior samples are round 0, anything else opens a new round
+        if proposal is None or proposal is self._prior:
+            current_round = 0
+        elif not self._data_round_index:
+            current_round = 1
+        else:
+            current_round = max(self._data_round_index) + 1
+        if current_round > 0:
+            if self._prior is None:
+                raise ValueError("You did not pass a prior at initialization, but now you passed a proposal. "
+                                 "Multi-round inference needs a prior.")
+            if getattr(proposal, "default_x", "unset") is None:     # check_if_proposal_has_default_x
+                raise ValueError("`proposal.default_x` is None: call `proposal.set_default_x(x_o)` first.")
+            if getattr(proposal, "posterior_estimator", None) is not None \
+                    and proposal.posterior_estimator is self._neural_net:
+                raise ValueError("The proposal's posterior_estimator is the same object as the trainer's "
+                                 "neural network; use trainer.build_posterior() or a deepcopy.")
+        if exclude_invalid_x is None:
+            exclude_invalid_x = current_round == 0
         if theta.dtype != torch.float32 or x.dtype != torch.float32:
             raise AssertionError("theta and x must be float32")
         if theta.shape[0] != x.shape[0]:
             raise AssertionError("Number of parameter sets must equal number of simulation outputs")
         xf = x.reshape(x.shape[0], -1)
         ok = ~torch.isnan(xf).any(1) & ~torch.isinf(xf).any(1)
-        if exclude_invalid_x is None or exclude_invalid_x:
-            if not bool(ok.all()):
+        if not bool(ok.all()):
+            if exclude_invalid_x:
                 warnings.warn(f"Found {int((~ok).sum())} invalid simulations; they are excluded.",
                               stacklevel=2)
                 theta, x = theta[ok], x[ok]
+            else:
+                warnings.warn(f"Found {int((~ok).sum())} simulations with NaN/Inf; they are kept "
+                              "(multi-round losses normalise across the batch).", stacklevel=2)
         theta = theta.reshape(theta.shape[0], -1)
+        self._data_round_index.append(current_round)
+        self._proposal_roundwise.append(proposal)
+        self._round_rows.append(int(theta.shape[0]))
         th = theta.to(self._device).contiguous()
         xx = x.to(self._device).contiguous()
         if self._theta is None:
@@ -187,6 +216,18 @@ class _FlowTrainer:
             raise ValueError("calibration_kernel is an argument of the posterior-estimator trainers (NPE)")
         if self._theta is None:
             raise RuntimeError("call append_simulations() first")
+        self._round = max(self._data_round_index) if getattr(self, "_data_round_index", None) else 0
+        if self._round > 0 and not self._swap and not force_first_round_loss:
+            # later rounds of NPE: atomic proposal correction (npe_c.py), eager steps
+            return self._train_multiround(
+                training_batch_size=training_batch_size, learning_rate=learning_rate,
+                validation_fraction=validation_fraction, stop_after_epochs=stop_after_epochs,
+                max_num_epochs=max_num_epochs, clip_max_norm=clip_max_norm, calibration_kernel=calibration_kernel,
+                resume_training=resume_training, discard_prior_samples=discard_prior_samples,
+                retrain_from_scratch=retrain_from_scratch)
+        if self._round > 0 and discard_prior_samples:
+            raise NotImplementedError("discard_prior_samples with the first-round loss is not implemented "
+                                      "(append only the rounds to train on)")
         lib = L.load()
         dev = self._device
         N = self._theta.shape[0]
@@ -413,6 +454,110 @@ class _FlowTrainer:
                 raise RuntimeError("peer-memory gradient exchange timed out (a rank fell behind or died)")
         return deepcopy(net)
 
+    def _train_multiround(self, training_batch_size, learning_rate, validation_fraction, stop_after_epochs,
+                          max_num_epochs, clip_max_norm, calibration_kernel, resume_training,
+                          discard_prior_samples, retrain_from_scratch):
+        """Rounds > 0 of NPE-C (npe_c.py:126-231 + the shared loop of trainers/base.py:1060-1284): the
+        network of the previous round keeps training on the simulations of all rounds with the atomic
+        proposal-posterior loss.  Steps are eager (log-prob kernel -> soft-max head in torch -> fused
+        forward+backward kernel through autograd -> clip_grad_norm_ -> Adam), exactly the reference's
+        operation sequence; the B x num_atoms evaluations per step are what the kernels are for."""
+        from .multiround import atomic_log_prob_proposal_posterior, clamp_num_atoms
+        from .posteriors import prior_to_device
+        if getattr(self, "_dist", None) is not None and self._dp()[1] > 1:
+            raise NotImplementedError("multi-round training is single-process")
+        dev = self._device
+        num_atoms = int(getattr(self, "_num_atoms", 10))
+        combined = bool(getattr(self, "_use_combined_loss", False))
+        start_round = int(bool(discard_prior_samples) and self._round > 0)        # base.py _get_start_index
+        rounds = torch.repeat_interleave(torch.as_tensor(self._data_round_index),
+                                         torch.as_tensor(self._round_rows)).to(dev)
+        sel = torch.nonzero(rounds >= start_round).reshape(-1)
+        theta_all, x_all = self._theta[sel], self._x[sel]
+        masks_all = (rounds[sel] == 0).to(torch.float32)                         # mask_sims_from_prior
+        N = theta_all.shape[0]
+        n_train = int((1 - validation_fraction) * N)
+        n_val = N - n_train
+        if not resume_training or getattr(self, "_mr_split_n", None) != N:
+            perm = torch.randperm(N)
+            self.train_indices, self.val_indices = perm[:n_train], perm[n_train:]
+            self._mr_split_n = N
+        if self._neural_net is None or retrain_from_scratch:
+            tr = self.train_indices.to(dev)
+            self._neural_net = self._build_neural_net(theta_all[tr].cpu(), x_all[tr].cpu())
+        net = self._neural_net.to(dev)
+        self._neural_net = net
+        prior = prior_to_device(self._prior, dev)
+        B, Bv = min(training_batch_size, n_train), min(training_batch_size, n_val)
+        steps, vsteps = n_train // B, (n_val // Bv if Bv > 0 else 0)
+        if not resume_training or not hasattr(self, "_mr_opt"):
+            self._mr_opt = torch.optim.Adam(list(net.parameters()), lr=learning_rate)
+            self.epoch, self._val_loss = 0, float("Inf")
+            self._best_val_loss, self._best_flat, self._epochs_since_last_improvement = float("Inf"), None, 0
+        opt = self._mr_opt
+        train_idx, val_idx = self.train_indices.to(dev), self.val_indices.to(dev)
+        w_all = None
+        if calibration_kernel is not None:
+            w_all = torch.as_tensor(calibration_kernel(x_all), dtype=torch.float32).reshape(-1).to(dev)
+
+        def losses_of(idx):
+            th, xx, mk = theta_all[idx], x_all[idx], masks_all[idx]
+            lp = atomic_log_prob_proposal_posterior(net, prior, th, xx, mk, num_atoms, combined)
+            if not bool(torch.isfinite(lp).all()):
+                raise AssertionError("NaN/Inf present in NPE loss.")
+            return -lp if w_all is None else -lp * w_all[idx]
+
+        def converged() -> bool:
+            if self.epoch == 0 or self._val_loss < self._best_val_loss:
+                self._best_val_loss, self._epochs_since_last_improvement = self._val_loss, 0
+                self._best_flat = net.flat.data.clone()
+            else:
+                self._epochs_since_last_improvement += 1
+            if self._epochs_since_last_improvement > stop_after_epochs - 1:
+                net.flat.data.copy_(self._best_flat)
+                return True
+            return False
+
+        clamp_num_atoms(num_atoms, min(B, Bv) if vsteps > 0 else B)      # warn once, like the reference does per call
+        with warnings.catch_warnings():
+            warnings.filterwarnings("ignore", message="num_atoms=")
+            while self.epoch <= max_num_epochs and not converged():
+                t0 = time.time()
+                net.train()
+                perm = train_idx[torch.randperm(n_train, device=dev)]
+                tsum = torch.zeros((), device=dev)
+                for s_ in range(steps):
+                    opt.zero_grad()
+                    losses = losses_of(perm[s_ * B:(s_ + 1) * B])
+                    losses.mean().backward()
+                    tsum += losses.detach().sum()
+                    if clip_max_norm is not None:
+                        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=clip_max_norm)
+                    opt.step()
+                net.eval()
+                vsum = torch.zeros((), device=dev)
+                with torch.no_grad():
+                    vperm = val_idx[torch.randperm(n_val, device=dev)] if vsteps > 0 else None
+                    for s_ in range(vsteps):
+                        vsum += losses_of(vperm[s_ * Bv:(s_ + 1) * Bv]).sum()
+                self._summary["training_loss"].append(float(tsum.item()) / (steps * B))
+                self._val_loss = float(vsum.item()) / (vsteps * Bv) if vsteps > 0 else float("nan")
+                self._summary["validation_loss"].append(self._val_loss)
+                self._summary["epoch_durations_sec"].append(time.time() - t0)
+                self.epoch += 1
+        if self.epoch > max_num_epochs:
+            if self._val_loss < self._best_val_loss:
+                self._best_val_loss, self._best_flat = self._val_loss, net.flat.data.clone()
+            elif self._best_flat is not None:
+                net.flat.data.copy_(self._best_flat)
+            warnings.warn(f"Maximum number of epochs `max_num_epochs={max_num_epochs}` reached, "
+                          "but network has not yet fully converged.", stacklevel=3)
+        self._summary["epochs_trained"].append(self.epoch)
+        self._summary["best_validation_loss"].append(self._best_val_loss)
+        net.zero_grad(set_to_none=True)
+        net._cache.clear()
+        return deepcopy(net)
+
     @property
     def summary(self):
         return self._summary
@@ -421,6 +566,25 @@ class _FlowTrainer:
 class NPE(_FlowTrainer):
     """Neural posterior estimation, first round (reference: NPE_C, npe_c.py:91 / npe_base.py)."""
     _swap = False
+
+    def train(self, num_atoms: int = 10, training_batch_size: int = 200, learning_rate: float = 5e-4,
+              validation_fraction: float = 0.1, stop_after_epochs: int = 20, max_num_epochs: int = 2 ** 31 - 1,
+              clip_max_norm: Optional[float] = 5.0, calibration_kernel: Optional[Callable] = None,
+              resume_training: bool = False, force_first_round_loss: bool = False,
+              discard_prior_samples: bool = False, use_combined_loss: bool = False,
+              retrain_from_scratch: bool = False, show_train_summary: bool = False,
+              dataloader_kwargs: Optional[dict] = None):
+        """npe_c.py:126-231 (same argument order): `num_atoms` / `use_combined_loss` only matter from the
+        second round on (atomic proposal correction, `_train_multiround`)."""
+        self._num_atoms, self._use_combined_loss = num_atoms, use_combined_loss
+        return super().train(training_batch_size=training_batch_size, learning_rate=learning_rate,
+                             validation_fraction=validation_fraction, stop_after_epochs=stop_after_epochs,
+                             max_num_epochs=max_num_epochs, clip_max_norm=clip_max_norm,
+                             calibration_kernel=calibration_kernel, resume_training=resume_training,
+                             force_first_round_loss=force_first_round_loss,
+                             discard_prior_samples=discard_prior_samples,
+                             retrain_from_scratch=retrain_from_scratch, show_train_summary=show_train_summary,
+                             dataloader_kwargs=dataloader_kwargs)
 
     def build_posterior(self, density_estimator: Optional[nn.Module] = None, prior=None,
                         sample_with: str = "direct", **kwargs):
@@ -510,11 +674,12 @@ class NRE_B(_FlowTrainer):
         own = torch.arange(lo, hi, device=device).unsqueeze(1)
         return draws + (draws >= own).long()
 
-    def _loss_on(self, net, idx: Tensor, num_atoms: int, choices: Optional[Tensor] = None,
-                 rows: Optional[tuple] = None) -> Tensor:
-        """NRE-B loss (nre_b.py:157-182) of the batch rows [rows[0], rows[1]) (default: all) of the
-        batch `idx`; the contrastive thetas of a row come from the WHOLE batch (with the
-        global batch on every rank the data-parallel loss keeps the single-GPU semantics)."""
+    def _logits_on(self, net, idx: Tensor, num_atoms: int, choices: Optional[Tensor] = None,
+                   rows: Optional[tuple] = None) -> Tensor:
+        """`_classifier_logits` (nre_base.py:396-415) of the batch rows [rows[0], rows[1]) (default: all)
+        of the batch `idx`: (n, num_atoms) logits, column 0 the jointly drawn pair; the contrastive thetas
+        of a row come from the WHOLE batch (with the global batch on every rank the
+        data-parallel loss keeps the single-GPU semantics)."""
         from .ratio import _RatioFn
         B = idx.shape[0]
         lo, hi = rows if rows is not None else (0, B)
@@ -523,7 +688,12 @@ class NRE_B(_FlowTrainer):
         local = torch.cat([torch.arange(lo, hi, device=idx.device).unsqueeze(1), choices], dim=1)   # (n, A)
         ti = idx[local].reshape(-1).contiguous()
         xi = idx[lo:hi].repeat_interleave(num_atoms).contiguous()
-        logits = _RatioFn.apply(net.net.flat, self._theta, self._x2d, net, ti, xi, False).reshape(hi - lo, num_atoms)
+        return _RatioFn.apply(net.net.flat, self._theta, self._x2d, net, ti, xi, False).reshape(hi - lo, num_atoms)
+
+    def _loss_on(self, net, idx: Tensor, num_atoms: int, choices: Optional[Tensor] = None,
+                 rows: Optional[tuple] = None) -> Tensor:
+        """NRE-B loss (nre_b.py:157-182): 1-out-of-`num_atoms` cross-entropy."""
+        logits = self._logits_on(net, idx, num_atoms, choices, rows)
         log_prob = logits[:, 0] - torch.logsumexp(logits, dim=-1)
         return -torch.mean(log_prob)
 
@@ -718,6 +888,69 @@ class NRE_B(_FlowTrainer):
 
 SNRE_B = NRE_B
 SNRE = NRE_B
+
+
+class NRE_A(NRE_B):
+    """AALR / NRE-A (reference: trainers/nre/nre_a.py:103-190): binary classification of the jointly drawn
+    pair against ONE contrastive pair; same trainer, two atoms, BCE head."""
+
+    def train(self, training_batch_size: int = 200, learning_rate: float = 5e-4, validation_fraction: float = 0.1,
+              stop_after_epochs: int = 20, max_num_epochs: int = 2 ** 31 - 1, clip_max_norm: Optional[float] = 5.0,
+              resume_training: bool = False, discard_prior_samples: bool = False, retrain_from_scratch: bool = False,
+              show_train_summary: bool = False, dataloader_kwargs: Optional[dict] = None):
+        return NRE_B.train(self, num_atoms=2, training_batch_size=training_batch_size, learning_rate=learning_rate,
+                           validation_fraction=validation_fraction, stop_after_epochs=stop_after_epochs,
+                           max_num_epochs=max_num_epochs, clip_max_norm=clip_max_norm,
+                           resume_training=resume_training, discard_prior_samples=discard_prior_samples,
+                           retrain_from_scratch=retrain_from_scratch, show_train_summary=show_train_summary,
+                           dataloader_kwargs=dataloader_kwargs)
+
+    def _loss_on(self, net, idx, num_atoms, choices=None, rows=None):
+        from .multiround import nre_a_loss
+        return nre_a_loss(self._logits_on(net, idx, 2, choices, rows))
+
+
+SNRE_A = NRE_A
+AALR = NRE_A
+
+
+class BNRE(NRE_A):
+    """Balanced NRE (reference: trainers/nre/bnre.py:103-200): NRE-A plus the balancing regulariser
+    `regularization_strength * (E[sigmoid(l_joint) + sigmoid(l_marginal) - 1])^2`."""
+
+    def train(self, regularization_strength: float = 100.0, training_batch_size: int = 200, **kwargs):
+        self._regularization_strength = float(regularization_strength)
+        if getattr(self, "_dist", None) is not None and self._dp()[1] > 1:
+            raise NotImplementedError("the balancing regulariser is a function of the batch mean: BNRE trains "
+                                      "on one process")
+        return NRE_A.train(self, training_batch_size=training_batch_size, **kwargs)
+
+    def _loss_on(self, net, idx, num_atoms, choices=None, rows=None):
+        from .multiround import bnre_loss
+        return bnre_loss(self._logits_on(net, idx, 2, choices, rows), self._regularization_strength)
+
+
+class NRE_C(NRE_B):
+    """Contrastive NRE (reference: trainers/nre/nre_c.py:103-259): `num_classes` = K contrastive classes
+    and the odds `gamma` of a jointly drawn pair; two independent contrastive draws per step (K + 1 and K
+    atoms)."""
+
+    def train(self, num_classes: int = 5, gamma: float = 1.0, training_batch_size: int = 200, **kwargs):
+        self._gamma = float(gamma)
+        return NRE_B.train(self, num_atoms=num_classes + 1, training_batch_size=training_batch_size, **kwargs)
+
+    def _loss_on(self, net, idx, num_atoms, choices=None, rows=None):
+        from .multiround import nre_c_loss
+        K = num_atoms - 1
+        if K < 1:
+            raise AssertionError(f"num_classes = {K} must be greater than 1.")
+        cm, cj = (choices if choices is not None else (None, None))
+        logits_marginal = self._logits_on(net, idx, K + 1, cm, rows)
+        logits_joint = self._logits_on(net, idx, K, cj, rows)
+        return nre_c_loss(logits_marginal, logits_joint, self._gamma)
+
+
+SNRE_C = NRE_C
 
 
 # =================================================================================================

@@ -212,7 +212,61 @@ def build_maf(
     return est
 
 
-_BUILDERS = {"nsf": build_nsf, "maf": build_maf}
+def build_maf_rqs(
+    batch_x: Tensor, batch_y: Tensor, z_score_x="independent", z_score_y="independent",
+    hidden_features: int = 50, num_transforms: int = 5, embedding_net: nn.Module = nn.Identity(),
+    num_blocks: int = 2, num_bins: int = 10, tails: Optional[str] = "linear", tail_bound: float = 3.0,
+    dropout_probability: float = 0.0, use_batch_norm: bool = False, min_bin_width: float = 1e-3,
+    min_bin_height: float = 1e-3, min_derivative: float = 1e-3, **kwargs,
+) -> FlowEstimator:
+    """Builds MAF p(x|y) whose element-wise maps are rational-quadratic splines; same arguments as the
+    reference (flow.py:212-330): per transform a `MaskedPiecewiseRationalQuadraticAutoregressiveTransform(
+    hidden, context, num_bins, tails="linear", tail_bound, num_blocks, use_residual_blocks=False, tanh)`
+    followed by a `RandomPermutation`.  Same MADE and RNG order as `build_maf`; the final masked layer
+    emits 3*num_bins - 1 raw spline parameters per feature."""
+    check_data_device(batch_x, batch_y)
+    if z_score_x == "transform_to_unconstrained":
+        raise ValueError("`transform_to_unconstrained` is not supported by build_maf_rqs.")
+    if dropout_probability != 0.0 or use_batch_norm:
+        raise NotImplementedError("dropout / batch norm are not implemented in the sm_100a MAF kernels")
+    if tails != "linear":
+        raise NotImplementedError("the sm_100a spline code implements tails='linear' (the reference default)")
+    x_numel = batch_x[0].numel()
+    with torch.no_grad():
+        y_numel = embedding_net(batch_y[:1]).numel()
+    zx, sx = z_score_parser(z_score_x)
+    zy, sy = z_score_parser(z_score_y)
+    H, C, D = hidden_features, y_numel, x_numel
+    mult = 3 * num_bins - 1
+    state, perms = {}, []
+    base = 1 if zx else 0
+    for l in range(num_transforms):
+        pa = f"net._transform._transforms.{base + 2 * l}.autoregressive_net."
+        state[pa + "initial_layer.weight"], state[pa + "initial_layer.bias"] = _linear_init(H, D)
+        state[pa + "context_layer.weight"], state[pa + "context_layer.bias"] = _linear_init(H, C)
+        for b in range(num_blocks):
+            state[pa + f"blocks.{b}.linear.weight"], state[pa + f"blocks.{b}.linear.bias"] = _linear_init(H, H)
+        state[pa + "final_layer.weight"], state[pa + "final_layer.bias"] = _linear_init(mult * D, H)
+        perms.append(torch.randperm(D).numpy())
+    lay = MafLayout(D=D, C=C, H=H, NB=num_blocks, T=num_transforms, perms=perms, zscore_input=zx,
+                    zscore_cond=zy, embed_is_identity=isinstance(embedding_net, nn.Identity),
+                    head="rqs", KB=num_bins, tail_bound=float(tail_bound), min_bin_width=float(min_bin_width),
+                    min_bin_height=float(min_bin_height), min_derivative=float(min_derivative))
+    if zx:
+        t_mean, t_std = z_standardization(batch_x.reshape(batch_x.shape[0], -1), sx)
+        shift, scale = -t_mean / t_std, 1 / t_std
+    else:
+        shift, scale = torch.zeros(()), torch.ones(())
+    c_mean, c_std = standardizing_stats(batch_y, sy) if zy else (None, None)
+    est = FlowEstimator(lay, input_shape=batch_x[0].shape, condition_shape=batch_y[0].shape,
+                        shift=shift, scale=scale, cond_mean=c_mean, cond_std=c_std,
+                        embedding_net=embedding_net)
+    with torch.no_grad():
+        lay.pack(state, out=est.net.flat.data, raw_out=est.net._raw)
+    return est
+
+
+_BUILDERS = {"nsf": build_nsf, "maf": build_maf, "maf_rqs": build_maf_rqs}
 
 
 def _density_build_fn(model: str, input_is_theta: bool, **kw) -> Callable:

@@ -405,13 +405,25 @@ class MafLayout(_LayoutOps):
     wcap_target: int = 4096
     n_params: int = 0
     index: Dict[str, np.ndarray] = field(default_factory=dict, repr=False)
+    # element-wise transform: "affine" (maf) or "rqs" (maf_rqs, flow.py:212-330; linear tails)
+    head: str = "affine"
+    KB: int = 10
+    tail_bound: float = 3.0
+    min_bin_width: float = 1e-3
+    min_bin_height: float = 1e-3
+    min_derivative: float = 1e-3
 
     def __post_init__(self):
         D, C, H, NB, T = self.D, self.C, self.H, self.NB, self.T
         if NB > 8:
             raise ValueError("num_blocks <= 8")
+        if self.head not in ("affine", "rqs"):
+            raise ValueError(self.head)
+        if self.head == "rqs" and not (2 <= self.KB <= 16):
+            raise ValueError("the spline code keeps <= 16 bins in registers")
+        self.OUTM = 2 if self.head == "affine" else 3 * self.KB - 1
         self.Dp, self.Cp, self.Hp = round4(D), round4(C), round4(H)
-        self.OUTp = round4(2 * D)
+        self.OUTp = round4(self.OUTM * D)
         Hp, Dp, Cp = self.Hp, self.Dp, self.Cp
         cap = max(self.wcap_target, 4 * (Dp + Cp), 4 * Hp)
 
@@ -428,8 +440,8 @@ class MafLayout(_LayoutOps):
         hid_deg = np.arange(H) % max_ + min_
         m_init = (hid_deg[:, None] >= in_deg[None, :]).astype(np.float32)      # (H, D)
         m_hid = (hid_deg[:, None] >= hid_deg[None, :]).astype(np.float32)      # (H, H)
-        out_deg = np.repeat(in_deg, 2)                                         # tile(.., 2)
-        m_out = (out_deg[:, None] > hid_deg[None, :]).astype(np.float32)       # (2D, H)
+        out_deg = np.repeat(in_deg, self.OUTM)                                 # tile(.., OUTM)
+        m_out = (out_deg[:, None] > hid_deg[None, :]).astype(np.float32)       # (OUTM*D, H)
         self.degrees = dict(input=in_deg, hidden=hid_deg, output=out_deg)
 
         off = 0
@@ -483,13 +495,13 @@ class MafLayout(_LayoutOps):
                 idx[pb + "bias"] = o + np.arange(H)
             o = take(self.OUTp * Hp)
             tab[l, L.M_WF] = o
-            idx[pa + "final_layer.weight"] = o + np.arange(2 * D)[:, None] * Hp + np.arange(H)[None, :]
+            idx[pa + "final_layer.weight"] = o + np.arange(self.OUTM * D)[:, None] * Hp + np.arange(H)[None, :]
             wm[pa + "final_layer.weight"] = m_out
             self.buffers[pa + "final_layer.mask"] = torch.as_tensor(m_out)
             self.buffers[pa + "final_layer.degrees"] = torch.as_tensor(out_deg)
             o = take(self.OUTp)
             tab[l, L.M_BF] = o
-            idx[pa + "final_layer.bias"] = o + np.arange(2 * D)
+            idx[pa + "final_layer.bias"] = o + np.arange(self.OUTM * D)
         self.n_params = off
         self.index = idx
         self._weight_masks = wm
@@ -525,6 +537,10 @@ class MafLayout(_LayoutOps):
         s.rpc0, s.rpc1, s.rpcf = self.rpc0, self.rpc1, self.rpcf
         s.wcap, s.nbuf, s.n_params = self.wcap, nbuf, self.n_params
         s.scale_softplus = 1 if self.scale_softplus else 0
+        s.head, s.KB, s.OUTM = (0 if self.head == "affine" else 1), self.KB, self.OUTM
+        s.tail_bound, s.min_w, s.min_h, s.min_d = (self.tail_bound, self.min_bin_width, self.min_bin_height,
+                                                   self.min_derivative)
+        s.isq = 1.0     # nflows' MADE has no `hidden_features` attribute: no 1/sqrt(H) logit scaling here
         return s
 
 

@@ -421,3 +421,28 @@ class VectorFieldPosterior:
         else:
             samples = proposal((num_samples,))[:, 0]
         return samples.reshape(*torch.Size(sample_shape), -1)
+
+    @torch.no_grad()
+    def log_prob(self, theta: Tensor, x: Optional[Tensor] = None, track_gradients: bool = False,
+                 ode_kwargs: Optional[dict] = None) -> Tensor:
+        """log q(theta | x) via the probability-flow ODE with the exact trace (reference:
+        vector_field_posterior.py:467-505 -> VectorFieldBasedPotential.__call__,
+        vector_field_potential.py:145-212): -inf outside the prior support."""
+        from .flowmatching import log_prob_ode
+        if track_gradients:
+            raise NotImplementedError("gradients of the neural-ODE log-probability are not implemented")
+        x = x if x is not None else self.default_x
+        if x is None:
+            raise ValueError("Context `x` needed when a default has not been set.")
+        x = torch.as_tensor(x, dtype=torch.float32).to(self._device)
+        est = self.vector_field_estimator
+        if x.reshape(-1).numel() != int(torch.Size(est.condition_shape).numel()):
+            raise NotImplementedError("iid observations are not supported by the ODE log-probability here")
+        th = torch.as_tensor(theta, dtype=torch.float32).to(self._device)
+        th = th.reshape(-1, th.shape[-1])
+        kw = dict(ode_kwargs or {})
+        lp, nfe = log_prob_ode(est, th, x, atol=kw.get("atol", 1e-6), rtol=kw.get("rtol", 1e-5), return_nfe=True)
+        self.num_function_evaluations += nfe
+        if self.prior is not None:
+            lp = torch.where(within_support(self.prior, th), lp, torch.full_like(lp, float("-inf")))
+        return lp

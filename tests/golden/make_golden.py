@@ -12,6 +12,7 @@ Fixtures (small, committed):
                   validation-loss trajectory, final state_dict, train/val indices.
   maf_d3c2.pt     reference `posterior_nn("maf")` (theta-dim 3, x-dim 2; BASELINE configs[0]): state_dict,
                   permutations, log_prob and inverse outputs.
+  maf_rqs_d4c3.pt reference `posterior_nn("maf_rqs")` (theta-dim 4, x-dim 3): same contents as maf_d3c2.pt.
   searchsorted.pt the reference's bin-search known-answer test vectors (tests/torchutils_test.py:135-157).
   ratio_d4x6.pt   reference `classifier_nn("resnet")` (theta-dim 4, x-dim 6): state_dict, pairs, logits.
   fm_d5c3.pt      reference `posterior_flow_nn("mlp")` (theta-dim 5, x-dim 3): state_dict, inputs, times,
@@ -56,12 +57,12 @@ def flow_fixture(D, C, seed, n=400):
                 inverse_logabsdet=lad, D=D, C=C, seed=seed)
 
 
-def maf_fixture(D, C, seed, n=400):
+def maf_fixture(D, C, seed, n=400, model="maf"):
     g = torch.Generator().manual_seed(seed)
     theta = 0.7 * torch.randn(n, D, generator=g) + 0.3
     x = 1.3 * torch.randn(n, C, generator=g) - 0.2
     torch.manual_seed(seed)
-    est = posterior_nn("maf")(theta, x)
+    est = posterior_nn(model)(theta, x)
     with torch.no_grad():
         for name, p in est.named_parameters():
             p.add_(0.1 * torch.randn(p.shape, generator=g))
@@ -147,6 +148,8 @@ if __name__ == "__main__":
     torch.save(flow_fixture(3, 2, 8), os.path.join(HERE, "nsf_d3c2.pt"))
     torch.save(train_fixture(), os.path.join(HERE, "npe_train.pt"))
     torch.save(maf_fixture(3, 2, 9), os.path.join(HERE, "maf_d3c2.pt"))
+    if "--new" in sys.argv or not os.path.exists(os.path.join(HERE, "maf_rqs_d4c3.pt")):
+        torch.save(maf_fixture(4, 3, 14, model="maf_rqs"), os.path.join(HERE, "maf_rqs_d4c3.pt"))
     torch.save(searchsorted_fixture(), os.path.join(HERE, "searchsorted.pt"))
     torch.save(ratio_fixture(4, 6, 12), os.path.join(HERE, "ratio_d4x6.pt"))
     torch.save(fm_fixture(5, 3, 13), os.path.join(HERE, "fm_d5c3.pt"))
