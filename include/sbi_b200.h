@@ -378,6 +378,24 @@ int sbi_b200_ode_stage(const float* d_y, const float* d_k, float* d_yi, int64_t 
 int sbi_b200_ode_error_commit(float* d_y, float* d_k, float* d_y5, float* d_red, int64_t n,
                               sbi_ode_ctrl* d_ctrl, void* stream);
 
+/* One Euler-Maruyama step of the reverse SDE of the flow-matching estimator (csrc/ode.cu; reference
+ * sbi/samplers/score/predictors.py:112-120 on flowmatching_estimator.py:374-469): d_theta (n = R*D) is
+ * updated in place from the velocity d_v at time ts[i-1] and the normal draw d_z; d_ctrl = [current time,
+ * step index i] (floats) is advanced to ts[i], i+1, so that a captured step can be replayed. */
+int sbi_b200_sde_em_step(float* d_theta, const float* d_v, const float* d_z, int64_t n, const float* d_ts,
+                         float* d_ctrl, float eta, float noise_scale, float t_eff, void* stream);
+
+/* ---- rejection sampling: accept / reject + order-preserving compaction of one batch of proposals
+ * (csrc/compact.cu; reference sbi/samplers/rejection/rejection.py:170-200, `keep = exp(potential - scaled
+ * proposal log-prob) > u; candidates[keep]`).  Accepted rows are appended, in proposal order, at
+ * d_out[*d_count ...] (rows past `cap` are dropped but counted), their global proposal indices
+ * (index_base + position) at d_out_idx (optional); *d_count is advanced on the device.
+ * d_scratch: sbi_b200_reject_scratch_ints(n) int32. */
+int64_t sbi_b200_reject_scratch_ints(int64_t n);
+int sbi_b200_reject_compact(const float* d_cand, int32_t D, const float* d_log_target, const float* d_log_scaled,
+                            const float* d_u, int64_t n, int64_t index_base, float* d_out, int64_t* d_out_idx,
+                            int64_t cap, int32_t* d_count, int32_t* d_scratch, void* stream);
+
 /* ---- multi-GPU: gradient sum over NVLink peer memory (csrc/peer.cu), replacing the NCCL all-reduce +
  * norm pass of the data-parallel step (reference semantics: clip_grad_norm_ + Adam on the summed
  * gradient, sbi/inference/trainers/base.py:1181-1187).  Each rank allocates a symmetric buffer

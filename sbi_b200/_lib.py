@@ -175,6 +175,12 @@ _EXPORTS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_fm_forward_div": (C.c_int, [C.POINTER(FmModel), C.POINTER(Rows), C.c_void_p, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "sbi_b200_sde_em_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "sbi_b200_reject_scratch_ints": (C.c_int64, [C.c_int64]),
+    "sbi_b200_reject_compact": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
     "sbi_b200_ode_red_size": (C.c_int, [C.c_int64]),
     "sbi_b200_ode_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                      C.c_void_p]),

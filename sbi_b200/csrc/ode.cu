@@ -121,6 +121,38 @@ __global__ void commit_kernel(float* __restrict__ y, const float* __restrict__ y
   }
 }
 
+// ---- reverse SDE, Euler-Maruyama predictor (no corrector) ---------------------------------------------------
+// One step of /root/reference/sbi/samplers/score/predictors.py:112-120 (EulerMaruyama.predict) on the
+// flow-matching estimator's SDE view (/root/reference/sbi/neural_nets/estimators/flowmatching_estimator.py:
+// 374-469: score, drift_fn, diffusion_fn), driven by Diffuser.run (samplers/score/diffuser.py:124-180):
+//   f = -theta / max(1 - t1, 1 - t_eff) ; g = sqrt(2 (t1 + s) / max(1 - t1, 1 - t_eff))
+//   score = (-(1 - t1) v - theta) / (t1 + s) ; theta <- theta - (f - (1 + eta^2)/2 g^2 score) dt + eta g z sqrt(dt)
+// with t1 = ts[i-1], dt = t1 - ts[i], v the velocity at (theta, t1) (fm_forward reads t1 from ctrl[0]).
+// ctrl = [t_cur, step index as float]; sde_advance moves it to the next grid point after the update.
+__global__ void sde_em_step_kernel(float* __restrict__ theta, const float* __restrict__ v, const float* __restrict__ z,
+                                   int64_t n, const float* __restrict__ ts, const float* __restrict__ ctrl, float eta,
+                                   float noise_scale, float t_eff) {
+  const int i = (int)ctrl[1];
+  const float t1 = ts[i - 1], t0 = ts[i];
+  const float dt = t1 - t0;
+  const float omt = fmaxf(1.f - t1, 1.f - t_eff);
+  const float g = sqrtf(2.f * (t1 + noise_scale) / omt);
+  const float c = (1.f + eta * eta) / 2.f * g * g;
+  const float sq = sqrtf(dt);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const float th = theta[e];
+    const float f = -th / omt;
+    const float score = (-(1.f - t1) * v[e] - th) / (t1 + noise_scale);
+    const float fb = f - c * score;
+    theta[e] = th - fb * dt + (eta * g) * z[e] * sq;
+  }
+}
+__global__ void sde_advance_kernel(const float* __restrict__ ts, float* __restrict__ ctrl) {
+  const int i = (int)ctrl[1];
+  ctrl[0] = ts[i];
+  ctrl[1] = (float)(i + 1);
+}
+
 static int grid_for(int64_t n) {
   const int64_t b = (n + kBlock - 1) / kBlock;
   const int64_t cap = (int64_t)dev_num_sms() * 8;
@@ -149,5 +181,15 @@ extern "C" int sbi_b200_ode_error_commit(float* d_y, float* d_k, float* d_y5, fl
   const int g = ode::grid_for(n);
   ode::error_kernel<<<g, ode::kBlock, 0, (cudaStream_t)stream>>>(d_y, d_k, d_y5, d_red, n, d_ctrl);
   ode::commit_kernel<<<g, ode::kBlock, 0, (cudaStream_t)stream>>>(d_y, d_y5, d_k, d_red, g, n, d_ctrl);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int sbi_b200_sde_em_step(float* d_theta, const float* d_v, const float* d_z, int64_t n, const float* d_ts,
+                                    float* d_ctrl, float eta, float noise_scale, float t_eff, void* stream) {
+  sbi::DeviceGuard dev_guard_(d_theta);
+  if (!d_theta || !d_v || !d_z || !d_ts || !d_ctrl || n < 1) return SBI_EINVAL;
+  ode::sde_em_step_kernel<<<ode::grid_for(n), ode::kBlock, 0, (cudaStream_t)stream>>>(d_theta, d_v, d_z, n, d_ts, d_ctrl,
+                                                                                     eta, noise_scale, t_eff);
+  ode::sde_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_ts, d_ctrl);
   return (int)cudaGetLastError();
 }

@@ -551,24 +551,64 @@ def log_prob_ode(est: FlowMatchingEstimator, theta: Tensor, condition: Tensor, a
 
 @torch.no_grad()
 def sample_sde(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, steps: int = 500,
-               ts: Optional[Tensor] = None, eta: float = 1.0) -> Tensor:
+               ts: Optional[Tensor] = None, eta: float = 1.0, fused: bool = True) -> Tensor:
     """Draw theta ~ q(theta | x) with the reverse SDE, Euler-Maruyama predictor, no corrector
     (Diffuser.run, samplers/score/diffuser.py:124-180; EulerMaruyama.predict,
     samplers/score/predictors.py:112-120; driver VectorFieldPosterior._sample_via_diffusion,
-    vector_field_posterior.py:331-433).  One `fm_forward` kernel per step, the step arithmetic in
-    the reference's order."""
+    vector_field_posterior.py:331-433).  A step is [velocity kernel -> normal draw -> fused update kernel]
+    (csrc/ode.cu `sde_em_step_kernel`), captured once as a CUDA graph and replayed for every grid point;
+    `fused=False` keeps the step arithmetic in torch ops in the reference's order (for comparison)."""
     assert eta > 0, "eta must be positive."
     dev = est.net.flat.device
-    cond = condition.reshape(1, *est.condition_shape).to(dev).float()
+    cond = condition.reshape(1, *est.condition_shape).to(dev).float().reshape(1, -1).contiguous()
     ts = est.solve_schedule(steps) if ts is None else ts
-    ts = ts.to(dev)
-    theta = est._mean_base.to(dev) + est._std_base.to(dev) * torch.randn(num_samples, est.layout.D, device=dev)
-    for i in range(1, ts.numel()):
-        t1, t0 = ts[i - 1], ts[i]
-        dt = t1 - t0
-        f = est.drift_fn(theta, t1)
-        g = est.diffusion_fn(theta, t1)
-        score = est.score(theta, cond, t1)
-        f_backward = f - (1 + eta ** 2) / 2 * g ** 2 * score
-        theta = theta - f_backward * dt + (eta * g) * torch.randn_like(theta) * torch.sqrt(dt)
+    ts = ts.to(dev).float().contiguous()
+    D = est.layout.D
+    theta = est._mean_base.to(dev).reshape(1, D) + est._std_base.to(dev).reshape(1, D) * torch.randn(
+        num_samples, D, device=dev)
+    if not fused:
+        for i in range(1, ts.numel()):
+            t1, t0 = ts[i - 1], ts[i]
+            dt = t1 - t0
+            f = est.drift_fn(theta, t1)
+            g = est.diffusion_fn(theta, t1)
+            score = est.score(theta, cond, t1)
+            f_backward = f - (1 + eta ** 2) / 2 * g ** 2 * score
+            theta = theta - f_backward * dt + (eta * g) * torch.randn_like(theta) * torch.sqrt(dt)
+        return theta
+    lib = L.load()
+    theta = theta.contiguous()
+    n = theta.numel()
+    v = torch.empty_like(theta)
+    z = torch.empty_like(theta)
+    ctrl = torch.stack([ts[0], torch.ones((), device=dev)]).contiguous()       # [t_cur, next grid index]
+    m = est._model(nbuf=2)
+    rows = L.Rows(theta.data_ptr(), cond.data_ptr(), None, num_samples, 1)
+
+    def step():
+        L.check(lib.sbi_b200_fm_forward(C.byref(m), C.byref(rows), ctrl.data_ptr(), 1, v.data_ptr(), L.stream_ptr()),
+                "fm_forward")
+        z.normal_()
+        L.check(lib.sbi_b200_sde_em_step(theta.data_ptr(), v.data_ptr(), z.data_ptr(), n, ts.data_ptr(),
+                                         ctrl.data_ptr(), float(eta), float(est.noise_scale), 0.99, L.stream_ptr()),
+                "sde_em_step")
+
+    nsteps = ts.numel() - 1
+    if nsteps < 1:
+        return theta
+    step()                                        # first step eagerly (kernel attributes), the rest replayed
+    if nsteps > 1:
+        graph = torch.cuda.CUDAGraph()
+        snap = (theta.clone(), ctrl.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        theta.copy_(snap[0]); ctrl.copy_(snap[1])
+        with torch.cuda.graph(graph):
+            step()
+        theta.copy_(snap[0]); ctrl.copy_(snap[1])
+        for _ in range(nsteps - 1):
+            graph.replay()
     return theta

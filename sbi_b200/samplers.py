@@ -207,30 +207,46 @@ def rejection_sample(potential_fn: Callable, proposal: Any, theta_transform: Opt
         return proposal.log_prob(theta) + max_log_ratio + log_m
 
     with torch.no_grad():
+        from . import _lib as L
+        lib = L.load()
         num_sampled_total, num_remaining = 0, num_samples
-        accepted, acc_idx, acceptance_rate = [], [], float("Nan")
+        acceptance_rate = float("Nan")
         leakage_warning_raised = False
         sampling_batch_size = min(num_samples, max_sampling_batch_size)
         start_time = time.time()
+        # accepted draws are appended on the device, in proposal order (csrc/compact.cu); the host reads the
+        # running count once per batch (the reference's boolean indexing synchronises once per batch too)
+        out = out_idx = count = None
+        collected = 0
         while num_remaining > 0:
             if max_sampling_time is not None and (time.time() - start_time) > max_sampling_time:
-                num_collected = sum(s.shape[0] for s in accepted)
-                if return_partial_on_timeout and num_collected > 0:
-                    warnings.warn(f"Timeout exceeded after collecting {num_collected}/{num_samples} samples. "
+                if return_partial_on_timeout and collected > 0:
+                    warnings.warn(f"Timeout exceeded after collecting {collected}/{num_samples} samples. "
                                   "Returning partial results.", stacklevel=2)
-                    return torch.cat(accepted), torch.as_tensor(acceptance_rate)
+                    return out[:collected].clone(), torch.as_tensor(acceptance_rate)
                 raise RuntimeError("Sampling aborted early because rejection sampling exceeded max_sampling_time. "
                                    "This is likely due to extremely low acceptance.")
             candidates = proposal.sample((sampling_batch_size,)).reshape(sampling_batch_size, -1)
-            target_proposal_ratio = torch.exp(potential_fn(candidates) - scaled_log_prob(candidates))
-            uniform_rand = torch.rand(target_proposal_ratio.shape).to(target_proposal_ratio.device)
-            keep = target_proposal_ratio > uniform_rand
-            samples = candidates[keep]
-            accepted.append(samples)
-            if return_indices:
-                acc_idx.append(torch.nonzero(keep).reshape(-1) + num_sampled_total)
+            log_target = potential_fn(candidates).reshape(-1).float().contiguous()
+            dev = log_target.device
+            candidates = candidates.to(dev).float().contiguous()
+            log_scaled = scaled_log_prob(candidates).reshape(-1).float().contiguous()
+            uniform_rand = torch.rand(log_target.shape).to(dev)
+            if out is None:
+                Dth = candidates.shape[1]
+                out = torch.empty(num_samples, Dth, dtype=torch.float32, device=dev)
+                out_idx = torch.empty(num_samples, dtype=torch.int64, device=dev) if return_indices else None
+                count = torch.zeros(1, dtype=torch.int32, device=dev)
+            scratch = torch.empty(int(lib.sbi_b200_reject_scratch_ints(sampling_batch_size)), dtype=torch.int32,
+                                  device=dev)
+            L.check(lib.sbi_b200_reject_compact(
+                candidates.data_ptr(), candidates.shape[1], log_target.data_ptr(), log_scaled.data_ptr(),
+                uniform_rand.data_ptr(), sampling_batch_size, num_sampled_total, out.data_ptr(), L.ptr(out_idx),
+                num_samples, count.data_ptr(), scratch.data_ptr(), L.stream_ptr()), "reject_compact")
+            total = int(count.item())
+            collected = min(total, num_samples)
             num_sampled_total += sampling_batch_size
-            num_remaining -= samples.shape[0]
+            num_remaining = num_samples - total
             acceptance_rate = (num_samples - num_remaining) / num_sampled_total
             sampling_batch_size = min(max_sampling_batch_size,
                                       max(int(1.5 * num_remaining / max(acceptance_rate, 1e-12)), 100))
@@ -238,10 +254,10 @@ def rejection_sample(potential_fn: Callable, proposal: Any, theta_transform: Opt
                 logging.warning(f"Only {acceptance_rate:.3%} proposal samples were accepted. It may take a long "
                                 f"time to collect the remaining {num_remaining} samples.")
                 leakage_warning_raised = True
-        samples = torch.cat(accepted)[:num_samples]
-        assert samples.shape[0] == num_samples, "Number of accepted samples must match required samples."
+        samples = out
+        assert collected == num_samples, "Number of accepted samples must match required samples."
     if return_indices:
-        return samples, torch.as_tensor(acceptance_rate), torch.cat(acc_idx)[:num_samples]
+        return samples, torch.as_tensor(acceptance_rate), out_idx
     return samples, torch.as_tensor(acceptance_rate)
 
 

@@ -169,3 +169,34 @@ def test_single_chain_slice_sampler_interface(cuda_lib):
     assert np.abs(out[200:].std(0) / sd - 1).max() < 0.3
     assert np.allclose(smp.x, out[-1])
     assert len(calls) > 1500
+
+
+def test_reject_compact_kernel_equals_boolean_indexing(cuda_lib):
+    """csrc/compact.cu: accepted rows, their order and their global indices equal `candidates[keep]` /
+    `nonzero(keep)` of the reference expression (rejection.py:178-181), across two appended batches and with
+    the capacity cut."""
+    from sbi_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(0)
+    D, cap = 10, 400_000
+    out = torch.full((cap, D), float("nan"), device="cuda")
+    out_idx = torch.full((cap,), -1, dtype=torch.int64, device="cuda")
+    count = torch.zeros(1, dtype=torch.int32, device="cuda")
+    want_rows, want_idx, base = [], [], 0
+    for n in (1_000_037, 300_001):
+        cand = torch.randn(n, D, generator=g).cuda()
+        lt = torch.randn(n, generator=g).cuda()
+        ls = (torch.randn(n, generator=g) + 1.0).cuda()
+        lt[::1000] = float("nan")
+        u = torch.rand(n, generator=g).cuda()
+        scratch = torch.empty(int(lib.sbi_b200_reject_scratch_ints(n)), dtype=torch.int32, device="cuda")
+        L.check(lib.sbi_b200_reject_compact(cand.data_ptr(), D, lt.data_ptr(), ls.data_ptr(), u.data_ptr(), n, base,
+                                            out.data_ptr(), out_idx.data_ptr(), cap, count.data_ptr(),
+                                            scratch.data_ptr(), L.stream_ptr()), "reject_compact")
+        keep = torch.exp(lt - ls) > u
+        want_rows.append(cand[keep])
+        want_idx.append(torch.nonzero(keep).reshape(-1) + base)
+        base += n
+    want_rows, want_idx = torch.cat(want_rows), torch.cat(want_idx)
+    assert int(count.item()) == want_rows.shape[0] > cap          # overflow is counted, not stored
+    assert torch.equal(out, want_rows[:cap]) and torch.equal(out_idx, want_idx[:cap])
