@@ -47,8 +47,19 @@ enum {
   SBI_L_LU_BIAS = 9,
   SBI_L_FEAT = 10,    /* offset into feat_tab: n_id identity features then n_tr transformed */
   SBI_L_HAS_LU = 11,
+  SBI_L_BC0 = 12,     /* head == SBI_NSF_MOG: second bias of the initial layer (MADE's context_layer.bias) */
   SBI_L_BLK0 = 16     /* per residual block b, 6 ints at SBI_L_BLK0+6*b: W1,B1,W2,B2,WC,BC */
 };
+/* what the conditioner's outputs parameterise (`head`):
+ *   SBI_NSF_SPLINE (0): rational-quadratic coupling transform + LULinear per layer, N(0, I) base (`nsf`)
+ *   SBI_NSF_MOG    (1): `made`: ONE masked residual conditioner (nflows MADE, masks folded into the packed
+ *                       weights) whose outputs are, per feature, M x (logit, mean, unconstrained std) of a
+ *                       mixture of Gaussians; log q = sum_f log MoG_f(z_f), no base density
+ *                       (sbi/neural_nets/net_builders/flow.py:37-112, sbi/utils/nn_utils.py:133-201:
+ *                       MADEMoGWrapper prepends a dummy feature, so D here = features + 1 and feature 0
+ *                       -- whose input the caller sets to 0 -- is excluded from the likelihood). */
+#define SBI_NSF_SPLINE 0
+#define SBI_NSF_MOG 1
 
 /* Neural spline flow (sbi `posterior_nn("nsf")` / `likelihood_nn("nsf")`,
  * reference builder sbi/neural_nets/net_builders/flow.py:333-460). */
@@ -61,6 +72,8 @@ typedef struct {
   int32_t wcap, nbuf;              /* weight ring: floats per slot, slots */
   int32_t n_params;                /* floats in d_params */
   float tail_bound, inv_sqrt_h, min_bw, min_bh, min_d, edge_raw;
+  int32_t head, M;                 /* SBI_NSF_SPLINE / SBI_NSF_MOG; mixture components (PR = round4(3M)) */
+  float mog_eps;                   /* std = softplus(.) + mog_eps */
   float ld_zscore;                 /* sum_d log|scale_d| of the input z-score transform */
   const float* d_params;           /* packed parameters (see sbi_b200/pack.py) */
   const int32_t* d_layer_tab;      /* T * SBI_NSF_LAYER_STRIDE */
@@ -101,6 +114,12 @@ int sbi_b200_nsf_vjp(const sbi_nsf_model* m, const sbi_rows* rows, const float* 
  * d_logabsdet (R,) optional = log|det d x / d noise|. */
 int sbi_b200_nsf_inverse(const sbi_nsf_model* m, const sbi_rows* rows, float* d_out,
                          float* d_logabsdet, void* stream);
+
+/* `made` sampling (MixtureOfGaussiansMADE.sample, D sequential conditioner passes): d_input of `rows` holds
+ * standard-normal draws (R, D), d_uniform (R, D) uniforms in [0, 1) that select the mixture components
+ * (inverse CDF); d_out (R, D) samples in the ORIGINAL space (column 0 is the wrapper's dummy feature). */
+int sbi_b200_made_sample(const sbi_nsf_model* m, const sbi_rows* rows, const float* d_uniform, float* d_out,
+                         void* stream);
 
 /* grad[p] = sum_i gpart[i][p]  (i < n_part) */
 int sbi_b200_reduce_partials(const float* d_gpart, int n_part, int64_t n_params, float* d_grad,

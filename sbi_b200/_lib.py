@@ -18,7 +18,7 @@ SBI_NSF_LAYER_STRIDE = 64
 SBI_NSF_MAX_BLOCKS = 8
 # layer-table field indices (mirror include/sbi_b200.h)
 L_NID, L_NTR, L_W0, L_B0, L_WF, L_BF = 0, 1, 2, 3, 4, 5
-L_LU_LOWER, L_LU_UPPER, L_LU_DIAG, L_LU_BIAS, L_FEAT, L_HAS_LU, L_BLK0 = 6, 7, 8, 9, 10, 11, 16
+L_LU_LOWER, L_LU_UPPER, L_LU_DIAG, L_LU_BIAS, L_FEAT, L_HAS_LU, L_BC0, L_BLK0 = 6, 7, 8, 9, 10, 11, 12, 16
 
 
 class NsfModel(C.Structure):
@@ -31,6 +31,7 @@ class NsfModel(C.Structure):
         ("wcap", C.c_int32), ("nbuf", C.c_int32), ("n_params", C.c_int32),
         ("tail_bound", C.c_float), ("inv_sqrt_h", C.c_float), ("min_bw", C.c_float),
         ("min_bh", C.c_float), ("min_d", C.c_float), ("edge_raw", C.c_float),
+        ("head", C.c_int32), ("M", C.c_int32), ("mog_eps", C.c_float),
         ("ld_zscore", C.c_float),
         ("d_params", C.c_void_p), ("d_layer_tab", C.c_void_p), ("d_feat_tab", C.c_void_p),
         ("d_stats", C.c_void_p),
@@ -175,6 +176,7 @@ _EXPORTS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_fm_forward_div": (C.c_int, [C.POINTER(FmModel), C.POINTER(Rows), C.c_void_p, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "sbi_b200_made_sample": (C.c_int, [C.POINTER(NsfModel), C.POINTER(Rows), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sbi_b200_sde_em_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "sbi_b200_reject_scratch_ints": (C.c_int64, [C.c_int64]),

@@ -42,8 +42,9 @@ nsf_logprob_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constan
     return;
   }
 
-  const float ld_const = lu_logdet_total(m, sm + L.PRM) + m.ld_zscore -
-                         0.5f * (float)m.D * 1.8378770664093453f;
+  const bool mog = m.head == SBI_NSF_MOG;          // no base density: the mixture terms are the likelihood
+  const float ld_const = mog ? m.ld_zscore
+                             : lu_logdet_total(m, sm + L.PRM) + m.ld_zscore - 0.5f * (float)m.D * 1.8378770664093453f;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * TM;
     load_tile<TM>(m, rows, row0, sm, L, false);
@@ -61,7 +62,8 @@ nsf_logprob_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constan
     for (int r = threadIdx.x; r < TM; r += kConsumerThreads) {
       if (row0 + r < rows.R) {
         float ss = 0.f;
-        for (int d = 0; d < m.D; ++d) ss = fmaf(Z[d * LD + r], Z[d * LD + r], ss);
+        if (!mog)
+          for (int d = 0; d < m.D; ++d) ss = fmaf(Z[d * LD + r], Z[d * LD + r], ss);
         logp[row0 + r] = -0.5f * ss + sm[L.LDACC + r] + ld_const;
       }
     }
@@ -256,8 +258,9 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
 
   // ------------------------------------------------------------------ consumers
   const RqsConst rc = rqs_const(m);
-  const float ld_const = lu_logdet_total(m, sm + L.PRM) + m.ld_zscore -
-                         0.5f * (float)m.D * 1.8378770664093453f;
+  const bool mog = m.head == SBI_NSF_MOG;
+  const float ld_const = mog ? m.ld_zscore
+                             : lu_logdet_total(m, sm + L.PRM) + m.ld_zscore - 0.5f * (float)m.D * 1.8378770664093453f;
   float* gp = gpart + (size_t)blockIdx.x * m.n_params;
   float* Z = sm + L.Z;
   float* U = sm + L.U;
@@ -313,7 +316,8 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
         float g = 0.f;
         if (row0 + r < rows.R) {
           float ss = 0.f;
-          for (int d = 0; d < m.D; ++d) ss = fmaf(Z[d * LD + r], Z[d * LD + r], ss);
+          if (!mog)
+            for (int d = 0; d < m.D; ++d) ss = fmaf(Z[d * LD + r], Z[d * LD + r], ss);
           const float lp = -0.5f * ss + sm[L.LDACC + r] + ld_const;
           if (logp != nullptr) logp[row0 + r] = lp;
           g = gout ? __ldg(gout + row0 + r) : g_const;
@@ -334,7 +338,7 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
     // d(sum g logp)/dz_T = -g z_T
     for (int e = threadIdx.x; e < m.Dp * TM; e += kConsumerThreads) {
       const int d = e / TM, r = e % TM;
-      dZ[d * LD + r] = -GR[r] * Z[d * LD + r];
+      dZ[d * LD + r] = mog ? 0.f : -GR[r] * Z[d * LD + r];
     }
     if (need_dctx)
       for (int e = threadIdx.x; e < Cp * LD; e += kConsumerThreads) dCTX[e] = 0.f;
@@ -369,12 +373,23 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
         const int oWF = __ldg(v.LT + SBI_L_WF), oBF = __ldg(v.LT + SBI_L_BF);
         const int N = v.n_tr * m.PR;
         if (!spill) final_layer<kConsumer, TM, RN>(m, v, pipe, sm, L, hf);
-        for (int t = threadIdx.x; t < v.n_tr * TM; t += kConsumerThreads) {
-          const int f = t / TM, r = t % TM;
-          const int j = __ldg(v.trf + f);
-          const float gx = rqs_backward(PRM + f * m.PR * LD + r, LD, rc, ZSl[j * LD + r],
-                                        dZ[j * LD + r], GR[r], dPRM + f * m.PR * LD + r, LD);
-          dZ[j * LD + r] = gx;
+        if (mog) {
+          for (int t = threadIdx.x; t < v.n_tr * TM; t += kConsumerThreads) {
+            const int f = t / TM, r = t % TM;
+            const int j = __ldg(v.trf + f);
+            // the dummy feature has no likelihood term; dPRM of its rows stays zero
+            dZ[j * LD + r] = j == 0 ? 0.f
+                                    : mog_backward(PRM + f * m.PR * LD + r, LD, m.M, m.mog_eps, ZSl[j * LD + r], GR[r],
+                                                   dPRM + f * m.PR * LD + r, LD);
+          }
+        } else {
+          for (int t = threadIdx.x; t < v.n_tr * TM; t += kConsumerThreads) {
+            const int f = t / TM, r = t % TM;
+            const int j = __ldg(v.trf + f);
+            const float gx = rqs_backward(PRM + f * m.PR * LD + r, LD, rc, ZSl[j * LD + r],
+                                          dZ[j * LD + r], GR[r], dPRM + f * m.PR * LD + r, LD);
+            dZ[j * LD + r] = gx;
+          }
         }
         consumer_sync();
         gemm_dw<TM>(dPRM, N, hf, m.H, Hp, gp + oWF, gp + oBF, accum);
@@ -456,6 +471,14 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
       // initial layer
       gemm_dw<TM>(dH, m.H, U, Cp + v.n_id, K0p, gp + __ldg(v.LT + SBI_L_W0),
                   gp + __ldg(v.LT + SBI_L_B0), accum);
+      if (mog) {   // context_layer.bias enters the same sum as initial_layer.bias: same gradient
+        float* gbc = gp + __ldg(v.LT + SBI_L_BC0);
+        for (int n = threadIdx.x; n < m.H; n += kConsumerThreads) {
+          float a = 0.f;
+          for (int r = 0; r < TM; ++r) a += dH[n * LD + r];
+          gbc[n] = accum ? (gbc[n] + a) : a;
+        }
+      }
       dx_stage<kConsumer, TM, RK>(
           pipe, nullptr, Hp, K0p, m.rpc0, dH, K0p, [&](int k0, int r0, float(&acc)[RK][4], bool first) {
 #pragma unroll
@@ -497,6 +520,58 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
   }
 }
 
+// =================================================================================================
+// `made` sampling: D sequential passes of the masked conditioner (MixtureOfGaussiansMADE.sample,
+// oracle/nflows_port/nn/nde/made.py); feature f is drawn from its mixture given features < f.
+// =================================================================================================
+template <int TM, int RN>
+__global__ void __launch_bounds__(kThreads, 2)
+made_sample_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ sbi_rows rows,
+                   const float* __restrict__ uniform, float* __restrict__ out) {
+  constexpr int LD = Tile<TM>::LD;
+  extern __shared__ __align__(128) float sm[];
+  const NsfSmem L = nsf_smem_layout(m, TM, false);
+  WPipe pipe = make_pipe(m, sm, L);
+  const int64_t ntiles = (rows.R + TM - 1) / TM;
+  const NsfLayerView v = layer_view(m, 0);
+  if (threadIdx.x >= kConsumerThreads) {
+    if (threadIdx.x == kConsumerThreads)
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int f = 0; f < m.D; ++f) {
+          float* hf = cond_forward<kProducer, TM, RN, false>(m, v, pipe, sm, L);
+          final_layer<kProducer, TM, RN>(m, v, pipe, sm, L, hf);
+        }
+    return;
+  }
+  const float* __restrict__ st = m.d_stats;
+  float* Z = sm + L.Z;
+  float* NZ = sm + L.Y;       // the normal draws of the tile (Y / Y2 are free: no LU here)
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TM;
+    load_tile<TM>(m, rows, row0, sm, L, true);          // Z = normal draws (raw), U[0:C] = context
+    for (int e = threadIdx.x; e < m.Dp * LD; e += kConsumerThreads) { NZ[e] = Z[e]; Z[e] = 0.f; }
+    consumer_sync();
+    for (int f = 0; f < m.D; ++f) {
+      gather_identity<TM>(m, v, Z, sm + L.U);
+      float* hf = cond_forward<kConsumer, TM, RN, false>(m, v, pipe, sm, L);
+      final_layer<kConsumer, TM, RN>(m, v, pipe, sm, L, hf);
+      consumer_sync();
+      for (int r = threadIdx.x; r < TM; r += kConsumerThreads) {
+        const int64_t gr = row0 + r;
+        const float u = gr < rows.R ? __ldg(uniform + gr * m.D + f) : 0.f;
+        Z[f * LD + r] = mog_sample(sm + L.PRM + f * m.PR * LD + r, LD, m.M, m.mog_eps, u, NZ[f * LD + r]);
+      }
+      consumer_sync();
+    }
+    for (int e = threadIdx.x; e < TM * m.D; e += kConsumerThreads) {
+      const int r = e / m.D, d = e % m.D;
+      if (row0 + r < rows.R)
+        out[(row0 + r) * m.D + d] = (Z[d * LD + r] - __ldg(st + d)) / __ldg(st + m.Dp + d);
+    }
+    consumer_sync();
+  }
+}
+
 }  // namespace sbi
 
 // =================================================================================================
@@ -512,7 +587,10 @@ static int check_model(const sbi_nsf_model* m) {
   if (m->KB > kRqsMaxBins) return SBI_EINVAL;
   if (m->NB > SBI_NSF_MAX_BLOCKS) return SBI_EINVAL;
   if (m->Dp != round4(m->D) || m->Cp != round4(m->C) || m->Hp != round4(m->H)) return SBI_EINVAL;
-  if (m->PR != round4(3 * m->KB - 1) || (m->IDp & 3) || m->nf_chunk < 1) return SBI_EINVAL;
+  if (m->head != SBI_NSF_SPLINE && m->head != SBI_NSF_MOG) return SBI_EINVAL;
+  if (m->head == SBI_NSF_MOG && (m->M < 1 || m->M > kMogMax || m->T != 1 || !(m->mog_eps > 0.f))) return SBI_EINVAL;
+  if (m->PR != (m->head == SBI_NSF_MOG ? round4(3 * m->M) : round4(3 * m->KB - 1)) || (m->IDp & 3) || m->nf_chunk < 1)
+    return SBI_EINVAL;
   if ((m->rpc0 & 3) || (m->rpc1 & 3) || (m->rpc2 & 3) || m->rpc0 < 4 || m->rpc1 < 4 || m->rpc2 < 4)
     return SBI_EINVAL;
   if (m->nbuf < 2 || m->nbuf > 8) return SBI_EINVAL;
@@ -591,6 +669,25 @@ extern "C" int sbi_b200_nsf_logprob(const sbi_nsf_model* m, const sbi_rows* rows
   return (int)cudaGetLastError();
 }
 
+extern "C" int sbi_b200_made_sample(const sbi_nsf_model* m, const sbi_rows* rows, const float* d_uniform,
+                                    float* d_out, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (m->head != SBI_NSF_MOG) return SBI_EINVAL;
+  if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_uniform || !d_out) return SBI_EINVAL;
+  if (rows->R == 0) return 0;
+  constexpr int TM = 32;
+  const NsfSmem L = nsf_smem_layout(*m, TM, false);
+  auto k = made_sample_kernel<TM, 2>;
+  if ((rc = set_smem<8>(k, L.total_bytes))) return rc;
+  const int64_t ntiles = (rows->R + TM - 1) / TM;
+  const int per_sm = (L.total_bytes <= 110 * 1024) ? 2 : 1;
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * per_sm);
+  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *rows, d_uniform, d_out);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int sbi_b200_nsf_inverse(const sbi_nsf_model* m, const sbi_rows* rows, float* d_out,
                                     float* d_logabsdet, void* stream) {
   sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
@@ -665,6 +762,17 @@ extern "C" int sbi_b200_nsf_vjp(const sbi_nsf_model* m, const sbi_rows* rows, co
   constexpr int TM = 32;
   const NsfSmem L = nsf_smem_layout(*m, TM, true);
   const int grid = sbi_b200_nsf_vjp_parts(rows->R);
+  if (L.total_bytes > 227 * 1024) {
+    // deep conditioners (`made`: five residual blocks) keep too many intermediates for a 32-row tile:
+    // 16-row tiles, per-layer recompute; every CTA walks its tiles and accumulates into its slab
+    constexpr int TS = 16;
+    const NsfSmem Ls = nsf_smem_layout(*m, TS, true);
+    auto k = nsf_vjp_kernel<TS, 2, 2, false>;
+    if ((rc = set_smem<7>(k, Ls.total_bytes))) return rc;
+    k<<<grid, kThreads, Ls.total_bytes, s>>>(*m, *rows, d_gout, g_const, d_logp, d_gpart, d_ginput, d_gcond,
+                                             d_loss_acc, nullptr);
+    return (int)cudaGetLastError();
+  }
   const size_t slab = (size_t)((4 * m->NB + 1) * m->Hp + m->TRmax * m->PR) * (TM + 4);
   float* scratch = vjp_scratch(sizeof(float) * slab * m->T * (size_t)num_sms(), s);
   if (scratch != nullptr) {

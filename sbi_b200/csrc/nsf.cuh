@@ -13,6 +13,7 @@
 #pragma once
 #include "../../include/sbi_b200.h"
 #include "rqs.cuh"
+#include "mog.cuh"
 #include "stages.cuh"
 
 namespace sbi {
@@ -127,12 +128,14 @@ __device__ __forceinline__ float* cond_forward(const sbi_nsf_model& m, const Nsf
   float* Hout = SAVE ? sm + L.HS : sm + L.H;
   {
     const float* b0 = P + __ldg(v.LT + SBI_L_B0);
+    // MADE adds the context projection's own bias (initial_layer(x) + context_layer(ctx))
+    const float* bc0 = m.head == SBI_NSF_MOG ? P + __ldg(v.LT + SBI_L_BC0) : nullptr;
     fwd_stage<R, TM, RN>(pipe, P + __ldg(v.LT + SBI_L_W0), Hp, K0p, m.rpc0, U,
                          [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
 #pragma unroll
                            for (int i = 0; i < RN; ++i) {
                              const int n = n0 + g + i * ng;
-                             const float b = __ldg(b0 + n);
+                             const float b = __ldg(b0 + n) + (bc0 ? __ldg(bc0 + n) : 0.f);
                              const float4 h = make_float4(acc[i][0] + b, acc[i][1] + b,
                                                           acc[i][2] + b, acc[i][3] + b);
                              st4(Hout + n * LD + r0, h);
@@ -219,7 +222,18 @@ __device__ __forceinline__ void spline_forward(const sbi_nsf_model& m, const Nsf
                                                const float* Hfin) {
   constexpr int LD = Tile<TM>::LD;
   final_layer<R, TM, RN>(m, v, pipe, sm, L, Hfin);
-  if (R == kConsumer) {
+  if (R == kConsumer && m.head == SBI_NSF_MOG) {
+    // mixture-of-Gaussians likelihood of every feature (feature 0 is the wrapper's dummy: no term)
+    const float* PRM = sm + L.PRM;
+    const float* Z = sm + L.Z;
+    float* LDF = sm + L.LDF;
+    for (int t = threadIdx.x; t < v.n_tr * TM; t += kConsumerThreads) {
+      const int f = t / TM, r = t % TM;
+      const int j = __ldg(v.trf + f);
+      LDF[f * LD + r] = j == 0 ? 0.f : mog_log_prob(PRM + f * m.PR * LD + r, LD, m.M, m.mog_eps, Z[j * LD + r]);
+    }
+    consumer_sync();
+  } else if (R == kConsumer) {
     const RqsConst rc = rqs_const(m);
     const float* PRM = sm + L.PRM;
     float* Z = sm + L.Z;

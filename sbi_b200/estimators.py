@@ -25,16 +25,19 @@ from .pack import MafLayout, NsfLayout
 class _Family:
     """C-ABI entry points + model struct of one flow family (include/sbi_b200.h)."""
 
-    def __init__(self, name, struct, tab_fields):
+    def __init__(self, name, struct, tab_fields, c_prefix=None):
         self.name, self.struct, self.tab_fields = name, struct, tab_fields
+        self.c_prefix = c_prefix or name
 
     def fn(self, what):
-        return getattr(L.load(), f"sbi_b200_{self.name}_{what}")
+        return getattr(L.load(), f"sbi_b200_{self.c_prefix}_{what}")
 
 
 FAMILIES = {
     "nsf": _Family("nsf", L.NsfModel, ("d_layer_tab", "d_feat_tab")),
     "maf": _Family("maf", L.MafModel, ("d_layer_tab", "d_perm_tab")),
+    # `made`: the masked residual conditioner + mixture head run on the NSF kernels (head = SBI_NSF_MOG)
+    "made": _Family("made", L.NsfModel, ("d_layer_tab", "d_feat_tab"), c_prefix="nsf"),
 }
 
 
@@ -551,3 +554,92 @@ class _NsfLogProb(torch.autograd.Function):
 
 NSFEstimator = FlowEstimator
 MAFEstimator = FlowEstimator
+
+
+class MadeEstimator(FlowEstimator):
+    r"""sbi's `made` density estimator (flow.py:37-112): z-scoring followed by a conditional MADE with a
+    mixture-of-Gaussians head (nflows MADEMoG behind sbi's MADEMoGWrapper, nn_utils.py:133-201), evaluated by
+    the NSF kernels with head = SBI_NSF_MOG.  The wrapper's dummy first feature is part of the network: the
+    kernels see `input dim + 1` features, feature 0 is fed 0 by `log_prob` and -- like the reference's
+    `_sample` -- drawn from its own mixture in `sample` and dropped from the result."""
+
+    def _kernel_stats(self, raw_condition: bool = False):
+        lay, net = self.layout, self.net
+        emb = net._embedding_net
+        std_mod = emb[0] if isinstance(emb, nn.Sequential) and isinstance(emb[0], Standardize) else None
+        srcs = [net._shift, net._scale] + ([std_mod._mean, std_mod._std] if std_mod is not None else [])
+        key = tuple((t.data_ptr(), t._version) for t in srcs) + (str(net.flat.device), raw_condition)
+        ck = "stats_raw" if raw_condition else "stats"
+        hit = self._cache.get(ck)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        dev = net.flat.device
+        Din = lay.D - 1
+        st = torch.zeros(2 * lay.Dp + 2 * lay.Cp, dtype=torch.float32, device=dev)
+        st[lay.Dp:2 * lay.Dp] = 1.0
+        st[2 * lay.Dp + lay.Cp:] = 1.0
+        st[1:lay.D] = net._shift.expand(Din)                      # feature 0 (dummy): shift 0, scale 1
+        st[lay.Dp + 1:lay.Dp + lay.D] = net._scale.expand(Din)
+        if std_mod is not None and self._embed_identity and not raw_condition:
+            st[2 * lay.Dp:2 * lay.Dp + lay.C] = std_mod._mean.reshape(-1).expand(lay.C)
+            st[2 * lay.Dp + lay.Cp:2 * lay.Dp + lay.Cp + lay.C] = std_mod._std.reshape(-1).expand(lay.C)
+        ld = float(torch.log(torch.abs(net._scale.double())).expand(Din).sum())
+        self._cache[ck] = (key, st, ld)
+        return st, ld
+
+    @staticmethod
+    def with_dummy(inp: Tensor) -> Tensor:
+        """(R, D) -> (R, D + 1) with the wrapper's zero first feature (nn_utils.py:166-167)."""
+        return torch.cat([torch.zeros(inp.shape[0], 1, dtype=inp.dtype, device=inp.device), inp], dim=1)
+
+    def log_prob(self, input: Tensor, condition: Tensor) -> Tensor:
+        self._check_input_shape(input)
+        self._check_condition_shape(condition)
+        if not self.net.flat.is_cuda:
+            from ._refabc import hop_to_device
+            return hop_to_device(self, "log_prob", input, condition)
+        inp, cond, shared, S, B = self._align(input, condition)
+        ctx = self._embed(cond)
+        lp = _NsfLogProb.apply(self.net.flat, self.with_dummy(inp.float()).contiguous(), ctx.contiguous().float(),
+                               self, shared)
+        return lp.reshape(S, B)
+
+    def inverse_transform(self, input: Tensor, condition: Tensor) -> Tensor:
+        """The flow's transform is the z-scoring alone (CompositeTransform([standardize, identity]))."""
+        return input * self.net._scale + self.net._shift
+
+    @torch.no_grad()
+    def sample(self, sample_shape, condition: Tensor) -> Tensor:
+        """(*sample_shape, batch_dim, *input_shape): D + 1 sequential conditioner passes in one kernel
+        (csrc/nsf.cu `made_sample_kernel`); the normal draws and the component-selecting uniforms come from
+        torch on the parameter device, condition-major like nflows (`repeat_interleave(context, n)`)."""
+        self._check_condition_shape(condition)
+        lib = L.load()
+        dev = self.net.flat.device
+        Bc = condition.shape[0]
+        n = torch.Size(sample_shape).numel()
+        Dn = self.layout.D
+        R = Bc * n
+        noise = torch.randn(R, Dn, device=dev)
+        unif = torch.rand(R, Dn, device=dev)
+        ctx = self._embed(condition.to(dev)).contiguous().float()
+        shared = Bc == 1
+        if not shared:
+            ctx = ctx.repeat_interleave(n, dim=0).contiguous()
+        out = torch.empty(R, Dn, dtype=torch.float32, device=dev)
+        m = self._model(nbuf=2)
+        rows = L.Rows(noise.data_ptr(), ctx.data_ptr(), None, R, 1 if shared else 0)
+        L.check(lib.sbi_b200_made_sample(C.byref(m), C.byref(rows), unif.data_ptr(), out.data_ptr(), L.stream_ptr()),
+                "made_sample")
+        x = out[:, 1:].reshape(Bc, n, Dn - 1).transpose(0, 1)
+        return x.reshape((*sample_shape, Bc, *self.input_shape))
+
+    @torch.no_grad()
+    def sample_and_log_prob(self, sample_shape, condition: Tensor, **kwargs):
+        samples = self.sample(sample_shape, condition)
+        n = torch.Size(sample_shape).numel()
+        flat = samples.reshape(n, condition.shape[0], -1)
+        return samples, self.log_prob(flat, condition).reshape((*sample_shape, -1))
+
+    def inverse_flow(self, noise: Tensor, condition: Tensor, reps: int = 1):
+        raise NotImplementedError("`made` is a conditional distribution, not an invertible flow of base noise")

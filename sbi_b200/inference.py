@@ -281,6 +281,8 @@ class _FlowTrainer:
             self._epochs_since_last_improvement = 0
 
         inp_all, cond_all = self._inp_cond()
+        if hasattr(net, "with_dummy"):     # `made`: the network's dummy first feature (nn_utils.py:166-167)
+            inp_all = net.with_dummy(inp_all).contiguous()
         train_idx = self.train_indices.to(dev)
         val_idx = self.val_indices.to(dev)
         # static buffers the epoch graph reads

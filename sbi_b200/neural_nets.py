@@ -17,8 +17,8 @@ import torch
 from torch import Tensor, nn
 from torch.nn import init
 
-from .estimators import FlowEstimator, NSFEstimator
-from .pack import MafLayout, NsfLayout
+from .estimators import FlowEstimator, MadeEstimator, NSFEstimator
+from .pack import MadeLayout, MafLayout, NsfLayout
 
 _NSF_MODELS = ("nsf",)
 
@@ -266,7 +266,61 @@ def build_maf_rqs(
     return est
 
 
-_BUILDERS = {"nsf": build_nsf, "maf": build_maf, "maf_rqs": build_maf_rqs}
+def build_made(
+    batch_x: Tensor, batch_y: Tensor, z_score_x="independent", z_score_y="independent",
+    hidden_features: int = 50, num_mixture_components: int = 10, embedding_net: nn.Module = nn.Identity(),
+    **kwargs,
+) -> MadeEstimator:
+    """Builds MADE p(x|y); same arguments as the reference (flow.py:37-112): z-scoring + MADEMoGWrapper(
+    features, hidden, context, num_blocks=5, num_mixture_components, use_residual_blocks=True, relu,
+    custom_initialization=True).  Modules are initialised in nflows' construction order (MADE: initial masked
+    layer, context layer, per block context layer + two masked linears with the last re-drawn U(-1e-3, 1e-3),
+    final masked layer; then MixtureOfGaussiansMADE._initialize), so a seed yields the reference's weights."""
+    check_data_device(batch_x, batch_y)
+    if z_score_x == "transform_to_unconstrained":
+        raise ValueError("`transform_to_unconstrained` is not supported by build_made.")
+    x_numel = batch_x[0].numel()
+    with torch.no_grad():
+        y_numel = embedding_net(batch_y[:1]).numel()
+    zx, sx = z_score_parser(z_score_x)
+    zy, sy = z_score_parser(z_score_y)
+    H, C, F, M, NB = hidden_features, y_numel, x_numel + 1, num_mixture_components, 5
+    eps = 1e-2
+    lay = MadeLayout(D=F, C=C, H=H, NB=NB, M=M, epsilon=eps, zscore_input=zx, zscore_cond=zy,
+                     embed_is_identity=isinstance(embedding_net, nn.Identity))
+    pm = "net._distribution._made."
+    st = {}
+    st[pm + "initial_layer.weight"], st[pm + "initial_layer.bias"] = _linear_init(H, F)
+    st[pm + "context_layer.weight"], st[pm + "context_layer.bias"] = _linear_init(H, C)
+    for b in range(NB):
+        pb = pm + f"blocks.{b}."
+        st[pb + "context_layer.weight"], st[pb + "context_layer.bias"] = _linear_init(H, C)
+        st[pb + "linear_layers.0.weight"], st[pb + "linear_layers.0.bias"] = _linear_init(H, H)
+        w, bb = _linear_init(H, H)
+        init.uniform_(w, -1e-3, 1e-3)
+        init.uniform_(bb, -1e-3, 1e-3)
+        st[pb + "linear_layers.1.weight"], st[pb + "linear_layers.1.bias"] = w, bb
+    wf, bf = _linear_init(3 * M * F, H)
+    wf, bf = wf.clone(), bf.clone()
+    wf[::3, :] = eps * torch.randn(F * M, H)
+    bf[::3] = eps * torch.randn(F * M)
+    wf[2::3] = eps * torch.randn(F * M, H)
+    bf[2::3] = torch.log(torch.exp(torch.Tensor([1 - eps])) - 1) * torch.ones(F * M) + eps * torch.randn(F * M)
+    st[pm + "final_layer.weight"], st[pm + "final_layer.bias"] = wf, bf
+    if zx:
+        t_mean, t_std = z_standardization(batch_x.reshape(batch_x.shape[0], -1), sx)
+        shift, scale = -t_mean / t_std, 1 / t_std
+    else:
+        shift, scale = torch.zeros(()), torch.ones(())
+    c_mean, c_std = standardizing_stats(batch_y, sy) if zy else (None, None)
+    est = MadeEstimator(lay, input_shape=batch_x[0].shape, condition_shape=batch_y[0].shape,
+                        shift=shift, scale=scale, cond_mean=c_mean, cond_std=c_std, embedding_net=embedding_net)
+    with torch.no_grad():
+        lay.pack(st, out=est.net.flat.data, raw_out=est.net._raw)
+    return est
+
+
+_BUILDERS = {"nsf": build_nsf, "maf": build_maf, "maf_rqs": build_maf_rqs, "made": build_made}
 
 
 def _density_build_fn(model: str, input_is_theta: bool, **kw) -> Callable:

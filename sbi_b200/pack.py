@@ -381,10 +381,151 @@ class NsfLayout(_LayoutOps):
         s.inv_sqrt_h = 1.0 / math.sqrt(self.H)
         s.min_bw = s.min_bh = s.min_d = 1e-3
         s.edge_raw = self.edge_raw
+        s.head, s.M, s.mog_eps = 0, 0, 0.0
         return s
 
 
 NsfLayout.family = "nsf"
+
+
+@dataclass
+class MadeLayout(_LayoutOps):
+    """Packed layout of sbi's `made` density estimator (flow.py:37-112): ONE masked residual network
+    (nflows MixtureOfGaussiansMADE behind sbi's MADEMoGWrapper, nn_utils.py:133-201: `features + 1`
+    inputs with a dummy first feature) emitting, per feature, num_mixture_components x (logit, mean,
+    unconstrained std).  The network is structurally the NSF conditioner (initial linear on
+    [context | inputs], residual blocks with GLU context gates, final linear), so it runs on the NSF
+    kernels (include/sbi_b200.h `sbi_nsf_model` with head = SBI_NSF_MOG): masks are folded into the
+    packed weights, every feature is both a conditioner input and an output, T = 1, no LU.
+    `D` here is the NETWORK's feature count (the estimator's input dim + 1)."""
+    D: int
+    C: int
+    H: int = 50
+    NB: int = 5
+    M: int = 10
+    epsilon: float = 1e-2
+    zscore_input: bool = True
+    zscore_cond: bool = True
+    embed_is_identity: bool = True
+    wcap_target: int = 4096
+    n_params: int = 0
+    index: Dict[str, np.ndarray] = field(default_factory=dict, repr=False)
+
+    def __post_init__(self):
+        D, C, H, NB, M = self.D, self.C, self.H, self.NB, self.M
+        if NB > L.SBI_NSF_MAX_BLOCKS:
+            raise ValueError(f"num_blocks <= {L.SBI_NSF_MAX_BLOCKS}")
+        if not (1 <= M <= 16):
+            raise ValueError("the mixture code keeps <= 16 components in registers")
+        self.T, self.KB = 1, 0
+        self.Dp, self.Cp, self.Hp = round4(D), round4(C), round4(H)
+        self.NPAR = 3 * M
+        self.PR = round4(self.NPAR)
+        self.IDp = round4(D)
+        self.TRmax = D
+        self.K0p = self.Cp + self.IDp
+        Hp, Cp = self.Hp, self.Cp
+        cap = max(self.wcap_target, 4 * self.K0p, 4 * (Hp + Cp), self.PR * Hp)
+
+        def rows(rowlen):
+            return max(4, min(Hp, (cap // rowlen) & ~3))
+
+        self.rpc0, self.rpc1, self.rpc2 = rows(self.K0p), rows(Hp), rows(Hp + Cp)
+        self.nf_chunk = max(1, min(self.TRmax, cap // (self.PR * Hp)))
+        used = max(self.rpc0 * self.K0p, self.rpc1 * Hp, self.rpc2 * (Hp + Cp), self.nf_chunk * self.PR * Hp)
+        self.wcap = (used + 31) & ~31
+
+        # MADE degrees / masks (nflows transforms/made.py, sequential degrees; residual blocks)
+        in_deg = np.arange(1, D + 1)
+        max_, min_ = max(1, D - 1), min(1, D - 1)
+        hid_deg = np.arange(H) % max_ + min_
+        m_init = (hid_deg[:, None] >= in_deg[None, :]).astype(np.float32)      # (H, D)
+        m_hid = (hid_deg[:, None] >= hid_deg[None, :]).astype(np.float32)      # (H, H)
+        out_deg = np.repeat(in_deg, 3 * M)
+        m_out = (out_deg[:, None] > hid_deg[None, :]).astype(np.float32)       # (3M*D, H)
+
+        off = 0
+
+        def take(n):
+            nonlocal off
+            o = off
+            off += round4(n)
+            return o
+
+        tab = np.zeros((1, L.SBI_NSF_LAYER_STRIDE), np.int32)
+        idx: Dict[str, np.ndarray] = {}
+        wm: Dict[str, np.ndarray] = {}
+        self.buffers: Dict[str, torch.Tensor] = {}
+        pm = "net._distribution._made."
+        feats = list(range(D))
+        tab[0, L.L_NID], tab[0, L.L_NTR], tab[0, L.L_FEAT] = D, D, 0
+        # initial layer: packed columns [ctx | pad | inputs | pad]; MADE's context_layer supplies the ctx columns
+        o = take(Hp * self.K0p)
+        tab[0, L.L_W0] = o
+        idx[pm + "initial_layer.weight"] = o + np.arange(H)[:, None] * self.K0p + (Cp + np.arange(D))[None, :]
+        wm[pm + "initial_layer.weight"] = m_init
+        self.buffers[pm + "initial_layer.mask"] = torch.as_tensor(m_init)
+        self.buffers[pm + "initial_layer.degrees"] = torch.as_tensor(hid_deg)
+        idx[pm + "context_layer.weight"] = o + np.arange(H)[:, None] * self.K0p + np.arange(C)[None, :]
+        o = take(Hp)
+        tab[0, L.L_B0] = o
+        idx[pm + "initial_layer.bias"] = o + np.arange(H)
+        o = take(Hp)
+        tab[0, L.L_BC0] = o
+        idx[pm + "context_layer.bias"] = o + np.arange(H)
+        for b in range(NB):
+            pb = pm + f"blocks.{b}."
+            t = L.L_BLK0 + 6 * b
+            for slot, (name, K, Kp, masked) in enumerate(
+                    [("linear_layers.0", H, Hp, True), ("linear_layers.1", H, Hp, True),
+                     ("context_layer", C, Cp, False)]):
+                o = take(Hp * Kp)
+                tab[0, t + 2 * slot] = o
+                idx[pb + name + ".weight"] = o + np.arange(H)[:, None] * Kp + np.arange(K)[None, :]
+                if masked:
+                    wm[pb + name + ".weight"] = m_hid
+                    self.buffers[pb + name + ".mask"] = torch.as_tensor(m_hid)
+                    self.buffers[pb + name + ".degrees"] = torch.as_tensor(hid_deg)
+                o = take(Hp)
+                tab[0, t + 2 * slot + 1] = o
+                idx[pb + name + ".bias"] = o + np.arange(H)
+        # final layer: feature f owns packed rows f*PR .. f*PR + 3M - 1 (nflows row f*3M + 3m + k)
+        o = take(D * self.PR * Hp)
+        tab[0, L.L_WF] = o
+        prow = (np.arange(D)[:, None] * self.PR + np.arange(self.NPAR)[None, :]).reshape(-1)
+        idx[pm + "final_layer.weight"] = o + prow[:, None] * Hp + np.arange(H)[None, :]
+        wm[pm + "final_layer.weight"] = m_out
+        self.buffers[pm + "final_layer.mask"] = torch.as_tensor(m_out)
+        self.buffers[pm + "final_layer.degrees"] = torch.as_tensor(out_deg)
+        o = take(D * self.PR)
+        tab[0, L.L_BF] = o
+        idx[pm + "final_layer.bias"] = o + prow
+        tab[0, L.L_HAS_LU] = 0
+        self.n_params = off
+        self.index = idx
+        self._weight_masks = wm
+        self.layer_tab = tab
+        self.feat_tab = np.asarray(feats + feats, np.int32)
+
+    def tables(self):
+        return self.layer_tab.reshape(-1).astype(np.int32), self.feat_tab.astype(np.int32)
+
+    def tc_plan(self):
+        return None
+
+    def fill_struct(self, s: "L.NsfModel", nbuf: int):
+        s.D, s.C, s.H, s.NB, s.KB, s.T = self.D, self.C, self.H, self.NB, 2, 1
+        s.Dp, s.Cp, s.IDp, s.Hp, s.PR = self.Dp, self.Cp, self.IDp, self.Hp, self.PR
+        s.TRmax, s.nf_chunk = self.TRmax, self.nf_chunk
+        s.rpc0, s.rpc1, s.rpc2 = self.rpc0, self.rpc1, self.rpc2
+        s.wcap, s.nbuf, s.n_params = self.wcap, nbuf, self.n_params
+        s.tail_bound, s.inv_sqrt_h, s.edge_raw = 1.0, 1.0, 0.0
+        s.min_bw = s.min_bh = s.min_d = 1e-3
+        s.head, s.M, s.mog_eps = 1, self.M, self.epsilon
+        return s
+
+
+MadeLayout.family = "made"
 
 
 @dataclass

@@ -13,6 +13,8 @@ Fixtures (small, committed):
   maf_d3c2.pt     reference `posterior_nn("maf")` (theta-dim 3, x-dim 2; BASELINE configs[0]): state_dict,
                   permutations, log_prob and inverse outputs.
   maf_rqs_d4c3.pt reference `posterior_nn("maf_rqs")` (theta-dim 4, x-dim 3): same contents as maf_d3c2.pt.
+  made_d3c2.pt    reference `posterior_nn("made")` (theta-dim 3, x-dim 2): state_dict, log_prob values, and
+                  moments / quantiles of 20 000 reference samples at one condition.
   searchsorted.pt the reference's bin-search known-answer test vectors (tests/torchutils_test.py:135-157).
   ratio_d4x6.pt   reference `classifier_nn("resnet")` (theta-dim 4, x-dim 6): state_dict, pairs, logits.
   fm_d5c3.pt      reference `posterior_flow_nn("mlp")` (theta-dim 5, x-dim 3): state_dict, inputs, times,
@@ -74,6 +76,28 @@ def maf_fixture(D, C, seed, n=400, model="maf"):
         samples, lad = est.net._transform.inverse(noise, context=emb)
     return dict(state_dict=est.state_dict(), theta=theta, x=x, inp=inp, cond=cond, noise=noise,
                 log_prob=lp, samples=samples, inverse_logabsdet=lad, D=D, C=C, seed=seed)
+
+
+def made_fixture(D, C, seed, n=400):
+    """reference `posterior_nn("made")`: log_prob at given inputs; `sample` is RNG-bound (Categorical draws),
+    so only moments of a large reference sample are stored."""
+    g = torch.Generator().manual_seed(seed)
+    theta = 0.7 * torch.randn(n, D, generator=g) + 0.3
+    x = 1.3 * torch.randn(n, C, generator=g) - 0.2
+    torch.manual_seed(seed)
+    est = posterior_nn("made")(theta, x)
+    with torch.no_grad():
+        for name, p in est.named_parameters():
+            p.add_(0.1 * torch.randn(p.shape, generator=g))
+    inp, cond = theta[:64] * 1.5, x[:64]
+    with torch.no_grad():
+        lp = est.log_prob(inp, cond)[0]
+        lp_shared = est.log_prob(inp.unsqueeze(1), cond[:1])[:, 0]
+        torch.manual_seed(seed + 1)
+        s = est.sample((20000,), cond[:1])[:, 0]
+    return dict(state_dict=est.state_dict(), theta=theta, x=x, inp=inp, cond=cond, log_prob=lp,
+                log_prob_shared=lp_shared, sample_mean=s.mean(0), sample_std=s.std(0),
+                sample_q=torch.quantile(s, torch.tensor([0.1, 0.5, 0.9]), dim=0), D=D, C=C, seed=seed)
 
 
 def train_fixture():
@@ -148,6 +172,8 @@ if __name__ == "__main__":
     torch.save(flow_fixture(3, 2, 8), os.path.join(HERE, "nsf_d3c2.pt"))
     torch.save(train_fixture(), os.path.join(HERE, "npe_train.pt"))
     torch.save(maf_fixture(3, 2, 9), os.path.join(HERE, "maf_d3c2.pt"))
+    if "--new" in sys.argv or not os.path.exists(os.path.join(HERE, "made_d3c2.pt")):
+        torch.save(made_fixture(3, 2, 15), os.path.join(HERE, "made_d3c2.pt"))
     if "--new" in sys.argv or not os.path.exists(os.path.join(HERE, "maf_rqs_d4c3.pt")):
         torch.save(maf_fixture(4, 3, 14, model="maf_rqs"), os.path.join(HERE, "maf_rqs_d4c3.pt"))
     torch.save(searchsorted_fixture(), os.path.join(HERE, "searchsorted.pt"))
