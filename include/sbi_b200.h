@@ -73,6 +73,9 @@ typedef struct {
   int32_t n_params;                /* floats in d_params */
   float tail_bound, inv_sqrt_h, min_bw, min_bh, min_d, edge_raw;
   int32_t head, M;                 /* SBI_NSF_SPLINE / SBI_NSF_MOG; mixture components (PR = round4(3M)) */
+  int32_t cond_mlp;                /* 1: the conditioner is the context-only MLP of the 1-D flow (flow.py:401-408,
+                                    * ContextSplineMap :1419-1478): relu(W0 ctx + b0), then NB applications of ONE
+                                    * shared hidden layer (W at SBI_L_BLK0, bias at +1) with relu, then the final layer */
   float mog_eps;                   /* std = softplus(.) + mog_eps */
   float ld_zscore;                 /* sum_d log|scale_d| of the input z-score transform */
   const float* d_params;           /* packed parameters (see sbi_b200/pack.py) */

@@ -31,7 +31,7 @@ class NsfModel(C.Structure):
         ("wcap", C.c_int32), ("nbuf", C.c_int32), ("n_params", C.c_int32),
         ("tail_bound", C.c_float), ("inv_sqrt_h", C.c_float), ("min_bw", C.c_float),
         ("min_bh", C.c_float), ("min_d", C.c_float), ("edge_raw", C.c_float),
-        ("head", C.c_int32), ("M", C.c_int32), ("mog_eps", C.c_float),
+        ("head", C.c_int32), ("M", C.c_int32), ("cond_mlp", C.c_int32), ("mog_eps", C.c_float),
         ("ld_zscore", C.c_float),
         ("d_params", C.c_void_p), ("d_layer_tab", C.c_void_p), ("d_feat_tab", C.c_void_p),
         ("d_stats", C.c_void_p),

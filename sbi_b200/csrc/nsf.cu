@@ -241,6 +241,10 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
           auto noop2 = [](int, int, float(&)[RK][4], bool) {};
           dx_stage<kProducer, TM, RK>(pipe, P + __ldg(v.LT + SBI_L_WF), v.n_tr * m.PR, Hp,
                                       m.nf_chunk * m.PR, nullptr, Hp, noop2);
+          if (m.cond_mlp) {
+            for (int k = m.NB; k >= 1; --k)
+              dx_stage<kProducer, TM, RK>(pipe, P + __ldg(v.LT + SBI_L_BLK0), Hp, Hp, m.rpc1, nullptr, Hp, noop2);
+          } else
           for (int b = m.NB - 1; b >= 0; --b) {
             const int* BT = v.LT + SBI_L_BLK0 + 6 * b;
             dx_stage<kProducer, TM, RK>(pipe, P + __ldg(BT + 2), Hp, Hp, m.rpc1, nullptr, Hp, noop2);
@@ -408,6 +412,41 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
               }
             });
       }
+      if (m.cond_mlp) {
+        // context-only MLP (1-D flow): dH = grad wrt the last relu output HS[NB]; the hidden layer is shared,
+        // so its weight gradient accumulates over its NB applications; ends with dH = grad wrt the
+        // pre-activation of the initial layer, which the common code below turns into dW0 / dU
+        const int oWh = __ldg(v.LT + SBI_L_BLK0), oBh = __ldg(v.LT + SBI_L_BLK0 + 1);
+        for (int k = m.NB; k >= 1; --k) {
+          const float* Hk = sm + L.HS + k * Hp * LD;
+          const float* Hkm1 = sm + L.HS + (k - 1) * Hp * LD;
+          for (int e = threadIdx.x; e < Hp * TM; e += kConsumerThreads) {
+            const int o = (e / TM) * LD + (e % TM);
+            dT[o] = Hk[o] > 0.f ? dH[o] : 0.f;
+          }
+          consumer_sync();
+          gemm_dw<TM>(dT, m.H, Hkm1, m.H, Hp, gp + oWh, gp + oBh, accum || k < m.NB);
+          dx_stage<kConsumer, TM, RK>(
+              pipe, nullptr, Hp, Hp, m.rpc1, dT, Hp, [&](int k0, int r0, float(&acc)[RK][4], bool first) {
+#pragma unroll
+                for (int j = 0; j < RK; ++j) {
+                  float* p = dH + (k0 + j) * LD + r0;
+                  float4 o4 = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                  if (!first) {
+                    const float4 c = ld4(p);
+                    o4.x += c.x; o4.y += c.y; o4.z += c.z; o4.w += c.w;
+                  }
+                  st4(p, o4);
+                }
+              });
+        }
+        const float* H0 = sm + L.HS;
+        for (int e = threadIdx.x; e < Hp * TM; e += kConsumerThreads) {
+          const int o = (e / TM) * LD + (e % TM);
+          dH[o] = H0[o] > 0.f ? dH[o] : 0.f;
+        }
+        consumer_sync();
+      } else
       // residual blocks, last to first.  dH = grad wrt HS[b+1]
       for (int b = m.NB - 1; b >= 0; --b) {
         const int* BT = v.LT + SBI_L_BLK0 + 6 * b;
@@ -588,6 +627,7 @@ static int check_model(const sbi_nsf_model* m) {
   if (m->NB > SBI_NSF_MAX_BLOCKS) return SBI_EINVAL;
   if (m->Dp != round4(m->D) || m->Cp != round4(m->C) || m->Hp != round4(m->H)) return SBI_EINVAL;
   if (m->head != SBI_NSF_SPLINE && m->head != SBI_NSF_MOG) return SBI_EINVAL;
+  if (m->cond_mlp && (m->head != SBI_NSF_SPLINE || m->TRmax * m->PR > m->Hp)) return SBI_EINVAL;
   if (m->head == SBI_NSF_MOG && (m->M < 1 || m->M > kMogMax || m->T != 1 || !(m->mog_eps > 0.f))) return SBI_EINVAL;
   if (m->PR != (m->head == SBI_NSF_MOG ? round4(3 * m->M) : round4(3 * m->KB - 1)) || (m->IDp & 3) || m->nf_chunk < 1)
     return SBI_EINVAL;

@@ -114,6 +114,48 @@ __device__ __forceinline__ void gather_identity(const sbi_nsf_model& m, const Ns
   consumer_sync();
 }
 
+// Context-only MLP conditioner of the 1-D flow (sbi's ContextSplineMap, flow.py:1419-1478): Linear -> ReLU ->
+// NB x [the SAME Linear -> ReLU] ; the final Linear is `final_layer`.  SAVE keeps every layer output
+// (HS[0..NB]) for the backward; otherwise two buffers alternate so that the last output lands in L.H.
+template <Role R, int TM, int RN, bool SAVE>
+__device__ __forceinline__ float* mlp_forward(const sbi_nsf_model& m, const NsfLayerView& v, WPipe& pipe, float* sm,
+                                              const NsfSmem& L) {
+  constexpr int LD = Tile<TM>::LD;
+  const float* __restrict__ P = m.d_params;
+  const int Hp = m.Hp, K0p = m.Cp + m.IDp;
+  auto buf = [&](int k) { return SAVE ? sm + L.HS + k * Hp * LD : (((m.NB - k) & 1) ? sm + L.A1 : sm + L.H); };
+  float* Hout = buf(0);
+  {
+    const float* b0 = P + __ldg(v.LT + SBI_L_B0);
+    fwd_stage<R, TM, RN>(pipe, P + __ldg(v.LT + SBI_L_W0), Hp, K0p, m.rpc0, sm + L.U,
+                         [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
+#pragma unroll
+                           for (int i = 0; i < RN; ++i) {
+                             const int n = n0 + g + i * ng;
+                             const float b = __ldg(b0 + n);
+                             st4(Hout + n * LD + r0, make_float4(relu_f(acc[i][0] + b), relu_f(acc[i][1] + b),
+                                                                 relu_f(acc[i][2] + b), relu_f(acc[i][3] + b)));
+                           }
+                         });
+  }
+  const float* bh = P + __ldg(v.LT + SBI_L_BLK0 + 1);
+  for (int k = 1; k <= m.NB; ++k) {
+    const float* Hin = Hout;
+    Hout = buf(k);
+    fwd_stage<R, TM, RN>(pipe, P + __ldg(v.LT + SBI_L_BLK0), Hp, Hp, m.rpc1, Hin,
+                         [&](int n0, int g, int ng, int r0, float(&acc)[RN][4]) {
+#pragma unroll
+                           for (int i = 0; i < RN; ++i) {
+                             const int n = n0 + g + i * ng;
+                             const float b = __ldg(bh + n);
+                             st4(Hout + n * LD + r0, make_float4(relu_f(acc[i][0] + b), relu_f(acc[i][1] + b),
+                                                                 relu_f(acc[i][2] + b), relu_f(acc[i][3] + b)));
+                           }
+                         });
+  }
+  return Hout;
+}
+
 // ResidualNet conditioner up to the last hidden state (restating nflows ResidualNet,
 // oracle/nflows_port/nn/nets/resnet.py).  SAVE keeps every intermediate for the backward.
 // Returns the buffer holding the final hidden state.
@@ -121,6 +163,7 @@ template <Role R, int TM, int RN, bool SAVE>
 __device__ __forceinline__ float* cond_forward(const sbi_nsf_model& m, const NsfLayerView& v,
                                                WPipe& pipe, float* sm, const NsfSmem& L) {
   constexpr int LD = Tile<TM>::LD;
+  if (m.cond_mlp) return mlp_forward<R, TM, RN, SAVE>(m, v, pipe, sm, L);
   const float* __restrict__ P = m.d_params;
   const int Hp = m.Hp, Cp = m.Cp, K0p = m.Cp + m.IDp;
   float* U = sm + L.U;

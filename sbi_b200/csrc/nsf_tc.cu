@@ -623,7 +623,7 @@ static int tc_plan_slots(const sbi_nsf_model* m, const sbi_nsf_tc* tc) {
 extern "C" int sbi_b200_nsf_tc_supported(const sbi_nsf_model* m, const sbi_nsf_tc* tc) {
   sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
   if (!m || !tc) return 0;
-  if (m->head != SBI_NSF_SPLINE) return 0;        // the tensor-core kernels implement the spline coupling flow
+  if (m->head != SBI_NSF_SPLINE || m->cond_mlp) return 0;   // spline coupling flow with the ResidualNet conditioner
   if (m->H != 50 || m->KB != 10) return 0;        // instantiated hidden width / bin count
   if (m->H + m->C > 64) return 0;                 // context rides in the hidden operand's K range
   if (m->IDp > 48 || m->PR > 32 || m->D > tc::kLuMax) return 0;

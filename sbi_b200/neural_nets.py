@@ -18,7 +18,7 @@ from torch import Tensor, nn
 from torch.nn import init
 
 from .estimators import FlowEstimator, MadeEstimator, NSFEstimator
-from .pack import MadeLayout, MafLayout, NsfLayout
+from .pack import MadeLayout, MafLayout, Nsf1dLayout, NsfLayout
 
 _NSF_MODELS = ("nsf",)
 
@@ -115,10 +115,35 @@ def build_nsf(
     x_numel = batch_x[0].numel()
     with torch.no_grad():
         y_numel = embedding_net(batch_y[:1]).numel()
-    if x_numel == 1:
-        raise NotImplementedError("1-D NSF (ContextSplineMap conditioner) is not implemented")
     zx, sx = z_score_parser(z_score_x)
     zy, sy = z_score_parser(z_score_y)
+    if x_numel == 1:
+        # scalar x (flow.py:401-408): a dummy mask and spline parameters learnt from the condition alone
+        # (ContextSplineMap: Linear, [one shared Linear] x hidden_layers, Linear -- constructed in that order)
+        H, C, hl = hidden_features, y_numel, int(hidden_layers_spline_context)
+        lay = Nsf1dLayout(C=C, H=H, NB=hl, KB=num_bins, T=num_transforms, tail_bound=float(tail_bound),
+                          zscore_input=zx, zscore_cond=zy, embed_is_identity=isinstance(embedding_net, nn.Identity))
+        state = {}
+        base = 1 if zx else 0
+        for l in range(num_transforms):
+            pn = f"net._transform._transforms.{base + l}.transform_net.spline_predictor."
+            state[pn + "0.weight"], state[pn + "0.bias"] = _linear_init(H, C)
+            w, b = _linear_init(H, H)        # constructed (RNG consumed) even when it is repeated zero times
+            if hl > 0:
+                for k in range(hl):
+                    state[pn + f"{2 + 2 * k}.weight"], state[pn + f"{2 + 2 * k}.bias"] = w, b
+            state[pn + f"{2 + 2 * hl}.weight"], state[pn + f"{2 + 2 * hl}.bias"] = _linear_init(3 * num_bins - 1, H)
+        if zx:
+            t_mean, t_std = z_standardization(batch_x.reshape(batch_x.shape[0], -1), sx)
+            shift, scale = -t_mean / t_std, 1 / t_std
+        else:
+            shift, scale = torch.zeros(()), torch.ones(())
+        c_mean, c_std = standardizing_stats(batch_y, sy) if zy else (None, None)
+        est = NSFEstimator(lay, input_shape=batch_x[0].shape, condition_shape=batch_y[0].shape, shift=shift,
+                           scale=scale, cond_mean=c_mean, cond_std=c_std, embedding_net=embedding_net)
+        with torch.no_grad():
+            lay.pack(state, out=est.net.flat.data)
+        return est
     lay = NsfLayout(D=x_numel, C=y_numel, H=hidden_features, NB=num_blocks, KB=num_bins,
                     T=num_transforms, tail_bound=float(tail_bound), zscore_input=zx,
                     zscore_cond=zy, embed_is_identity=isinstance(embedding_net, nn.Identity))

@@ -381,11 +381,119 @@ class NsfLayout(_LayoutOps):
         s.inv_sqrt_h = 1.0 / math.sqrt(self.H)
         s.min_bw = s.min_bh = s.min_d = 1e-3
         s.edge_raw = self.edge_raw
-        s.head, s.M, s.mog_eps = 0, 0, 0.0
+        s.head, s.M, s.mog_eps, s.cond_mlp = 0, 0, 0.0, 0
         return s
 
 
 NsfLayout.family = "nsf"
+
+
+@dataclass
+class Nsf1dLayout(_LayoutOps):
+    """Packed layout of the ONE-dimensional neural spline flow (flow.py:401-432 with x_numel == 1): T spline
+    transforms of the single feature whose 3K-1 parameters come from a context-only MLP (`ContextSplineMap`,
+    flow.py:1419-1478: Linear -> ReLU -> hidden_layers x [one shared Linear -> ReLU] -> Linear), no LULinear.
+    Runs on the NSF kernels (`sbi_nsf_model` with cond_mlp = 1, NB = hidden_layers, no identity features)."""
+    C: int
+    H: int = 50
+    NB: int = 1                  # hidden_layers_spline_context
+    KB: int = 10
+    T: int = 5
+    tail_bound: float = 3.0
+    zscore_input: bool = True
+    zscore_cond: bool = True
+    embed_is_identity: bool = True
+    wcap_target: int = 4096
+    n_params: int = 0
+    index: Dict[str, np.ndarray] = field(default_factory=dict, repr=False)
+    D: int = 1
+
+    def __post_init__(self):
+        C, H, NB, KB, T = self.C, self.H, self.NB, self.KB, self.T
+        if NB < 0 or NB > L.SBI_NSF_MAX_BLOCKS:
+            raise ValueError(f"0 <= hidden_layers_spline_context <= {L.SBI_NSF_MAX_BLOCKS}")
+        self.Dp, self.Cp, self.Hp = 4, round4(C), round4(H)
+        self.NPAR = 3 * KB - 1
+        self.PR = round4(self.NPAR)
+        if self.PR > self.Hp:
+            raise ValueError("hidden_features must be >= the padded spline parameter count")
+        self.IDp, self.TRmax, self.K0p = 0, 1, self.Cp
+        Hp, Cp = self.Hp, self.Cp
+        cap = max(self.wcap_target, 4 * self.K0p, 4 * (Hp + Cp), self.PR * Hp)
+
+        def rows(rowlen):
+            return max(4, min(Hp, (cap // rowlen) & ~3))
+
+        self.rpc0, self.rpc1, self.rpc2 = rows(self.K0p), rows(Hp), rows(Hp + Cp)
+        self.nf_chunk = 1
+        used = max(self.rpc0 * self.K0p, self.rpc1 * Hp, self.rpc2 * (Hp + Cp), self.PR * Hp)
+        self.wcap = (used + 31) & ~31
+        off = 0
+
+        def take(n):
+            nonlocal off
+            o = off
+            off += round4(n)
+            return o
+
+        tab = np.zeros((T, L.SBI_NSF_LAYER_STRIDE), np.int32)
+        idx: Dict[str, np.ndarray] = {}
+        self.buffers: Dict[str, torch.Tensor] = {}
+        base = 1 if self.zscore_input else 0
+        for l in range(T):
+            pc = f"net._transform._transforms.{base + l}."
+            pn = pc + "transform_net.spline_predictor."
+            tab[l, L.L_NID], tab[l, L.L_NTR], tab[l, L.L_FEAT] = 0, 1, l
+            self.buffers[pc + "identity_features"] = torch.zeros(0, dtype=torch.int64)
+            self.buffers[pc + "transform_features"] = torch.zeros(1, dtype=torch.int64)
+            o = take(Hp * Cp)
+            tab[l, L.L_W0] = o
+            idx[pn + "0.weight"] = o + np.arange(H)[:, None] * Cp + np.arange(C)[None, :]
+            o = take(Hp)
+            tab[l, L.L_B0] = o
+            idx[pn + "0.bias"] = o + np.arange(H)
+            ow, ob = take(Hp * Hp), take(Hp)
+            tab[l, L.L_BLK0], tab[l, L.L_BLK0 + 1] = ow, ob
+            for k in range(NB):      # nn.Sequential lists the shared module once per position
+                idx[pn + f"{2 + 2 * k}.weight"] = ow + np.arange(H)[:, None] * Hp + np.arange(H)[None, :]
+                idx[pn + f"{2 + 2 * k}.bias"] = ob + np.arange(H)
+            o = take(self.PR * Hp)
+            tab[l, L.L_WF] = o
+            idx[pn + f"{2 + 2 * NB}.weight"] = o + np.arange(self.NPAR)[:, None] * Hp + np.arange(H)[None, :]
+            o = take(self.PR)
+            tab[l, L.L_BF] = o
+            idx[pn + f"{2 + 2 * NB}.bias"] = o + np.arange(self.NPAR)
+            tab[l, L.L_HAS_LU] = 0
+        self.n_params = off
+        self.index = idx
+        self.layer_tab = tab
+        self.feat_tab = np.zeros(T, np.int32)            # layer l: no identity features, transformed feature 0
+        self.edge_raw = float(np.log(np.exp(1 - 1e-3) - 1))
+
+    def tables(self):
+        return self.layer_tab.reshape(-1).astype(np.int32), self.feat_tab.astype(np.int32)
+
+    def tc_plan(self):
+        return None
+
+    def num_real_params(self) -> int:
+        return int(len({int(i) for v in self.index.values() for i in v.reshape(-1)}))
+
+    def fill_struct(self, s: "L.NsfModel", nbuf: int):
+        s.D, s.C, s.H, s.NB, s.KB, s.T = 1, self.C, self.H, self.NB, self.KB, self.T
+        s.Dp, s.Cp, s.IDp, s.Hp, s.PR = self.Dp, self.Cp, 0, self.Hp, self.PR
+        s.TRmax, s.nf_chunk = 1, 1
+        s.rpc0, s.rpc1, s.rpc2 = self.rpc0, self.rpc1, self.rpc2
+        s.wcap, s.nbuf, s.n_params = self.wcap, nbuf, self.n_params
+        s.tail_bound = self.tail_bound
+        s.inv_sqrt_h = 1.0 / math.sqrt(self.H)
+        s.min_bw = s.min_bh = s.min_d = 1e-3
+        s.edge_raw = self.edge_raw
+        s.head, s.M, s.mog_eps, s.cond_mlp = 0, 0, 0.0, 1
+        return s
+
+
+Nsf1dLayout.family = "nsf"
 
 
 @dataclass
@@ -521,7 +629,7 @@ class MadeLayout(_LayoutOps):
         s.wcap, s.nbuf, s.n_params = self.wcap, nbuf, self.n_params
         s.tail_bound, s.inv_sqrt_h, s.edge_raw = 1.0, 1.0, 0.0
         s.min_bw = s.min_bh = s.min_d = 1e-3
-        s.head, s.M, s.mog_eps = 1, self.M, self.epsilon
+        s.head, s.M, s.mog_eps, s.cond_mlp = 1, self.M, self.epsilon, 0
         return s
 
 

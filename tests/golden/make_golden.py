@@ -13,6 +13,7 @@ Fixtures (small, committed):
   maf_d3c2.pt     reference `posterior_nn("maf")` (theta-dim 3, x-dim 2; BASELINE configs[0]): state_dict,
                   permutations, log_prob and inverse outputs.
   maf_rqs_d4c3.pt reference `posterior_nn("maf_rqs")` (theta-dim 4, x-dim 3): same contents as maf_d3c2.pt.
+  nsf_d1c3.pt     the ONE-dimensional NSF (scalar theta, x-dim 3; ContextSplineMap conditioner): as nsf_d3c2.pt.
   made_d3c2.pt    reference `posterior_nn("made")` (theta-dim 3, x-dim 2): state_dict, log_prob values, and
                   moments / quantiles of 20 000 reference samples at one condition.
   searchsorted.pt the reference's bin-search known-answer test vectors (tests/torchutils_test.py:135-157).
@@ -172,6 +173,8 @@ if __name__ == "__main__":
     torch.save(flow_fixture(3, 2, 8), os.path.join(HERE, "nsf_d3c2.pt"))
     torch.save(train_fixture(), os.path.join(HERE, "npe_train.pt"))
     torch.save(maf_fixture(3, 2, 9), os.path.join(HERE, "maf_d3c2.pt"))
+    if "--new" in sys.argv or not os.path.exists(os.path.join(HERE, "nsf_d1c3.pt")):
+        torch.save(flow_fixture(1, 3, 16), os.path.join(HERE, "nsf_d1c3.pt"))
     if "--new" in sys.argv or not os.path.exists(os.path.join(HERE, "made_d3c2.pt")):
         torch.save(made_fixture(3, 2, 15), os.path.join(HERE, "made_d3c2.pt"))
     if "--new" in sys.argv or not os.path.exists(os.path.join(HERE, "maf_rqs_d4c3.pt")):
