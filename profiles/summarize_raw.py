@@ -25,7 +25,7 @@ STALLS = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") a
 seen = {}
 for r in rows[2:]:
     name = r[ix["Kernel Name"]]
-    if not re.search(r"sbi::|tc::", name):
+    if not re.search(r"sbi::|tc::|nsf_|maf_|fm_|ratio_|slice_|ode|sde|adam|reduce_partials|peer_", name):
         continue
     short = re.sub(r"\(.*", "", name).replace("void ", "")
     key = (short, r[ix["launch__grid_size"]])

@@ -34,6 +34,28 @@ def within_support(distribution: Any, samples: Tensor) -> Tensor:
         return torch.isfinite(distribution.log_prob(samples))
 
 
+class DeviceMultivariateNormal(torch.distributions.MultivariateNormal):
+    """MultivariateNormal whose `log_prob` is one (rows, D) x (D, D) product with the inverse Cholesky factor.
+    torch's implementation solves a triangular system with the rows as right-hand sides, which on CUDA takes
+    seconds for the 10^6-row batches of the rejection / MCMC potentials (measured 5.4 s per call at
+    1 M x 10 on a B200, bench cfg5); same value to fp32 rounding."""
+
+    def __init__(self, loc, covariance_matrix=None, scale_tril=None, validate_args=None):
+        super().__init__(loc, covariance_matrix=covariance_matrix, scale_tril=scale_tril, validate_args=validate_args)
+        L_ = self._unbroadcasted_scale_tril
+        eye = torch.eye(L_.shape[-1], dtype=L_.dtype, device=L_.device)
+        self._linv_t = torch.linalg.solve_triangular(L_, eye, upper=False).transpose(-1, -2).contiguous()
+        self._half_log_det = L_.diagonal(dim1=-2, dim2=-1).log().sum(-1)
+
+    def log_prob(self, value):
+        if self._validate_args:
+            self._validate_sample(value)
+        if self.loc.dim() != 1:
+            return super().log_prob(value)
+        z = (value - self.loc) @ self._linv_t
+        return -0.5 * (z * z).sum(-1) - self._half_log_det - 0.5 * self.loc.shape[-1] * 1.8378770664093453
+
+
 def prior_to_device(prior, device):
     """Move a torch.distributions prior to `device` (the reference requires the user to do
     this, inference_on_device_test.py; we do it for the common families)."""
@@ -42,13 +64,14 @@ def prior_to_device(prior, device):
     try:
         import torch.distributions as td
         if isinstance(prior, td.MultivariateNormal):
-            return td.MultivariateNormal(prior.loc.to(device), covariance_matrix=prior.covariance_matrix.to(device))
+            return DeviceMultivariateNormal(prior.loc.to(device), covariance_matrix=prior.covariance_matrix.to(device),
+                                            validate_args=False)
         if isinstance(prior, td.Independent):
             return td.Independent(prior_to_device(prior.base_dist, device), prior.reinterpreted_batch_ndims)
         if isinstance(prior, td.Uniform):
             return td.Uniform(prior.low.to(device), prior.high.to(device), validate_args=False)
         if isinstance(prior, td.Normal):
-            return td.Normal(prior.loc.to(device), prior.scale.to(device))
+            return td.Normal(prior.loc.to(device), prior.scale.to(device), validate_args=False)
     except Exception:   # pragma: no cover
         pass
     if hasattr(prior, "to"):
@@ -300,7 +323,7 @@ class MCMCPosterior:
 
         sampler = SliceSamplerVectorized(log_prob_fn=log_prob_fn, init_params=initial_params.double().cpu().numpy(),
                                          num_chains=num_chains, thin=thin, verbose=show_progress_bars,
-                                         device=self._device)
+                                         device=self._device, graph=True)
         warmup_ = warmup_steps * thin
         num_samples_ = ceil((num_samples * thin) / num_chains)
         samples = sampler.run(warmup_ + num_samples_)          # (chains, n, dim), already thinned

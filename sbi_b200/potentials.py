@@ -119,7 +119,7 @@ class PosteriorBasedPotential(BasePotential):
         with torch.set_grad_enabled(track_gradients):
             lp = self.posterior_estimator.log_prob(theta.unsqueeze(1), condition=x)[:, 0]
             inside = within_support(self.prior, theta)
-            return torch.where(inside, lp, torch.tensor(float("-inf"), dtype=torch.float32, device=self.device))
+            return torch.where(inside, lp, torch.full_like(lp, float("-inf")))    # (no host scalar: graph-capturable)
 
 
 class LikelihoodBasedPotential(BasePotential):

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import os
 import time
 import warnings
 from typing import Any, Callable, Optional, Tuple, Union
@@ -35,7 +36,7 @@ class SliceSamplerVectorized:
                  thin: int = 1, tuning: int = 50, verbose: bool = False,
                  init_width: Union[float, np.ndarray] = 0.01, max_width: float = float("inf"),
                  num_workers: int = 1, device: str = "cuda", seed: Optional[int] = None,
-                 check_every: int = 16):
+                 check_every: int = 16, graph: bool = False):
         self._log_prob_fn = log_prob_fn
         self.x = init_params
         self.num_chains = num_chains
@@ -48,6 +49,10 @@ class SliceSamplerVectorized:
         self._device = device
         self._seed = seed
         self._check_every = check_every
+        # graph=True: `check_every` lock-steps [potential -> state machine] are captured once as a CUDA graph
+        # and replayed (the potential must be pure device work without host synchronisation: the estimator
+        # potentials of sbi_b200.potentials with a device-resident prior are; a numpy callback is not)
+        self._graph = bool(graph) and os.environ.get("SBI_B200_SLICE_GRAPH", "1") != "0"
         self.num_potential_evals = 0
         if num_workers > 1:
             warn("Parallelization of vectorized slice sampling not implement, running serially.", stacklevel=2)
@@ -74,15 +79,35 @@ class SliceSamplerVectorized:
                           samples.data_ptr())
         L.check(lib.sbi_b200_slice_init(C.byref(s), L.ptr(params), L.stream_ptr()), "slice_init")
         it = 0
-        while True:
+
+        def lock_step():
             lp = self._log_prob_fn(params)
             lp = torch.as_tensor(lp, dtype=torch.float32).to(dev).reshape(-1).contiguous()
-            self.num_potential_evals += Cn
             L.check(lib.sbi_b200_slice_step(C.byref(s), L.ptr(lp), L.ptr(params), L.ptr(n_done),
                                             L.stream_ptr()), "slice_step")
-            it += 1
-            if it % self._check_every == 0 and int(n_done.item()) == Cn:
-                break
+
+        graph = None
+        while True:
+            if graph is not None:
+                graph.replay()
+                it += self._check_every
+                self.num_potential_evals += Cn * self._check_every
+            else:
+                lock_step()
+                it += 1
+                self.num_potential_evals += Cn
+            if it % self._check_every == 0:
+                if int(n_done.item()) == Cn:
+                    break
+                if self._graph and graph is None:
+                    # the eager round above warmed everything up; capture the next rounds
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side):
+                        for _ in range(self._check_every):
+                            lock_step()
+                    torch.cuda.current_stream().wait_stream(side)
         self.num_lock_steps = it
         out = samples[:, :int(num_samples)].cpu().numpy()
         out = out[:, :: self.thin, :]
