@@ -15,7 +15,7 @@ import logging
 import time
 import warnings
 from math import log
-from typing import Any, Callable, Optional, Tuple
+from typing import Union, Any, Callable, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -230,6 +230,112 @@ class DirectPosterior:
             log_factor = (log(self.leakage_correction(x=x, **(leakage_correction_params or {})))
                           if norm_posterior and self.prior is not None else 0)
             return unnorm - log_factor
+
+    # ---- batched observations (direct_posterior.py:218-306, 388-465): the hot loop of SBC / TARP / coverage ----
+    @torch.no_grad()
+    def sample_batched(self, sample_shape, x: Tensor, max_sampling_batch_size: int = 10_000,
+                       show_progress_bars: bool = False, reject_outside_prior: bool = True,
+                       max_sampling_time: Optional[float] = None, return_partial_on_timeout: bool = False) -> Tensor:
+        """Samples from p(theta | x_1), ..., p(theta | x_B): (*sample_shape, B, *input_shape).  Every round is ONE
+        sampling-kernel launch over (draws x B) rows; acceptance (prior support) is resolved for all observations
+        at once with a cumulative count per observation -- no per-observation host loop."""
+        num_samples = torch.Size(sample_shape).numel()
+        x = self._batch_x(torch.as_tensor(x, dtype=torch.float32).to(self._device))
+        B = x.shape[0]
+        est = self.posterior_estimator
+        D = int(torch.Size(est.input_shape).numel())
+        if B * num_samples > 2 ** 21:
+            warnings.warn(f"Batched sampling generates {B} * {num_samples} = {B * num_samples} samples.", stacklevel=2)
+        if max_sampling_batch_size is None:
+            max_sampling_batch_size = self.max_sampling_batch_size
+        if max_sampling_batch_size * B > 4_000_000:          # rows per launch (the reference caps at 100 000)
+            max_sampling_batch_size = max(1, 4_000_000 // B)
+        if not (reject_outside_prior and self.prior is not None):
+            return est.sample(torch.Size([num_samples]), condition=x).reshape(*torch.Size(sample_shape), B, *est.input_shape)
+        out = torch.empty(num_samples, B, D, dtype=torch.float32, device=self._device)
+        filled = torch.zeros(B, dtype=torch.int64, device=self._device)
+        drawn, accepted_total = 0, torch.zeros(B, dtype=torch.int64, device=self._device)
+        batch = min(num_samples, max_sampling_batch_size)
+        start = time.time()
+        bidx = torch.arange(B, device=self._device)
+        while True:
+            cand = est.sample(torch.Size([batch]), condition=x).reshape(batch, B, D)
+            ok = within_support(self.prior, cand.reshape(-1, D)).reshape(batch, B)
+            pos = torch.cumsum(ok.long(), dim=0) - 1 + filled.unsqueeze(0)            # slot of every accepted draw
+            valid = ok & (pos < num_samples)
+            sel = torch.nonzero(valid)                                                # the round's one host sync
+            out[pos[sel[:, 0], sel[:, 1]], sel[:, 1]] = cand[sel[:, 0], sel[:, 1]]
+            acc = ok.sum(0)
+            accepted_total += acc
+            drawn += batch
+            filled = torch.minimum(filled + acc, torch.full_like(filled, num_samples))
+            remaining = int((num_samples - filled).max().item())
+            if remaining <= 0:
+                break
+            if max_sampling_time is not None and (time.time() - start) > max_sampling_time:
+                n_ok = int(filled.min().item())
+                if return_partial_on_timeout and n_ok > 0:
+                    warnings.warn(f"Timeout exceeded after collecting {n_ok}/{num_samples} samples. "
+                                  "Returning partial results.", stacklevel=2)
+                    return out[:n_ok]
+                raise RuntimeError("Sampling aborted early because rejection sampling exceeded max_sampling_time. "
+                                   "This is likely due to extremely low acceptance.")
+            rate = float((accepted_total.float() / drawn).min().item())
+            batch = min(max_sampling_batch_size, max(int(1.5 * remaining / max(rate, 1e-12)), 100))
+        self._last_acceptance_rate = accepted_total.float() / drawn
+        return out.reshape(*torch.Size(sample_shape), B, *est.input_shape)
+
+    def log_prob_batched(self, theta: Tensor, x: Tensor, norm_posterior: bool = True, track_gradients: bool = False,
+                         leakage_correction_params: Optional[dict] = None) -> Tensor:
+        """log p(theta_b | x_b) for a batch of observations: theta (*sample_shape, B, *input_shape) or
+        (B, *input_shape), x (B, *condition_shape) -> (len(theta), B); -inf outside the prior support."""
+        est = self.posterior_estimator
+        x = self._batch_x(torch.as_tensor(x, dtype=torch.float32).to(self._device))
+        theta = torch.as_tensor(theta, dtype=torch.float32).to(self._device)
+        ev = len(est.input_shape)
+        if theta.dim() == ev:
+            theta = theta.unsqueeze(0)
+        th = theta.unsqueeze(0) if theta.dim() - ev == 1 else theta.reshape(-1, *theta.shape[-(ev + 1):])
+        est.eval()
+        with torch.set_grad_enabled(track_gradients):
+            unnorm = est.log_prob(th, condition=x)                                  # (S, B)
+            if self.prior is not None:
+                inside = within_support(self.prior, th.reshape(-1, *est.input_shape)).reshape(unnorm.shape)
+                unnorm = torch.where(inside, unnorm, torch.full_like(unnorm, float("-inf")))
+            if norm_posterior and self.prior is not None:
+                kw = dict(leakage_correction_params or {})
+                self.sample_batched((kw.get("num_rejection_samples", 10_000),), x,
+                                    max_sampling_batch_size=kw.get("rejection_sampling_batch_size", 10_000))
+                unnorm = unnorm - torch.log(self._last_acceptance_rate).unsqueeze(0)
+            return unnorm
+
+    def map(self, x: Optional[Tensor] = None, num_iter: int = 1_000, num_to_optimize: int = 100,
+            learning_rate: float = 0.01, init_method: Union[str, Tensor] = "posterior", num_init_samples: int = 1_000,
+            save_best_every: int = 10, show_progress_bars: bool = False, force_update: bool = False) -> Tensor:
+        """Maximum-a-posteriori estimate by gradient ascent on the posterior potential in unconstrained space
+        (base_posterior.py `_calculate_map` -> sbiutils.gradient_ascent); gradients w.r.t. theta come from the
+        fused VJP kernels."""
+        from .potentials import posterior_estimator_based_potential
+        from .samplers import gradient_ascent
+        x = self._batch_x(self._x_else_default_x(x))
+        if not force_update and getattr(self, "_map", None) is not None and getattr(self, "_map_x", None) is not None \
+                and self._map_x.shape == x.shape and bool((self._map_x == x).all()):
+            return self._map
+        potential_fn, theta_transform = posterior_estimator_based_potential(self.posterior_estimator, self.prior, x_o=x)
+        if isinstance(init_method, str):
+            if init_method == "posterior":
+                inits = self.sample((num_init_samples,), x=x)
+            elif init_method == "proposal":
+                inits = self.prior.sample((num_init_samples,))
+            else:
+                raise ValueError
+        else:
+            inits = torch.as_tensor(init_method, dtype=torch.float32).to(self._device)
+        self._map = gradient_ascent(potential_fn=potential_fn, inits=inits, theta_transform=theta_transform,
+                                    num_iter=num_iter, num_to_optimize=num_to_optimize, learning_rate=learning_rate,
+                                    save_best_every=save_best_every, show_progress_bars=show_progress_bars)[0]
+        self._map_x = x
+        return self._map
 
     @torch.no_grad()
     def leakage_correction(self, x: Tensor, num_rejection_samples: int = 10_000,
