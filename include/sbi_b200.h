@@ -354,6 +354,10 @@ typedef struct {
   int32_t wcap, nbuf, n_params;
   float noise_scale;                /* sigma_min = 1e-3 */
   float ln_eps;
+  int32_t raw;                      /* 1: the bare network (score estimators): d_input is already the network
+                                     * input, d_time the value fed to the time embedding, outputs are the raw
+                                     * network outputs -- no flow-matching noising / standardisation / rescaling */
+  int32_t pad_;
   const float* d_params;
   const int32_t* d_tab;
   const float* d_stats;             /* [mean_0(Dp) | std_0(Dp) | ctx_mean(Cp) | ctx_std(Cp) | div_term(TEp/2)] */
@@ -366,7 +370,8 @@ int sbi_b200_fm_forward(const sbi_fm_model* m, const sbi_rows* rows, const float
 /* the same velocity field and its exact divergence sum_i dv_i/dtheta_i (d_div (R,); d_v optional): the
  * right-hand side of the augmented neural ODE behind `VectorFieldPosterior.log_prob`
  * (sbi/samplers/ode_solvers/zuko_ode.py:80-124 -> zuko FreeFormJacobianTransform(exact=True);
- * sbi/inference/potentials/vector_field_potential.py:145-212). */
+ * sbi/inference/potentials/vector_field_potential.py:145-212).  With m->raw the kernel writes the DIAGONAL of the bare
+ * network's input Jacobian instead, d_div (R, D): the caller (score estimators) weights it per dimension. */
 int sbi_b200_fm_forward_div(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
                             int32_t time_shared, float* d_v, float* d_div, void* stream);
 /* flow-matching loss of a batch and its parameter gradient (FlowMatchingEstimator.loss :270-347
@@ -376,6 +381,14 @@ int sbi_b200_fm_vjp_parts(int64_t R);
 int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
                          const float* d_eps, const float* d_gout, float g_const, float* d_loss,
                          float* d_gpart, float* d_loss_acc, void* stream);
+
+/* Parameter gradient of the bare network for a given upstream gradient d_dout (R, D) of its outputs (m->raw must
+ * be 1): the backward of `ConditionalScoreEstimator.forward` (sbi/neural_nets/estimators/score_estimator.py:149-215)
+ * through the VectorFieldMLP; everything around the network (time-dependent z-scoring, the Gaussian skip term, the
+ * denoising-score-matching loss with its control variate, :230-316) is element-wise host code.
+ * d_gpart (sbi_b200_fm_vjp_parts(R), n_params) receives per-CTA partial gradients. */
+int sbi_b200_fm_net_vjp(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time, const float* d_dout,
+                        float* d_gpart, void* stream);
 
 /* ---- adaptive Dormand-Prince 5(4) with the step control on the device (csrc/ode.cu), replacing the
  * host-side loop of the solver the reference delegates to (zuko.utils.odeint; call sites

@@ -96,7 +96,7 @@ class FmModel(C.Structure):
         ("rpc_i", C.c_int32), ("rpc_c", C.c_int32), ("rpc_m", C.c_int32), ("rpc_t", C.c_int32),
         ("rpc_h", C.c_int32), ("rpc_o", C.c_int32),
         ("wcap", C.c_int32), ("nbuf", C.c_int32), ("n_params", C.c_int32),
-        ("noise_scale", C.c_float), ("ln_eps", C.c_float),
+        ("noise_scale", C.c_float), ("ln_eps", C.c_float), ("raw", C.c_int32), ("pad_", C.c_int32),
         ("d_params", C.c_void_p), ("d_tab", C.c_void_p), ("d_stats", C.c_void_p),
     ]
 
@@ -174,6 +174,8 @@ _EXPORTS = {
     "sbi_b200_ratio_vjp_parts": (C.c_int, [C.c_int64]),
     "sbi_b200_ratio_vjp": (C.c_int, [C.POINTER(RatioModel), C.POINTER(Pairs), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sbi_b200_fm_net_vjp": (C.c_int, [C.POINTER(FmModel), C.POINTER(Rows), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
     "sbi_b200_fm_forward_div": (C.c_int, [C.POINTER(FmModel), C.POINTER(Rows), C.c_void_p, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
     "sbi_b200_made_sample": (C.c_int, [C.POINTER(NsfModel), C.POINTER(Rows), C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -112,15 +112,19 @@ __device__ __forceinline__ void fm_load(const sbi_fm_model& m, const sbi_rows& r
       const float th = __ldg(rows.d_input + src * D + d);
       const float t = __ldg(time + (time_shared ? 0 : gr));
       const float mu0 = __ldg(st + d), sd0 = __ldg(st + Dp + d);
-      float tht = th;
-      if (TRAIN) {
-        const float e1 = __ldg(eps + gr * D + d);
-        tht = (1.f - t) * th + (t + m.noise_scale) * e1;
-        tg = ((e1 - th) + mu0) / sqrtf(1.f + sd0 * sd0);
+      if (m.raw) {            // bare network (score estimators): the caller prepared the network input
+        tn = th;
+      } else {
+        float tht = th;
+        if (TRAIN) {
+          const float e1 = __ldg(eps + gr * D + d);
+          tht = (1.f - t) * th + (t + m.noise_scale) * e1;
+          tg = ((e1 - th) + mu0) / sqrtf(1.f + sd0 * sd0);
+        }
+        const float a = (1.f - t) * sd0;
+        const float sdt = sqrtf(a * a + t * t + 1e-6f);
+        tn = (tht - (1.f - t) * mu0) / sdt;
       }
-      const float a = (1.f - t) * sd0;
-      const float sdt = sqrtf(a * a + t * t + 1e-6f);
-      tn = (tht - (1.f - t) * mu0) / sdt;
     }
     TN[d * LD + r] = tn;
     if (TRAIN) TGT[d * LD + r] = tg;
@@ -304,7 +308,8 @@ fm_forward_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant_
       const int r = e / m.D, d = e % m.D;
       if (row0 + r < rows.R) {
         const float sd0 = __ldg(st + m.Dp + d);
-        v[(row0 + r) * m.D + d] = sm[L.OUT + d * LD + r] * sqrtf(1.f + sd0 * sd0) - __ldg(st + d);
+        v[(row0 + r) * m.D + d] = m.raw ? sm[L.OUT + d * LD + r]
+                                          : sm[L.OUT + d * LD + r] * sqrtf(1.f + sd0 * sd0) - __ldg(st + d);
       }
     }
     consumer_sync();
@@ -386,7 +391,7 @@ __device__ __forceinline__ void fm_tangent_pass(const sbi_fm_model& m, WPipe& pi
     const float dv = row_reduce<TM>(H, RED, [&](int k, int r) { return __ldg(wo + k) * dH[k * LD + r]; });
     if (threadIdx.x < TM) {
       const float sd0 = __ldg(m.d_stats + m.Dp + i);
-      sm[L.DIV + threadIdx.x] += dv * sqrtf(1.f + sd0 * sd0);
+      sm[L.DIV + threadIdx.x] += dv * (m.raw ? 1.f : sqrtf(1.f + sd0 * sd0));
     }
     consumer_sync();
   }
@@ -423,7 +428,8 @@ fm_trace_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ 
         const int r = e / m.D, d = e % m.D;
         if (row0 + r < rows.R) {
           const float sd0 = __ldg(st + m.Dp + d);
-          v[(row0 + r) * m.D + d] = sm[L.OUT + d * LD + r] * sqrtf(1.f + sd0 * sd0) - __ldg(st + d);
+          v[(row0 + r) * m.D + d] = m.raw ? sm[L.OUT + d * LD + r]
+                                          : sm[L.OUT + d * LD + r] * sqrtf(1.f + sd0 * sd0) - __ldg(st + d);
         }
       }
     if (threadIdx.x < TM) sm[L.DIV + threadIdx.x] = 0.f;
@@ -434,14 +440,18 @@ fm_trace_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ 
         if (gr < rows.R) {
           const float t = __ldg(time + (time_shared ? 0 : gr));
           const float a = (1.f - t) * __ldg(st + m.Dp + i);
-          inv = rsqrtf(a * a + t * t + 1e-6f);
+          inv = m.raw ? 1.f : rsqrtf(a * a + t * t + 1e-6f);
         }
         s_inv[threadIdx.x] = inv;
       }
       consumer_sync();
       fm_tangent_pass<kConsumer, TM, RN>(m, pipe, sm, L, i, s_inv);
+      if (m.raw && threadIdx.x < TM) {   // bare network: the Jacobian's diagonal, entry by entry
+        if (row0 + threadIdx.x < rows.R) div[(row0 + threadIdx.x) * m.D + i] = sm[L.DIV + threadIdx.x];
+        sm[L.DIV + threadIdx.x] = 0.f;
+      }
     }
-    if (threadIdx.x < TM && row0 + threadIdx.x < rows.R) div[row0 + threadIdx.x] = sm[L.DIV + threadIdx.x];
+    if (!m.raw && threadIdx.x < TM && row0 + threadIdx.x < rows.R) div[row0 + threadIdx.x] = sm[L.DIV + threadIdx.x];
     consumer_sync();
   }
 }
@@ -451,7 +461,8 @@ template <int TM, int RN, int RK>
 __global__ void __launch_bounds__(kThreads, 1)
 fm_vjp_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sbi_rows rows,
               const float* __restrict__ time, const float* __restrict__ eps, const float* __restrict__ gout,
-              float g_const, float* __restrict__ loss, float* __restrict__ gpart, float* __restrict__ loss_acc) {
+              float g_const, float* __restrict__ loss, float* __restrict__ gpart, float* __restrict__ loss_acc,
+              const float* __restrict__ dout) {
   constexpr int LD = Tile<TM>::LD;
   constexpr int PARTS = kConsumerThreads / TM;
   extern __shared__ __align__(128) float sm[];
@@ -493,6 +504,14 @@ fm_vjp_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sb
     const int64_t row0 = tile * TM;
     fm_load<TM, true>(m, rows, time, 0, eps, row0, sm, L);
     fm_net_forward<kConsumer, TM, RN, kFmTrain>(m, pipe, sm, L);
+    if (dout != nullptr) {
+      // bare network: the upstream gradient of the outputs is given (score estimators, sbi_b200_fm_net_vjp)
+      for (int e = threadIdx.x; e < m.Dp * TM; e += kConsumerThreads) {
+        const int d = e / TM, r = e % TM;
+        OUT[d * LD + r] = (d < m.D && row0 + r < rows.R) ? __ldg(dout + (row0 + r) * m.D + d) : 0.f;
+      }
+      consumer_sync();
+    } else
     // loss_r = mean_d (v_out - target)^2 ; dOUT = g_r * 2/D * (v_out - target)   (in place in OUT)
     {
       float lsum = 0.f, bad = 0.f;
@@ -712,6 +731,23 @@ extern "C" int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows,
   if ((rc = fm_set_smem<1>(k, L.total_bytes))) return rc;
   const int grid = sbi_b200_fm_vjp_parts(rows->R);
   k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *rows, d_time, d_eps, d_gout, g_const, d_loss,
-                                                           d_gpart, d_loss_acc);
+                                                           d_gpart, d_loss_acc, nullptr);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int sbi_b200_fm_net_vjp(const sbi_fm_model* m, const sbi_rows* rows, const float* d_time,
+                                   const float* d_dout, float* d_gpart, void* stream) {
+  sbi::DeviceGuard dev_guard_(m ? m->d_params : nullptr);
+  int rc = fm_check(m);
+  if (rc) return rc;
+  if (!m->raw || !rows || !rows->d_input || !rows->d_cond || rows->R < 1 || !d_time || !d_dout || !d_gpart)
+    return SBI_EINVAL;
+  constexpr int TM = 16;
+  const FmSmem L = fm_smem_layout(*m, TM, kFmTrain);
+  auto k = fm_vjp_kernel<TM, 2, 2>;
+  if ((rc = fm_set_smem<1>(k, L.total_bytes))) return rc;
+  const int grid = sbi_b200_fm_vjp_parts(rows->R);
+  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *rows, d_time, nullptr, nullptr, 0.f, nullptr, d_gpart,
+                                                           nullptr, d_dout);
   return (int)cudaGetLastError();
 }

@@ -430,6 +430,7 @@ class DeviceDopri5:
         self.ctrl = torch.zeros(16, dtype=torch.float32, device=device)
         self.ctrl_i = self.ctrl.view(torch.int32)
         self.t_ptr = self.ctrl.data_ptr() + 4 * self._OFF_TSTAGE
+        self.t_stage = self.ctrl[self._OFF_TSTAGE:self._OFF_TSTAGE + 1]     # the same device scalar as a tensor
         self._host = torch.zeros(16, dtype=torch.float32).pin_memory()
         self.use_graph = use_graph
         self.graph = None
@@ -507,6 +508,33 @@ def _fm_rhs(est: FlowMatchingEstimator, cond: Tensor, R: int, with_div: bool):
     return rhs
 
 
+def _generic_rhs(est, cond: Tensor, R: int, with_div: bool, solver: "DeviceDopri5"):
+    """Right-hand side for estimators whose ODE is `ode_fn` around the network kernel (score estimators,
+    score.py): the element-wise arithmetic runs as torch ops on the solver's device-resident stage time, so
+    the step still captures into one CUDA graph."""
+    D = est.layout.D
+    t_view = solver.t_stage
+
+    def rhs(y: Tensor, t_ptr: int, out: Tensor):
+        t = t_view.expand(R)
+        th = y[:R * D].reshape(R, D)
+        if with_div:
+            f, dv = est.ode_fn_and_divergence(th, cond, t)
+            out[:R * D].copy_(f.reshape(-1))
+            out[R * D:].copy_(dv.reshape(-1))
+        else:
+            out.copy_(est.ode_fn(th, cond, t).reshape(-1))
+    return rhs
+
+
+def _make_solver(est, cond, R, n, dev, with_div, atol, rtol):
+    if getattr(est, "IS_SCORE", False):
+        solver = DeviceDopri5(n, dev, None, atol=atol, rtol=rtol)
+        solver.rhs = _generic_rhs(est, cond, R, with_div, solver)
+        return solver
+    return DeviceDopri5(n, dev, _fm_rhs(est, cond, R, with_div), atol=atol, rtol=rtol)
+
+
 @torch.no_grad()
 def sample_ode(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, atol: float = 1e-6,
                rtol: float = 1e-5, return_nfe: bool = False, device_control: bool = True):
@@ -518,10 +546,10 @@ def sample_ode(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, 
     D = est.layout.D
     y0 = est._mean_base.to(dev) + est._std_base.to(dev) * torch.randn(num_samples, D, device=dev)
     if not device_control:
-        y, nfe = odeint_dopri5(lambda y, t: est.forward(y, cond, torch.tensor(t, device=dev)), y0, est.t_max, est.t_min,
+        y, nfe = odeint_dopri5(lambda y, t: est.ode_fn(y, cond, torch.tensor(t, device=dev)), y0, est.t_max, est.t_min,
                                atol=atol, rtol=rtol)
         return (y, nfe) if return_nfe else y
-    solver = DeviceDopri5(num_samples * D, dev, _fm_rhs(est, cond, num_samples, False), atol=atol, rtol=rtol)
+    solver = _make_solver(est, cond, num_samples, num_samples * D, dev, False, atol, rtol)
     y, nfe, _, _ = solver.solve(y0, est.t_max, est.t_min)
     y = y.reshape(num_samples, D).clone()
     return (y, nfe) if return_nfe else y
@@ -540,7 +568,7 @@ def log_prob_ode(est: FlowMatchingEstimator, theta: Tensor, condition: Tensor, a
     R = th.shape[0]
     cond = condition.reshape(1, *est.condition_shape).to(dev).float().reshape(1, -1).contiguous()
     y0 = torch.cat([th.reshape(-1), torch.zeros(R, device=dev)])
-    solver = DeviceDopri5(R * D + R, dev, _fm_rhs(est, cond, R, True), atol=atol, rtol=rtol)
+    solver = _make_solver(est, cond, R, R * D + R, dev, True, atol, rtol)
     y, nfe, _, _ = solver.solve(y0, est.t_min, est.t_max)
     z, ladj = y[:R * D].reshape(R, D), y[R * D:]
     mu, sd = est._mean_base.to(dev).reshape(1, D), est._std_base.to(dev).reshape(1, D)
@@ -566,7 +594,7 @@ def sample_sde(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, 
     D = est.layout.D
     theta = est._mean_base.to(dev).reshape(1, D) + est._std_base.to(dev).reshape(1, D) * torch.randn(
         num_samples, D, device=dev)
-    if not fused:
+    if not fused or getattr(est, "IS_SCORE", False):      # generic estimator: its own score / drift / diffusion
         for i in range(1, ts.numel()):
             t1, t0 = ts[i - 1], ts[i]
             dt = t1 - t0

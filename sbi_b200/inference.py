@@ -1034,24 +1034,7 @@ class FMPE(_FlowTrainer):
                 grad_local = torch.zeros(P, dtype=torch.float32, device=dev)
                 sumsq = torch.zeros(peer.n_sumsq, dtype=torch.float32, device=dev)
 
-        def converged() -> bool:   # base_vf_inference.py:352-420
-            if self.epoch == 0:
-                self._best_val_loss, self._epochs_since_last_improvement, self._best_flat = float("inf"), 0, None
-            if self._val_loss < self._best_val_loss:
-                self._best_val_loss, self._epochs_since_last_improvement = self._val_loss, 0
-                self._best_flat = net.flat.data.clone()
-            else:
-                if len(self._summary["validation_loss"]) >= stop_after_epochs:
-                    recent = torch.tensor(self._summary["validation_loss"][-stop_after_epochs * 2:])
-                    z = (self._val_loss - self._best_val_loss) / recent.std().item()
-                    self._epochs_since_last_improvement = self._epochs_since_last_improvement + 1 if z > 2.0 else 0
-                else:
-                    return False
-            if self._epochs_since_last_improvement > stop_after_epochs - 1:
-                if self._best_flat is not None:
-                    net.flat.data.copy_(self._best_flat)
-                return True
-            return False
+        converged = lambda: self._vf_converged(net, stop_after_epochs)
 
         # One CUDA graph per epoch (single GPU): every step is [t ~ U, theta_1 ~ N draws, fused loss
         # fwd+bwd kernel, reduce, clip+Adam]; the epoch's row permutations live in static buffers.
@@ -1130,17 +1113,50 @@ class FMPE(_FlowTrainer):
             val_loss = vl / (vsteps * Bv * (1 if glob else world) * vt.shape[0]) if vsteps > 0 else float("nan")
             # the reference normalises by len(loader) * loader.batch_size, i.e. WITHOUT the repeat over times
             val_loss *= vt.shape[0] if vsteps > 0 else 1.0
-            # base.py:1110 keeps the RAW validation loss in self._val_loss (what _converged compares
-            # with the best loss); only the summaries hold the exponential moving averages
-            # (base_vf_inference.py:589-636), whose spread normalises the stopping rule
-            self._val_loss = val_loss
-            if self._summary["training_loss"]:
-                train_loss = (1 - ema_loss_decay) * self._summary["training_loss"][-1] + ema_loss_decay * train_loss
-                val_loss = (1 - ema_loss_decay) * self._summary["validation_loss"][-1] + ema_loss_decay * val_loss
-            self._summary["training_loss"].append(train_loss)
-            self._summary["validation_loss"].append(val_loss)
-            self._summary["epoch_durations_sec"].append(time.time() - t0)
-            self.epoch += 1
+            self._vf_record_epoch(train_loss, val_loss, ema_loss_decay, t0)
+        self._vf_finish(net, max_num_epochs)
+        if peer is not None:
+            timed_out = peer.error()
+            peer.close()
+            if timed_out:
+                raise RuntimeError("peer-memory gradient exchange timed out (a rank fell behind or died)")
+        return deepcopy(net)
+
+    def _vf_converged(self, net, stop_after_epochs: int) -> bool:
+        """base_vf_inference.py:352-420: an epoch counts as "no improvement" only if the validation loss sits more
+        than two standard deviations (of the recent EMA-smoothed losses) above the best one."""
+        if self.epoch == 0:
+            self._best_val_loss, self._epochs_since_last_improvement, self._best_flat = float("inf"), 0, None
+        if self._val_loss < self._best_val_loss:
+            self._best_val_loss, self._epochs_since_last_improvement = self._val_loss, 0
+            self._best_flat = net.flat.data.clone()
+        else:
+            if len(self._summary["validation_loss"]) >= stop_after_epochs:
+                recent = torch.tensor(self._summary["validation_loss"][-stop_after_epochs * 2:])
+                z = (self._val_loss - self._best_val_loss) / recent.std().item()
+                self._epochs_since_last_improvement = self._epochs_since_last_improvement + 1 if z > 2.0 else 0
+            else:
+                return False
+        if self._epochs_since_last_improvement > stop_after_epochs - 1:
+            if self._best_flat is not None:
+                net.flat.data.copy_(self._best_flat)
+            return True
+        return False
+
+    def _vf_record_epoch(self, train_loss: float, val_loss: float, ema_loss_decay: float, t0: float):
+        # base.py:1110 keeps the RAW validation loss in self._val_loss (what _converged compares
+        # with the best loss); only the summaries hold the exponential moving averages
+        # (base_vf_inference.py:589-636), whose spread normalises the stopping rule
+        self._val_loss = val_loss
+        if self._summary["training_loss"]:
+            train_loss = (1 - ema_loss_decay) * self._summary["training_loss"][-1] + ema_loss_decay * train_loss
+            val_loss = (1 - ema_loss_decay) * self._summary["validation_loss"][-1] + ema_loss_decay * val_loss
+        self._summary["training_loss"].append(train_loss)
+        self._summary["validation_loss"].append(val_loss)
+        self._summary["epoch_durations_sec"].append(time.time() - t0)
+        self.epoch += 1
+
+    def _vf_finish(self, net, max_num_epochs: int):
         if self.epoch > max_num_epochs:
             if self._val_loss < self._best_val_loss:
                 self._best_val_loss, self._best_flat = self._val_loss, net.flat.data.clone()
@@ -1148,12 +1164,6 @@ class FMPE(_FlowTrainer):
                 net.flat.data.copy_(self._best_flat)
         self._summary["epochs_trained"].append(self.epoch)
         self._summary["best_validation_loss"].append(self._best_val_loss)
-        if peer is not None:
-            timed_out = peer.error()
-            peer.close()
-            if timed_out:
-                raise RuntimeError("peer-memory gradient exchange timed out (a rank fell behind or died)")
-        return deepcopy(net)
 
     def build_posterior(self, density_estimator=None, prior=None, sample_with: str = "ode", **kwargs):
         from .posteriors import VectorFieldPosterior
@@ -1162,3 +1172,145 @@ class FMPE(_FlowTrainer):
         est = deepcopy(density_estimator if density_estimator is not None else self._neural_net)
         return VectorFieldPosterior(est, prior if prior is not None else self._prior, device=self._device,
                                     sample_with=sample_with)
+
+
+
+class NPSE(FMPE):
+    """Neural posterior score estimation (reference: trainers/vfpe/npse.py:69-268 on the shared loop of
+    base_vf_inference.py): denoising score matching of a VE / VP / sub-VP score network (score.py).
+
+    A step is [times + noise draws, noising and target arithmetic in torch, ONE launch of the network kernel over
+    the noised inputs and the control-variate means, loss head in torch, ONE launch of the network's
+    parameter-gradient kernel, clip + Adam kernel], captured once as a CUDA graph and replayed per batch; the
+    validation step (all validation times at once, base_vf_inference.py:524-543) is a second graph."""
+
+    def __init__(self, prior=None, vf_estimator: Union[str, Callable, None] = None,
+                 score_estimator: Union[str, Callable, None] = None, density_estimator: Optional[Callable] = None,
+                 sde_type: Optional[str] = None, device: str = "cuda", logging_level: Union[int, str] = "WARNING",
+                 summary_writer=None, tracker=None, show_progress_bars: bool = False):
+        from .score import posterior_score_nn
+        given = [e for e in (vf_estimator, score_estimator, density_estimator) if e is not None]
+        if len(given) > 1:
+            raise ValueError("pass only one of vf_estimator / score_estimator / density_estimator")
+        est = given[0] if given else "mlp"
+        super().__init__(prior=prior, density_estimator=(lambda *a: None), device=device)
+        if isinstance(est, str):
+            self._build_neural_net = posterior_score_nn(model=est, sde_type=sde_type or "ve")
+        else:
+            if sde_type is not None:
+                warnings.warn("sde_type is ignored when a build function is passed", stacklevel=2)
+            self._build_neural_net = est
+
+    def train(self, training_batch_size: int = 200, learning_rate: float = 5e-4, validation_fraction: float = 0.1,
+              stop_after_epochs: int = 20, max_num_epochs: int = 2 ** 31 - 1, clip_max_norm: Optional[float] = 5.0,
+              calibration_kernel=None, ema_loss_decay: float = 0.1, validation_times: Union[Tensor, int] = 10,
+              validation_times_nugget: float = 0.05, resume_training: bool = False, **kwargs):
+        if self._theta is None:
+            raise RuntimeError("call append_simulations() first")
+        if self._dp()[1] > 1:
+            raise NotImplementedError("NPSE training is single-process")
+        lib = L.load()
+        dev = self._device
+        N = self._theta.shape[0]
+        x2d = self._x.reshape(N, -1).contiguous()
+        n_train = int((1 - validation_fraction) * N)
+        n_val = N - n_train
+        if not resume_training or not hasattr(self, "train_indices"):
+            self.train_indices, self.val_indices = self._dp_split(N, n_train)
+        if self._neural_net is None:
+            tr = self.train_indices.to(dev)
+            self._neural_net = self._build_neural_net(self._theta[tr].cpu(), self._x[tr].cpu())
+        net = self._neural_net.to(dev)
+        self._neural_net = net
+        P = net.layout.n_params
+        B, Bv = min(training_batch_size, n_train), min(training_batch_size, n_val)
+        steps, vsteps = n_train // B, (n_val // Bv if Bv > 0 else 0)
+        if isinstance(validation_times, int):
+            validation_times = torch.linspace(net.t_min + validation_times_nugget,
+                                              net.t_max - validation_times_nugget, validation_times)
+        vt = validation_times.to(dev).float()
+        nt = vt.shape[0]
+        if not resume_training or not hasattr(self, "_opt_state"):
+            self._opt_state = torch.zeros(2 * P, dtype=torch.float32, device=dev)
+            self._opt_step = torch.zeros(2, dtype=torch.int32, device=dev)
+            self.epoch, self._val_loss = 0, float("Inf")
+        train_idx, val_idx = self.train_indices.to(dev), self.val_indices.to(dev)
+        max_norm = float(clip_max_norm) if clip_max_norm is not None else 0.0
+        w_all = None
+        if calibration_kernel is not None:
+            w_all = torch.as_tensor(calibration_kernel(self._x), dtype=torch.float32).reshape(-1).to(dev)
+        idx_buf = torch.zeros(B, dtype=torch.int64, device=dev)
+        vidx_buf = torch.zeros(max(Bv, 1), dtype=torch.int64, device=dev)
+        stats = torch.zeros(4, dtype=torch.float32, device=dev)     # train loss sum, bad, val loss sum, bad
+
+        def losses_on(idx, times):
+            losses = net.loss(self._theta[idx], x2d[idx], times=times)
+            return losses if w_all is None else w_all[idx] * losses
+
+        def train_step():
+            net.net.flat.grad = None
+            losses = losses_on(idx_buf, None)
+            losses.mean().backward()
+            ld = losses.detach()
+            stats[0] += ld.sum()
+            stats[1] += (~torch.isfinite(ld)).sum()
+            L.check(lib.sbi_b200_adam_clip_step(
+                L.ptr(net.flat.data), L.ptr(net.flat.grad), L.ptr(self._opt_state), L.ptr(self._opt_step),
+                L.ptr(net.net._mask), P, learning_rate, 0.9, 0.999, 1e-8, max_norm, 1.0, L.stream_ptr()),
+                "adam_clip_step")
+
+        def val_step():      # the batch repeated over all validation times (base_vf_inference.py:524-543)
+            with torch.no_grad():
+                ld = losses_on(vidx_buf.repeat(nt), vt.repeat_interleave(Bv))
+                stats[2] += ld.sum()
+                stats[3] += (~torch.isfinite(ld)).sum()
+
+        g_train = g_val = None
+        if os.environ.get("SBI_B200_NPSE_GRAPH", "1") != "0" and steps > 0:
+            snap = (net.flat.data.clone(), self._opt_state.clone(), self._opt_step.clone())
+            idx_buf.copy_(train_idx[:B])
+            if vsteps > 0:
+                vidx_buf.copy_(val_idx[:Bv])
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up outside capture (allocations, kernel attributes)
+                for _ in range(3):
+                    train_step()
+                if vsteps > 0:
+                    val_step()
+            torch.cuda.current_stream().wait_stream(side)
+            g_train = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_train):
+                train_step()
+            if vsteps > 0:
+                g_val = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_val):
+                    val_step()
+            net.flat.data.copy_(snap[0]); self._opt_state.copy_(snap[1]); self._opt_step.copy_(snap[2])
+
+        while self.epoch <= max_num_epochs and not self._vf_converged(net, stop_after_epochs):
+            t0 = time.time()
+            perm = train_idx[torch.randperm(n_train, device=dev)]
+            vperm = val_idx[torch.randperm(n_val, device=dev)] if vsteps > 0 else None
+            stats.zero_()
+            for s_ in range(steps):
+                idx_buf.copy_(perm[s_ * B:(s_ + 1) * B])
+                g_train.replay() if g_train is not None else train_step()
+            for s_ in range(vsteps):
+                vidx_buf.copy_(vperm[s_ * Bv:(s_ + 1) * Bv])
+                g_val.replay() if g_val is not None else val_step()
+            tl, tb, vl, vb = stats.tolist()                    # the one host sync of the epoch
+            if tb > 0 or vb > 0:
+                raise AssertionError("NaN/Inf present in NPSE loss.")
+            # the reference normalises the validation sum by len(loader) * batch_size, i.e. WITHOUT the repeat over times
+            self._vf_record_epoch(tl / (steps * B), vl / (vsteps * Bv) if vsteps > 0 else float("nan"),
+                                  ema_loss_decay, t0)
+        self._vf_finish(net, max_num_epochs)
+        net.zero_grad(set_to_none=True)
+        net._cache.clear()
+        return deepcopy(net)
+
+    def build_posterior(self, vector_field_estimator=None, prior=None, sample_with: str = "sde", **kwargs):
+        """npse.py:219-261: same posterior as FMPE's, reverse-SDE sampling by default."""
+        return super().build_posterior(density_estimator=vector_field_estimator, prior=prior, sample_with=sample_with,
+                                       **kwargs)
