@@ -472,12 +472,16 @@ fm_vjp_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sb
   const float* __restrict__ P = m.d_params;
   const int* T = m.d_tab;
   const int Hp = m.Hp, H = m.H;
+  // no upstream gradient at all (validation, the autograd Function's forward): the loss values only -- the
+  // backward sweep and its weight stream are skipped and the gradient slab is left untouched
+  const bool loss_only = dout == nullptr && gout == nullptr && g_const == 0.f;
 
   if (threadIdx.x >= kConsumerThreads) {
     if (threadIdx.x == kConsumerThreads) {
       auto noop = [](int, int, float(&)[RK][4], bool) {};
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         fm_net_forward<kProducer, TM, RN, kFmTrain>(m, pipe, sm, L);
+        if (loss_only) continue;
         dx_stage<kProducer, TM, RK>(pipe, P + __ldg(T + SBI_F_WO), m.Dp, Hp, m.rpc_o, nullptr, Hp, noop);
         for (int l = m.NL - 1; l >= 0; --l)
           dx_stage<kProducer, TM, RK>(pipe, P + __ldg(T + SBI_F_LAYER0 + 4 * l), Hp, Hp, m.rpc_h, nullptr, Hp, noop);
@@ -539,6 +543,7 @@ fm_vjp_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sb
         }
       }
       consumer_sync();
+      if (loss_only) continue;
       for (int e = threadIdx.x; e < m.Dp * TM; e += kConsumerThreads) {
         const int d = e / TM, r = e % TM;
         OUT[d * LD + r] = d < m.D ? RED[r] * (OUT[d * LD + r] - TGT[d * LD + r]) : 0.f;
@@ -585,10 +590,8 @@ fm_vjp_kernel(const __grid_constant__ sbi_fm_model m, const __grid_constant__ sb
           sg = fmaf(dy, X1[k * LD + r], sg);
           sb += dy;
         }
-        float* pg = gp + __ldg(LT + 2) + k;
-        float* pb = gp + __ldg(LT + 3) + k;
-        *pg = accum ? *pg + sg : sg;
-        *pb = accum ? *pb + sb : sb;
+        grad_out(gp + __ldg(LT + 2) + k, sg, accum);
+        grad_out(gp + __ldg(LT + 3) + k, sb, accum);
       }
       const float m1 = row_reduce<TM>(H, RED, [&](int k, int r) { return X2[k * LD + r]; }) / (float)H;
       const float m2 = row_reduce<TM>(H, RED, [&](int k, int r) { return X2[k * LD + r] * X1[k * LD + r]; }) / (float)H;

@@ -188,7 +188,7 @@ __device__ __forceinline__ void lu_backward(const sbi_nsf_model& m, const NsfLay
       for (int r = 0; r < TM; ++r) a += dZ[i * LD + r];
       dst = gp + o_bi + i;
     }
-    *dst = accumulate ? (*dst + a) : a;
+    grad_out(dst, a, accumulate);
   }
   consumer_sync();
   for (int t = threadIdx.x; t < D * TM; t += kConsumerThreads) {
@@ -515,7 +515,7 @@ nsf_vjp_kernel(const __grid_constant__ sbi_nsf_model m, const __grid_constant__ 
         for (int n = threadIdx.x; n < m.H; n += kConsumerThreads) {
           float a = 0.f;
           for (int r = 0; r < TM; ++r) a += dH[n * LD + r];
-          gbc[n] = accum ? (gbc[n] + a) : a;
+          grad_out(gbc + n, a, accum);
         }
       }
       dx_stage<kConsumer, TM, RK>(

@@ -191,12 +191,10 @@ __device__ __forceinline__ void gemm_dw(const float* __restrict__ dY, int N,
       for (int j = 0; j < 4; ++j) {
         const int k = kb + lk + 4 * j;
         if (k >= K) continue;
-        float* p = gW + (size_t)n * Kp + k;
-        *p = accumulate ? (*p + acc[i][j]) : acc[i][j];
+        grad_out(gW + (size_t)n * Kp + k, acc[i][j], accumulate);
       }
       if (gB != nullptr && kb == 0 && lk == 0) {
-        float* p = gB + n;
-        *p = accumulate ? (*p + sdy[i]) : sdy[i];
+        grad_out(gB + n, sdy[i], accumulate);
       }
     }
   }
