@@ -658,6 +658,27 @@ using namespace sbi;
 
 static int fm_num_sms() { return sbi::dev_num_sms(); }
 
+// The weight ring the caller asked for (nbuf stages of wcap floats) is a lower bound: the launch deepens it to what
+// the 227 KB of shared memory leave after the activation tile (3 stages in training at H = 100, 8 in evaluation).
+// ncu attributes ~25 % of fm_vjp's stall samples to the ring's `full` barrier (profiles/r02_fm_vjp.md), but the
+// deeper ring only moved cfg4 from 9.80 to 9.99 M samples/s: the wait is the chunk turn-around of one producer
+// thread at 16-row tiles, not the ring depth.
+#ifndef SBI_RING_AUTO
+#define SBI_RING_AUTO 1
+#endif
+static sbi_fm_model fm_deepen_ring(const sbi_fm_model& m, int TM, int mode) {
+  sbi_fm_model c = m;
+#if SBI_RING_AUTO
+  constexpr int kBudget = 227 * 1024 - 1024;      // static shared memory of the kernels stays below 1 KB
+  for (int nb = 8; nb > m.nbuf; --nb) {
+    c.nbuf = nb;
+    if (fm_smem_layout(c, TM, mode).total_bytes <= kBudget) return c;
+  }
+  c.nbuf = m.nbuf;
+#endif
+  return c;
+}
+
 static int fm_check(const sbi_fm_model* m) {
   if (!m || !m->d_params || !m->d_tab || !m->d_stats) return SBI_EINVAL;
   if (m->D < 1 || m->C < 1 || m->H < 1 || m->NL < 2 || m->NL > SBI_FM_MAX_LAYERS || m->TE < 2 || (m->TE & 1)) return SBI_EINVAL;
@@ -690,12 +711,13 @@ extern "C" int sbi_b200_fm_forward(const sbi_fm_model* m, const sbi_rows* rows, 
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_time || !d_v) return SBI_EINVAL;
   if (rows->R == 0) return 0;
   constexpr int TM = 32;
-  const FmSmem L = fm_smem_layout(*m, TM, kFmEval);
+  const sbi_fm_model md = fm_deepen_ring(*m, TM, kFmEval);
+  const FmSmem L = fm_smem_layout(md, TM, kFmEval);
   auto k = fm_forward_kernel<TM, 2>;
   if ((rc = fm_set_smem<0>(k, L.total_bytes))) return rc;
   const int64_t ntiles = (rows->R + TM - 1) / TM;
   const int grid = (int)std::min<int64_t>(ntiles, fm_num_sms());
-  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *rows, d_time, time_shared, d_v);
+  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(md, *rows, d_time, time_shared, d_v);
   return (int)cudaGetLastError();
 }
 
@@ -707,12 +729,13 @@ extern "C" int sbi_b200_fm_forward_div(const sbi_fm_model* m, const sbi_rows* ro
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_time || !d_div) return SBI_EINVAL;
   if (rows->R == 0) return 0;
   constexpr int TM = 16;
-  const FmSmem L = fm_smem_layout(*m, TM, kFmTrace);
+  const sbi_fm_model md = fm_deepen_ring(*m, TM, kFmTrace);
+  const FmSmem L = fm_smem_layout(md, TM, kFmTrace);
   auto k = fm_trace_kernel<TM, 2>;
   if ((rc = fm_set_smem<2>(k, L.total_bytes))) return rc;
   const int64_t ntiles = (rows->R + TM - 1) / TM;
   const int grid = (int)std::min<int64_t>(ntiles, fm_num_sms());
-  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *rows, d_time, time_shared, d_v, d_div);
+  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(md, *rows, d_time, time_shared, d_v, d_div);
   return (int)cudaGetLastError();
 }
 
@@ -729,11 +752,12 @@ extern "C" int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows,
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 1 || !d_time || !d_eps || !d_gpart) return SBI_EINVAL;
   constexpr int TM = 16;
-  const FmSmem L = fm_smem_layout(*m, TM, kFmTrain);
+  const sbi_fm_model md = fm_deepen_ring(*m, TM, kFmTrain);
+  const FmSmem L = fm_smem_layout(md, TM, kFmTrain);
   auto k = fm_vjp_kernel<TM, 2, 2>;
   if ((rc = fm_set_smem<1>(k, L.total_bytes))) return rc;
   const int grid = sbi_b200_fm_vjp_parts(rows->R);
-  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *rows, d_time, d_eps, d_gout, g_const, d_loss,
+  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(md, *rows, d_time, d_eps, d_gout, g_const, d_loss,
                                                            d_gpart, d_loss_acc, nullptr);
   return (int)cudaGetLastError();
 }
@@ -746,11 +770,12 @@ extern "C" int sbi_b200_fm_net_vjp(const sbi_fm_model* m, const sbi_rows* rows, 
   if (!m->raw || !rows || !rows->d_input || !rows->d_cond || rows->R < 1 || !d_time || !d_dout || !d_gpart)
     return SBI_EINVAL;
   constexpr int TM = 16;
-  const FmSmem L = fm_smem_layout(*m, TM, kFmTrain);
+  const sbi_fm_model md = fm_deepen_ring(*m, TM, kFmTrain);
+  const FmSmem L = fm_smem_layout(md, TM, kFmTrain);
   auto k = fm_vjp_kernel<TM, 2, 2>;
   if ((rc = fm_set_smem<1>(k, L.total_bytes))) return rc;
   const int grid = sbi_b200_fm_vjp_parts(rows->R);
-  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(*m, *rows, d_time, nullptr, nullptr, 0.f, nullptr, d_gpart,
+  k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(md, *rows, d_time, nullptr, nullptr, 0.f, nullptr, d_gpart,
                                                            nullptr, d_dout);
   return (int)cudaGetLastError();
 }

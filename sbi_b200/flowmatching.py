@@ -579,7 +579,8 @@ def log_prob_ode(est: FlowMatchingEstimator, theta: Tensor, condition: Tensor, a
 
 @torch.no_grad()
 def sample_sde(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, steps: int = 500,
-               ts: Optional[Tensor] = None, eta: float = 1.0, fused: bool = True) -> Tensor:
+               ts: Optional[Tensor] = None, eta: float = 1.0, fused: bool = True, corrector: Optional[str] = None,
+               corrector_params: Optional[dict] = None) -> Tensor:
     """Draw theta ~ q(theta | x) with the reverse SDE, Euler-Maruyama predictor, no corrector
     (Diffuser.run, samplers/score/diffuser.py:124-180; EulerMaruyama.predict,
     samplers/score/predictors.py:112-120; driver VectorFieldPosterior._sample_via_diffusion,
@@ -594,15 +595,41 @@ def sample_sde(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, 
     D = est.layout.D
     theta = est._mean_base.to(dev).reshape(1, D) + est._std_base.to(dev).reshape(1, D) * torch.randn(
         num_samples, D, device=dev)
-    if not fused or getattr(est, "IS_SCORE", False):      # generic estimator: its own score / drift / diffusion
-        for i in range(1, ts.numel()):
-            t1, t0 = ts[i - 1], ts[i]
+    if corrector not in (None, "langevin", "gibbs"):
+        raise NotImplementedError(f"corrector {corrector!r}: one of None, 'langevin', 'gibbs'")
+    cp = dict(corrector_params or {})
+    if not fused or corrector is not None or getattr(est, "IS_SCORE", False):
+        # generic path: the estimator's own score / drift / diffusion around the network kernel
+        def predict(theta, t1, t0):            # EulerMaruyama.predict (predictors.py:112-120)
             dt = t1 - t0
             f = est.drift_fn(theta, t1)
             g = est.diffusion_fn(theta, t1)
             score = est.score(theta, cond, t1)
             f_backward = f - (1 + eta ** 2) / 2 * g ** 2 * score
-            theta = theta - f_backward * dt + (eta * g) * torch.randn_like(theta) * torch.sqrt(dt)
+            return theta - f_backward * dt + (eta * g) * torch.randn_like(theta) * torch.sqrt(dt)
+
+        def correct(theta, t0, t1):            # Diffuser.run calls corrector(samples, t_next, t_current)
+            if corrector == "langevin":        # LangevinCorrector.correct (correctors.py:93-132): score at t1
+                step = cp.get("step_size", 1e-4)
+                std = math.sqrt(2 * step)
+                for _ in range(cp.get("num_steps", 5)):
+                    score = est.score(theta, cond, t1)
+                    theta = theta + step * score + std * torch.randn_like(theta)
+                return theta
+            for _ in range(cp.get("num_steps", 5)):   # GibbsCorrector (correctors.py:135-166): re-noise, predict back
+                f = est.drift_fn(theta, t0)
+                g = est.diffusion_fn(theta, t0)
+                eps = torch.randn_like(theta)
+                dt = t1 - t0
+                theta = theta + f * dt + g * eps * torch.sqrt(dt)
+                theta = predict(theta, t1, t0)
+            return theta
+
+        for i in range(1, ts.numel()):
+            t1, t0 = ts[i - 1], ts[i]
+            theta = predict(theta, t1, t0)
+            if corrector is not None:
+                theta = correct(theta, t0, t1)
         return theta
     lib = L.load()
     theta = theta.contiguous()

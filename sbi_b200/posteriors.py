@@ -524,6 +524,11 @@ class VectorFieldPosterior:
         if sample_with not in ("ode", "sde"):
             raise ValueError(f"Expected sample_with to be 'ode' or 'sde', but got {sample_with}.")
         steps, ts, eta = kwargs.get("steps", 500), kwargs.get("ts"), (kwargs.get("predictor_params") or {}).get("eta", 1.0)
+        if kwargs.get("predictor", "euler_maruyama") != "euler_maruyama":
+            raise NotImplementedError("predictor: only 'euler_maruyama' (the reference's only predictor)")
+        if kwargs.get("iid_method") is not None or kwargs.get("guidance_method") is not None:
+            raise NotImplementedError("iid score composition / guidance are not implemented")
+        corrector, corrector_params = kwargs.get("corrector"), kwargs.get("corrector_params")
         x = x if x is not None else self.default_x
         if x is None:
             raise ValueError("Context `x` needed when a default has not been set.")
@@ -534,7 +539,8 @@ class VectorFieldPosterior:
         def proposal(shape, **kw):
             n = torch.Size(shape).numel()
             if sample_with == "sde":
-                s = sample_sde(est, n, x, steps=steps, ts=ts, eta=eta)
+                s = sample_sde(est, n, x, steps=steps, ts=ts, eta=eta, corrector=corrector,
+                               corrector_params=corrector_params)
                 self.num_function_evaluations += (steps if ts is None else ts.numel()) - 1
             else:
                 s, nfe = sample_ode(est, n, x, return_nfe=True)
