@@ -382,6 +382,12 @@ int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows, const floa
                          const float* d_eps, const float* d_gout, float g_const, float* d_loss,
                          float* d_gpart, float* d_loss_acc, void* stream);
 
+/* Introspection, no device work: the weight-pipeline plan (ring depth, chunk rows, shared memory) that a launch of
+ * kernel 0 (sbi_b200_fm_forward), 1 (sbi_b200_fm_loss_vjp / sbi_b200_fm_net_vjp) or 2 (sbi_b200_fm_forward_div)
+ * uses for this model: out10 = [nbuf, wcap, rpc_i, rpc_c, rpc_m, rpc_t, rpc_h, rpc_o, dynamic smem bytes, output
+ * rows per thread].  The launches re-chunk the caller's plan to fill the 227 KB of shared memory. */
+int sbi_b200_fm_plan(const sbi_fm_model* m, int32_t kernel, int32_t* out10);
+
 /* Parameter gradient of the bare network for a given upstream gradient d_dout (R, D) of its outputs (m->raw must
  * be 1): the backward of `ConditionalScoreEstimator.forward` (sbi/neural_nets/estimators/score_estimator.py:149-215)
  * through the VectorFieldMLP; everything around the network (time-dependent z-scoring, the Gaussian skip term, the

@@ -658,23 +658,59 @@ using namespace sbi;
 
 static int fm_num_sms() { return sbi::dev_num_sms(); }
 
-// The weight ring the caller asked for (nbuf stages of wcap floats) is a lower bound: the launch deepens it to what
-// the 227 KB of shared memory leave after the activation tile (3 stages in training at H = 100, 8 in evaluation).
-// ncu attributes ~25 % of fm_vjp's stall samples to the ring's `full` barrier (profiles/r02_fm_vjp.md), but the
-// deeper ring only moved cfg4 from 9.80 to 9.99 M samples/s: the wait is the chunk turn-around of one producer
-// thread at 16-row tiles, not the ring depth.
+// Launch-side tuning of the weight pipeline (the kernels read nbuf / wcap / rpc_* from the model struct, the
+// packed weights do not depend on them).  Measured on cfg4 (FMPE dim 20, batch 16384, trainer level, M samples/s;
+// profiles/r02_bench_cfg4*.json):
+//  * SBI_RING_AUTO >= 1: the ring the caller asked for is a lower bound; deepen it to what the 227 KB of shared
+//    memory leave after the activation tile.  ncu attributes ~25 % of fm_vjp's stall samples to the ring's `full`
+//    barrier (profiles/r02_fm_vjp.md), but depth alone only moved 9.80 -> 9.99.
+//  * SBI_RING_AUTO >= 2: re-chunk per kernel.  A forward chunk of `cnt` weight rows occupies cnt / RN of the
+//    256 / (TM / 4) output-thread groups, so the caller's 32-row chunks of a 100-wide layer kept 25 % (16-row
+//    tiles) to 50 % (32-row tiles) of the consumer threads busy, the 16-row chunks of the merge layer half of
+//    that.  Two stages of the largest chunk that fits (60 rows in training, whole layers in evaluation) with
+//    RN = SBI_FM_RN = 1 output row per thread fill them: 9.99 -> 12.5.  (RN = 1 with the 32-row chunks is SLOWER,
+//    7.67: five shared-memory wavefronts per 16 FMAs without the extra parallelism.)
 #ifndef SBI_RING_AUTO
-#define SBI_RING_AUTO 1
+#define SBI_RING_AUTO 2
 #endif
-static sbi_fm_model fm_deepen_ring(const sbi_fm_model& m, int TM, int mode) {
+#ifndef SBI_FM_RN
+#define SBI_FM_RN 1
+#endif
+static sbi_fm_model fm_tune(const sbi_fm_model& m, int TM, int mode) {
   sbi_fm_model c = m;
-#if SBI_RING_AUTO
   constexpr int kBudget = 227 * 1024 - 1024;      // static shared memory of the kernels stays below 1 KB
-  for (int nb = 8; nb > m.nbuf; --nb) {
+#if SBI_RING_AUTO >= 2
+  {
+    sbi_fm_model z = m;
+    z.nbuf = 0;
+    z.wcap = 0;
+    const int act = fm_smem_layout(z, TM, mode).total_bytes;          // activation tile
+    int cap = (kBudget - act - 2 * 8 * 8) / 4 / 2;                    // floats per stage with two stages
+    cap = std::min(cap, 2 * m.Hp * m.Hp);                             // the merge layer is the largest matrix
+    cap &= ~31;
+    if (cap >= 4 * 2 * m.Hp) {
+      auto rows = [&](int rowlen, int nmax) { return std::max(4, std::min(nmax, (cap / rowlen) & ~3)); };
+      c.rpc_i = rows(m.Dp, m.Hp);
+      c.rpc_c = rows(m.Cp, m.Hp);
+      c.rpc_m = rows(2 * m.Hp, m.Hp);
+      c.rpc_t = rows(m.TEp, m.Hp);
+      c.rpc_h = rows(m.Hp, m.Hp);
+      c.rpc_o = rows(m.Hp, m.Dp);
+      const int used = std::max({c.rpc_i * m.Dp, c.rpc_c * m.Cp, c.rpc_m * 2 * m.Hp, c.rpc_t * m.TEp,
+                                 c.rpc_h * m.Hp, c.rpc_o * m.Hp});
+      c.wcap = (used + 31) & ~31;
+      c.nbuf = 2;
+      if (fm_smem_layout(c, TM, mode).total_bytes > kBudget) c = m;   // (cannot happen; keep the caller's plan)
+    }
+  }
+#endif
+#if SBI_RING_AUTO >= 1
+  const int nb0 = c.nbuf;
+  for (int nb = 8; nb > nb0; --nb) {
     c.nbuf = nb;
     if (fm_smem_layout(c, TM, mode).total_bytes <= kBudget) return c;
   }
-  c.nbuf = m.nbuf;
+  c.nbuf = nb0;
 #endif
   return c;
 }
@@ -711,9 +747,9 @@ extern "C" int sbi_b200_fm_forward(const sbi_fm_model* m, const sbi_rows* rows, 
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_time || !d_v) return SBI_EINVAL;
   if (rows->R == 0) return 0;
   constexpr int TM = 32;
-  const sbi_fm_model md = fm_deepen_ring(*m, TM, kFmEval);
+  const sbi_fm_model md = fm_tune(*m, TM, kFmEval);
   const FmSmem L = fm_smem_layout(md, TM, kFmEval);
-  auto k = fm_forward_kernel<TM, 2>;
+  auto k = fm_forward_kernel<TM, SBI_FM_RN>;
   if ((rc = fm_set_smem<0>(k, L.total_bytes))) return rc;
   const int64_t ntiles = (rows->R + TM - 1) / TM;
   const int grid = (int)std::min<int64_t>(ntiles, fm_num_sms());
@@ -729,14 +765,28 @@ extern "C" int sbi_b200_fm_forward_div(const sbi_fm_model* m, const sbi_rows* ro
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 0 || !d_time || !d_div) return SBI_EINVAL;
   if (rows->R == 0) return 0;
   constexpr int TM = 16;
-  const sbi_fm_model md = fm_deepen_ring(*m, TM, kFmTrace);
+  const sbi_fm_model md = fm_tune(*m, TM, kFmTrace);
   const FmSmem L = fm_smem_layout(md, TM, kFmTrace);
-  auto k = fm_trace_kernel<TM, 2>;
+  auto k = fm_trace_kernel<TM, SBI_FM_RN>;
   if ((rc = fm_set_smem<2>(k, L.total_bytes))) return rc;
   const int64_t ntiles = (rows->R + TM - 1) / TM;
   const int grid = (int)std::min<int64_t>(ntiles, fm_num_sms());
   k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(md, *rows, d_time, time_shared, d_v, d_div);
   return (int)cudaGetLastError();
+}
+
+extern "C" int sbi_b200_fm_plan(const sbi_fm_model* m, int32_t kernel, int32_t* out10) {
+  // introspection (no device work): the weight-pipeline plan a launch of `kernel` (0 forward, 1 loss / parameter
+  // gradient, 2 forward + divergence) would use: [nbuf, wcap, rpc_i, rpc_c, rpc_m, rpc_t, rpc_h, rpc_o,
+  // dynamic shared memory bytes, output rows per thread]
+  if (!m || !out10 || kernel < 0 || kernel > 2) return SBI_EINVAL;
+  const int TM = kernel == 0 ? 32 : 16;
+  const int mode = kernel == 0 ? kFmEval : (kernel == 1 ? kFmTrain : kFmTrace);
+  const sbi_fm_model c = fm_tune(*m, TM, mode);
+  const int v[10] = {c.nbuf, c.wcap, c.rpc_i, c.rpc_c, c.rpc_m, c.rpc_t, c.rpc_h, c.rpc_o,
+                     fm_smem_layout(c, TM, mode).total_bytes, SBI_FM_RN};
+  for (int i = 0; i < 10; ++i) out10[i] = v[i];
+  return 0;
 }
 
 extern "C" int sbi_b200_fm_vjp_parts(int64_t R) {
@@ -752,9 +802,9 @@ extern "C" int sbi_b200_fm_loss_vjp(const sbi_fm_model* m, const sbi_rows* rows,
   if (rc) return rc;
   if (!rows || !rows->d_input || !rows->d_cond || rows->R < 1 || !d_time || !d_eps || !d_gpart) return SBI_EINVAL;
   constexpr int TM = 16;
-  const sbi_fm_model md = fm_deepen_ring(*m, TM, kFmTrain);
+  const sbi_fm_model md = fm_tune(*m, TM, kFmTrain);
   const FmSmem L = fm_smem_layout(md, TM, kFmTrain);
-  auto k = fm_vjp_kernel<TM, 2, 2>;
+  auto k = fm_vjp_kernel<TM, SBI_FM_RN, 2>;
   if ((rc = fm_set_smem<1>(k, L.total_bytes))) return rc;
   const int grid = sbi_b200_fm_vjp_parts(rows->R);
   k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(md, *rows, d_time, d_eps, d_gout, g_const, d_loss,
@@ -770,9 +820,9 @@ extern "C" int sbi_b200_fm_net_vjp(const sbi_fm_model* m, const sbi_rows* rows, 
   if (!m->raw || !rows || !rows->d_input || !rows->d_cond || rows->R < 1 || !d_time || !d_dout || !d_gpart)
     return SBI_EINVAL;
   constexpr int TM = 16;
-  const sbi_fm_model md = fm_deepen_ring(*m, TM, kFmTrain);
+  const sbi_fm_model md = fm_tune(*m, TM, kFmTrain);
   const FmSmem L = fm_smem_layout(md, TM, kFmTrain);
-  auto k = fm_vjp_kernel<TM, 2, 2>;
+  auto k = fm_vjp_kernel<TM, SBI_FM_RN, 2>;
   if ((rc = fm_set_smem<1>(k, L.total_bytes))) return rc;
   const int grid = sbi_b200_fm_vjp_parts(rows->R);
   k<<<grid, kThreads, L.total_bytes, (cudaStream_t)stream>>>(md, *rows, d_time, nullptr, nullptr, 0.f, nullptr, d_gpart,
