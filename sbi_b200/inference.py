@@ -982,6 +982,7 @@ class FMPE(_FlowTrainer):
               validation_times_nugget: float = 0.05, resume_training: bool = False, **kwargs):
         if self._theta is None:
             raise RuntimeError("call append_simulations() first")
+        self._vf_check_rounds(kwargs)
         lib = L.load()
         dev = self._device
         N = self._theta.shape[0]
@@ -1122,6 +1123,13 @@ class FMPE(_FlowTrainer):
                 raise RuntimeError("peer-memory gradient exchange timed out (a rank fell behind or died)")
         return deepcopy(net)
 
+    def _vf_check_rounds(self, kwargs):
+        """base_vf_inference.py:451-496: only the first-round loss exists for vector-field trainers."""
+        rounds = getattr(self, "_data_round_index", None) or [0]
+        if max(rounds) > 0 and not kwargs.get("force_first_round_loss", False):
+            raise NotImplementedError(
+                f"Multi-round {self.__class__.__name__} with arbitrary proposals is not implemented")
+
     def _vf_converged(self, net, stop_after_epochs: int) -> bool:
         """base_vf_inference.py:352-420: an epoch counts as "no improvement" only if the validation loss sits more
         than two standard deviations (of the recent EMA-smoothed losses) above the best one."""
@@ -1207,6 +1215,7 @@ class NPSE(FMPE):
               validation_times_nugget: float = 0.05, resume_training: bool = False, **kwargs):
         if self._theta is None:
             raise RuntimeError("call append_simulations() first")
+        self._vf_check_rounds(kwargs)
         if self._dp()[1] > 1:
             raise NotImplementedError("NPSE training is single-process")
         lib = L.load()

@@ -141,3 +141,17 @@ def test_within_support_matches_reference_semantics():
     prior = Independent(Uniform(-torch.ones(2), torch.ones(2), validate_args=False), 1)
     th = torch.tensor([[0.0, 0.5], [1.5, 0.0], [-0.2, -1.2]])
     assert within_support(prior, th).tolist() == [True, False, False]
+
+
+def test_vector_field_trainers_refuse_later_rounds_like_the_reference():
+    """base_vf_inference.py:451-496: FMPE / NPSE have the first-round loss only."""
+    from sbi_b200.inference import FMPE, NPSE
+    for cls in (FMPE, NPSE):
+        t = object.__new__(cls)
+        t._vf_check_rounds({})                                   # nothing appended yet
+        t._data_round_index = [0, 0]
+        t._vf_check_rounds({})
+        t._data_round_index = [0, 1]
+        with pytest.raises(NotImplementedError, match=f"Multi-round {cls.__name__}"):
+            t._vf_check_rounds({})
+        t._vf_check_rounds({"force_first_round_loss": True})
