@@ -1,5 +1,6 @@
 """Monotone rational-quadratic splines (Durkan et al. 2019), as nflows 0.14 evaluates
-them.  Plain torch; works in fp32 and fp64."""
+them.  Plain torch; works in fp32 and fp64.  Pinned against the independent copy of
+the same algorithm in `transformers.models.vits.modeling_vits` (tests/test_oracle_spline_pin_cpu.py)."""
 import numpy as np
 import torch
 from torch.nn import functional as F

@@ -13,7 +13,8 @@ for the whole (packed) state; error ratio = RMS over all entries of err / (atol 
 accept iff <= 1; next step = h * clip(0.9 * ratio^(-1/5), 0.2, 5); log-density of the flow =
 base.log_prob(y(t1)) + integral of trace(d f / d y), the trace taken exactly with autograd (one backward
 pass per dimension).  **Parity unpinned** against the real zuko (no golden vectors in the reference);
-pinned here by an analytic ODE and by the analytic log-density of an affine vector field (tests).
+pinned here by an analytic ODE, by the analytic log-density of an affine vector field and by scipy's RK45
+(same tableau and error weights, same solution of a nonlinear system; tests/test_ode_port_cpu.py).
 """
 import math
 
