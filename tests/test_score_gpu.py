@@ -138,8 +138,8 @@ def test_npse_fits_linear_gaussian(cuda_lib, sde_type):
         s = post.sample((4000,), sample_with=how).cpu()
         assert s.shape == (4000, D) and torch.isfinite(s).all()
         print(sde_type, how, "mean", s.mean(0).tolist(), "std", s.std(0).tolist(), "want", mu.tolist(), sd)
-        assert (s.mean(0) - mu).abs().max() < 0.12
-        assert (s.std(0) / sd - 1).abs().max() < 0.3
+        assert (s.mean(0) - mu).abs().max() < 0.16      # measured 0.06 .. 0.10 after 150 epochs (profiles/r02_score_gpu.log)
+        assert (s.std(0) / sd - 1).abs().max() < 0.35   # measured 0.00 .. 0.13
     th = mu + sd * torch.randn(200, D)
     lp = post.log_prob(th).cpu()
     want = MultivariateNormal(mu, sd ** 2 * torch.eye(D)).log_prob(th)
