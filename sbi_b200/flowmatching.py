@@ -580,31 +580,55 @@ def log_prob_ode(est: FlowMatchingEstimator, theta: Tensor, condition: Tensor, a
 @torch.no_grad()
 def sample_sde(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, steps: int = 500,
                ts: Optional[Tensor] = None, eta: float = 1.0, fused: bool = True, corrector: Optional[str] = None,
-               corrector_params: Optional[dict] = None) -> Tensor:
+               corrector_params: Optional[dict] = None, iid_method: Optional[str] = None, prior=None,
+               iid_params: Optional[dict] = None) -> Tensor:
     """Draw theta ~ q(theta | x) with the reverse SDE, Euler-Maruyama predictor, no corrector
     (Diffuser.run, samplers/score/diffuser.py:124-180; EulerMaruyama.predict,
     samplers/score/predictors.py:112-120; driver VectorFieldPosterior._sample_via_diffusion,
     vector_field_posterior.py:331-433).  A step is [velocity kernel -> normal draw -> fused update kernel]
     (csrc/ode.cu `sde_em_step_kernel`), captured once as a CUDA graph and replayed for every grid point;
-    `fused=False` keeps the step arithmetic in torch ops in the reference's order (for comparison)."""
+    `fused=False` keeps the step arithmetic in torch ops in the reference's order (for comparison).
+    `corrector` in {None, "langevin", "gibbs"} (samplers/score/correctors.py) and several iid observations
+    (`condition` of N rows, `iid_method="fnpe"`, inference/potentials/vector_field_adaptor.py:725-813) take the
+    generic path: the same torch arithmetic as the reference around the network kernel."""
     assert eta > 0, "eta must be positive."
     dev = est.net.flat.device
-    cond = condition.reshape(1, *est.condition_shape).to(dev).float().reshape(1, -1).contiguous()
+    cond = condition.to(dev).float().reshape(-1, est.layout.C).contiguous()
+    n_iid = cond.shape[0]
+    if n_iid > 1 and iid_method != "fnpe":
+        raise NotImplementedError(f"{n_iid} iid observations need iid_method='fnpe' (the factorised score, "
+                                  "vector_field_adaptor.py:725-813); 'gauss' / 'auto_gauss' / 'jac_gauss' are not built")
+    if n_iid > 1 and prior is None:
+        raise AssertionError("Prior is required for iid methods.")
     ts = est.solve_schedule(steps) if ts is None else ts
     ts = ts.to(dev).float().contiguous()
     D = est.layout.D
-    theta = est._mean_base.to(dev).reshape(1, D) + est._std_base.to(dev).reshape(1, D) * torch.randn(
-        num_samples, D, device=dev)
+    std0 = est._std_base.to(dev).reshape(1, D)
+    if iid_method == "fnpe":        # Diffuser.initialize (diffuser.py:104-121) narrows the base for this method
+        std0 = math.sqrt(1 / n_iid) * std0
+    theta = est._mean_base.to(dev).reshape(1, D) + std0 * torch.randn(num_samples, D, device=dev)
+    score_of = lambda th, t: est.score(th, cond, t)
+    if n_iid > 1:
+        w_fn = (iid_params or {}).get("prior_score_weight") or (lambda t: (est.t_max - t) / est.t_max)
+
+        def score_of(th, t):
+            """FactorizedNPEScoreFunction.__call__: sum of the per-observation scores + (1 - N) w(t) grad log prior."""
+            with torch.enable_grad():          # compute_score (vector_field_adaptor.py:1329-1354)
+                q = th.detach().clone().requires_grad_(True)
+                lp = prior.log_prob(q)
+                prior_score = torch.autograd.grad(lp, q, grad_outputs=torch.ones_like(lp))[0].detach()
+            base = est.score(th[:, None, :], cond, t)                     # (n, N, D): one network launch of n N rows
+            return (1 - n_iid) * (w_fn(t) * prior_score) + base.sum(-2)
     if corrector not in (None, "langevin", "gibbs"):
         raise NotImplementedError(f"corrector {corrector!r}: one of None, 'langevin', 'gibbs'")
     cp = dict(corrector_params or {})
-    if not fused or corrector is not None or getattr(est, "IS_SCORE", False):
+    if not fused or corrector is not None or n_iid > 1 or getattr(est, "IS_SCORE", False):
         # generic path: the estimator's own score / drift / diffusion around the network kernel
         def predict(theta, t1, t0):            # EulerMaruyama.predict (predictors.py:112-120)
             dt = t1 - t0
             f = est.drift_fn(theta, t1)
             g = est.diffusion_fn(theta, t1)
-            score = est.score(theta, cond, t1)
+            score = score_of(theta, t1)
             f_backward = f - (1 + eta ** 2) / 2 * g ** 2 * score
             return theta - f_backward * dt + (eta * g) * torch.randn_like(theta) * torch.sqrt(dt)
 
@@ -613,7 +637,7 @@ def sample_sde(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, 
                 step = cp.get("step_size", 1e-4)
                 std = math.sqrt(2 * step)
                 for _ in range(cp.get("num_steps", 5)):
-                    score = est.score(theta, cond, t1)
+                    score = score_of(theta, t1)
                     theta = theta + step * score + std * torch.randn_like(theta)
                 return theta
             for _ in range(cp.get("num_steps", 5)):   # GibbsCorrector (correctors.py:135-166): re-noise, predict back

@@ -526,8 +526,9 @@ class VectorFieldPosterior:
         steps, ts, eta = kwargs.get("steps", 500), kwargs.get("ts"), (kwargs.get("predictor_params") or {}).get("eta", 1.0)
         if kwargs.get("predictor", "euler_maruyama") != "euler_maruyama":
             raise NotImplementedError("predictor: only 'euler_maruyama' (the reference's only predictor)")
-        if kwargs.get("iid_method") is not None or kwargs.get("guidance_method") is not None:
-            raise NotImplementedError("iid score composition / guidance are not implemented")
+        if kwargs.get("guidance_method") is not None:
+            raise NotImplementedError("guided sampling is not implemented")
+        iid_method, iid_params = kwargs.get("iid_method"), kwargs.get("iid_params")
         corrector, corrector_params = kwargs.get("corrector"), kwargs.get("corrector_params")
         x = x if x is not None else self.default_x
         if x is None:
@@ -535,12 +536,15 @@ class VectorFieldPosterior:
         x = torch.as_tensor(x, dtype=torch.float32).to(self._device)
         num_samples = torch.Size(sample_shape).numel()
         est = self.vector_field_estimator
+        if x.numel() > int(torch.Size(est.condition_shape).numel()) and sample_with == "ode":
+            raise NotImplementedError("iid observations are sampled with sample_with='sde' and iid_method='fnpe'")
 
         def proposal(shape, **kw):
             n = torch.Size(shape).numel()
             if sample_with == "sde":
                 s = sample_sde(est, n, x, steps=steps, ts=ts, eta=eta, corrector=corrector,
-                               corrector_params=corrector_params)
+                               corrector_params=corrector_params, iid_method=iid_method, prior=self.prior,
+                               iid_params=iid_params)
                 self.num_function_evaluations += (steps if ts is None else ts.numel()) - 1
             else:
                 s, nfe = sample_ode(est, n, x, return_nfe=True)

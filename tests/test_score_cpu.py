@@ -182,3 +182,33 @@ def test_sde_sampler_with_correctors_equals_reference_diffuser(ref, sde_type, co
     torch.manual_seed(7)
     got = sample_sde(b, 50, x_o, ts=ts, corrector=corrector, corrector_params=cp)
     assert torch.allclose(got, want.reshape(50, D), rtol=1e-5, atol=1e-5), (got - want.reshape(50, D)).abs().max()
+
+
+@pytest.mark.parametrize("sde_type,corrector", [("vp", None), ("ve", "langevin")])
+def test_factorised_iid_score_sampler_equals_reference(ref, sde_type, corrector, monkeypatch):
+    """Several iid observations, iid_method='fnpe' (vector_field_adaptor.py:725-813; narrowed base of
+    diffuser.py:104-121): same samples as the reference's Diffuser on the reference estimator."""
+    from sbi.inference.potentials.vector_field_potential import vector_field_estimator_based_potential
+    from sbi.samplers.score.diffuser import Diffuser
+    from torch.distributions import MultivariateNormal
+    from sbi_b200.flowmatching import sample_sde
+    a, b, theta, x = _pair(sde_type)
+    with torch.no_grad():
+        a.net.output_layer.weight.normal_(0, 0.3)
+    prior = MultivariateNormal(torch.zeros(D), 2.0 * torch.eye(D))
+    x_o = x[:5]
+    monkeypatch.setattr("sbi.inference.potentials.vector_field_potential.build_neural_ode",
+                        lambda *aa, **kk: (lambda *u, **v: None))
+    pot, _ = vector_field_estimator_based_potential(a, prior, None)
+    pot.set_x(x_o, x_is_iid=True, iid_method="fnpe")
+    ts = a.solve_schedule(10)
+    cp = dict(step_size=1e-3, num_steps=2) if corrector else None
+    torch.manual_seed(3)
+    want = Diffuser(pot, predictor="euler_maruyama", corrector=corrector, corrector_params=cp).run(
+        40, ts, show_progress_bars=False)
+    torch.manual_seed(3)
+    got = sample_sde(b, 40, x_o, ts=ts, corrector=corrector, corrector_params=cp, iid_method="fnpe", prior=prior)
+    assert got.shape == (40, D)
+    assert torch.allclose(got, want.reshape(40, D), rtol=1e-4, atol=1e-4), (got - want.reshape(40, D)).abs().max()
+    with pytest.raises(NotImplementedError):
+        sample_sde(b, 4, x_o, ts=ts, iid_method="auto_gauss", prior=prior)
