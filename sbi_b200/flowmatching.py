@@ -577,6 +577,21 @@ def log_prob_ode(est: FlowMatchingEstimator, theta: Tensor, condition: Tensor, a
     return (lp, nfe) if return_nfe else lp
 
 
+def factorised_iid_score(est, prior, theta: Tensor, cond: Tensor, t: Tensor, prior_score_weight=None) -> Tensor:
+    """Score of the posterior given N iid observations, factorised approximation (FactorizedNPEScoreFunction,
+    /root/reference/sbi/inference/potentials/vector_field_adaptor.py:725-813):
+        sum_i score(theta | x_i, t) + (1 - N) w(t) grad_theta log prior(theta),   w(t) = (t_max - t) / t_max.
+    theta (n, D), cond (N, C); the N per-observation scores of all n particles are ONE launch of n N rows."""
+    n_iid = cond.shape[0]
+    w = prior_score_weight(t) if prior_score_weight is not None else (est.t_max - t) / est.t_max
+    with torch.enable_grad():          # compute_score (vector_field_adaptor.py:1329-1354)
+        q = theta.detach().clone().requires_grad_(True)
+        lp = prior.log_prob(q)
+        prior_score = torch.autograd.grad(lp, q, grad_outputs=torch.ones_like(lp))[0].detach()
+    base = est.score(theta[:, None, :], cond, t)                       # (n, N, D)
+    return (1 - n_iid) * (w * prior_score) + base.sum(-2)
+
+
 @torch.no_grad()
 def sample_sde(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, steps: int = 500,
                ts: Optional[Tensor] = None, eta: float = 1.0, fused: bool = True, corrector: Optional[str] = None,
@@ -609,16 +624,8 @@ def sample_sde(est: FlowMatchingEstimator, num_samples: int, condition: Tensor, 
     theta = est._mean_base.to(dev).reshape(1, D) + std0 * torch.randn(num_samples, D, device=dev)
     score_of = lambda th, t: est.score(th, cond, t)
     if n_iid > 1:
-        w_fn = (iid_params or {}).get("prior_score_weight") or (lambda t: (est.t_max - t) / est.t_max)
-
-        def score_of(th, t):
-            """FactorizedNPEScoreFunction.__call__: sum of the per-observation scores + (1 - N) w(t) grad log prior."""
-            with torch.enable_grad():          # compute_score (vector_field_adaptor.py:1329-1354)
-                q = th.detach().clone().requires_grad_(True)
-                lp = prior.log_prob(q)
-                prior_score = torch.autograd.grad(lp, q, grad_outputs=torch.ones_like(lp))[0].detach()
-            base = est.score(th[:, None, :], cond, t)                     # (n, N, D): one network launch of n N rows
-            return (1 - n_iid) * (w_fn(t) * prior_score) + base.sum(-2)
+        w_fn = (iid_params or {}).get("prior_score_weight")
+        score_of = lambda th, t: factorised_iid_score(est, prior, th, cond, t, w_fn)
     if corrector not in (None, "langevin", "gibbs"):
         raise NotImplementedError(f"corrector {corrector!r}: one of None, 'langevin', 'gibbs'")
     cp = dict(corrector_params or {})
